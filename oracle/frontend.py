@@ -1,0 +1,209 @@
+"""Oracle (TEST INFRASTRUCTURE): CPU restatement of the two audio front-ends.
+
+VoiceEncoder front-end = librosa 0.11.0 calls made by the reference
+(``melspec.py:9-16`` filters.mel, ``melspec.py:54-64`` stft,
+``voice_encoder.py:267`` effects.trim).  librosa is a third-party dependency
+pinned at 0.11.0 in the reference's ``pyproject.toml:13`` and is absent from
+/root/reference and from this image, so its published algorithm is restated
+here (parity unpinned at that boundary, see ``oracle/__init__.py``).
+
+CAMPPlus front-end = ``torchaudio.compliance.kaldi.fbank(num_mel_bins=80)``
+followed by per-utterance mean subtraction (``xvector.py:45-58``).  torchaudio
+is installed, so ``kaldi_fbank_numpy`` is validated against it directly.
+"""
+from __future__ import annotations
+
+import math
+import types
+
+import numpy as np
+
+# ----------------------------------------------------------------------------
+# librosa.filters.mel  (Slaney scale, slaney area-norm)  -- melspec.py:11-16
+# ----------------------------------------------------------------------------
+_F_SP = 200.0 / 3
+_MIN_LOG_HZ = 1000.0
+_MIN_LOG_MEL = _MIN_LOG_HZ / _F_SP
+_LOGSTEP = math.log(6.4) / 27.0
+
+
+def hz_to_mel_slaney(f):
+    f = np.asarray(f, dtype=np.float64)
+    mel = f / _F_SP
+    big = f >= _MIN_LOG_HZ
+    return np.where(big, _MIN_LOG_MEL + np.log(np.maximum(f, 1e-30) / _MIN_LOG_HZ) / _LOGSTEP, mel)
+
+
+def mel_to_hz_slaney(m):
+    m = np.asarray(m, dtype=np.float64)
+    hz = m * _F_SP
+    big = m >= _MIN_LOG_MEL
+    return np.where(big, _MIN_LOG_HZ * np.exp(_LOGSTEP * (m - _MIN_LOG_MEL)), hz)
+
+
+def filters_mel(sr, n_fft, n_mels=128, fmin=0.0, fmax=None):
+    """librosa.filters.mel(htk=False, norm='slaney', dtype=float32)."""
+    if fmax is None:
+        fmax = sr / 2.0
+    n_bins = 1 + n_fft // 2
+    fft_hz = np.linspace(0.0, sr / 2.0, n_bins)
+    edges = mel_to_hz_slaney(np.linspace(hz_to_mel_slaney(fmin), hz_to_mel_slaney(fmax), n_mels + 2))
+    widths = np.diff(edges)
+    dist = edges[:, None] - fft_hz[None, :]
+    bank = np.zeros((n_mels, n_bins), dtype=np.float32)
+    for m in range(n_mels):
+        rising = -dist[m] / widths[m]
+        falling = dist[m + 2] / widths[m + 1]
+        bank[m] = np.maximum(0.0, np.minimum(rising, falling))
+    area = 2.0 / (edges[2:] - edges[:-2])
+    bank *= area[:, None]
+    return bank
+
+
+# ----------------------------------------------------------------------------
+# librosa.stft  -- melspec.py:57-64 (center=True, reflect, periodic hann)
+# ----------------------------------------------------------------------------
+def hann_periodic(n):
+    return 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n) / n)
+
+
+def stft(y, n_fft=2048, hop_length=None, win_length=None, center=True, pad_mode="constant"):
+    y = np.asarray(y)
+    win_length = n_fft if win_length is None else win_length
+    hop_length = win_length // 4 if hop_length is None else hop_length
+    win = hann_periodic(win_length)
+    if win_length < n_fft:
+        lp = (n_fft - win_length) // 2
+        win = np.pad(win, (lp, n_fft - win_length - lp))
+    if center:
+        y = np.pad(y, n_fft // 2, mode=pad_mode)
+    n_frames = 1 + (len(y) - n_fft) // hop_length
+    idx = np.arange(n_fft)[:, None] + hop_length * np.arange(n_frames)[None, :]
+    frames = y[idx].astype(np.float64) * win[:, None]
+    out = np.fft.rfft(frames, axis=0)
+    return out.astype(np.complex64 if y.dtype == np.float32 else np.complex128)
+
+
+# ----------------------------------------------------------------------------
+# librosa.effects.trim -- voice_encoder.py:267
+# ----------------------------------------------------------------------------
+def trim_bounds(y, top_db=60.0, frame_length=2048, hop_length=512):
+    """[start, end) sample range kept by librosa.effects.trim(y, top_db)."""
+    y = np.asarray(y)
+    n = len(y)
+    yp = np.pad(y, frame_length // 2, mode="constant")
+    n_frames = 1 + (len(yp) - frame_length) // hop_length
+    idx = np.arange(frame_length)[None, :] + hop_length * np.arange(n_frames)[:, None]
+    power = np.mean(np.abs(yp[idx]) ** 2, axis=1)
+    rms = np.sqrt(power)
+    amin = 1e-5
+    ref = rms.max() if n_frames else 0.0
+    db = 10.0 * np.log10(np.maximum(amin ** 2, rms.astype(np.float64) ** 2))
+    db -= 10.0 * np.log10(max(amin ** 2, float(ref) ** 2))
+    keep = np.flatnonzero(db > -top_db)
+    if keep.size == 0:
+        return 0, 0
+    return int(keep[0]) * hop_length, min(n, (int(keep[-1]) + 1) * hop_length)
+
+
+def effects_trim(y, top_db=60.0, frame_length=2048, hop_length=512):
+    s, e = trim_bounds(y, top_db, frame_length, hop_length)
+    return y[s:e], np.asarray([s, e])
+
+
+def _no_resample(*a, **k):  # voice_encoder.py:262 is dead code for 16 kHz input
+    raise NotImplementedError("oracle shim: librosa.resample (kaiser_fast) is out of scope")
+
+
+def make_librosa_shim():
+    """Module object standing in for ``import librosa`` when the verbatim
+    reference files are imported."""
+    mod = types.ModuleType("librosa")
+    mod.stft = stft
+    mod.resample = _no_resample
+    mod.filters = types.ModuleType("librosa.filters")
+    mod.filters.mel = filters_mel
+    mod.effects = types.ModuleType("librosa.effects")
+    mod.effects.trim = effects_trim
+    mod.__version__ = "0.11.0-oracle-shim"
+    return mod
+
+
+# ----------------------------------------------------------------------------
+# VoiceEncoder mel -- melspec.py:26-51 with hp of config.py:1-18
+# ----------------------------------------------------------------------------
+VE_SR, VE_NFFT, VE_HOP, VE_NMEL = 16000, 400, 160, 40
+_ve_basis = None
+
+
+def ve_mel_basis():
+    global _ve_basis
+    if _ve_basis is None:
+        _ve_basis = filters_mel(VE_SR, VE_NFFT, VE_NMEL, 0.0, 8000.0)
+    return _ve_basis
+
+
+def ve_melspectrogram(wav):
+    """(L,) float32 -> (T, 40) float32, T = 1 + L // 160.  Power mel, no log."""
+    spec = stft(np.asarray(wav, dtype=np.float32), VE_NFFT, VE_HOP, VE_NFFT, True, "reflect")
+    mag = np.abs(spec)
+    mag **= 2.0
+    mel = np.dot(ve_mel_basis(), mag)
+    return np.ascontiguousarray(mel.T.astype(np.float32))
+
+
+# ----------------------------------------------------------------------------
+# Kaldi fbank (torchaudio.compliance.kaldi.fbank defaults, 80 bins) + CMN
+# ----------------------------------------------------------------------------
+KALDI_EPS = float(np.finfo(np.float32).eps)
+
+
+def kaldi_mel_banks(num_bins=80, padded=512, sr=16000.0, low=20.0, high=0.0):
+    nyq = 0.5 * sr
+    if high <= 0:
+        high += nyq
+    mel = lambda f: 1127.0 * np.log(1.0 + np.asarray(f, dtype=np.float64) / 700.0)
+    lo, hi = mel(low), mel(high)
+    delta = (hi - lo) / (num_bins + 1)
+    b = np.arange(num_bins, dtype=np.float64)[:, None]
+    left, center, right = lo + b * delta, lo + (b + 1) * delta, lo + (b + 2) * delta
+    m = mel((sr / padded) * np.arange(padded // 2))[None, :]
+    up = (m - left) / (center - left)
+    down = (right - m) / (right - center)
+    bank = np.maximum(0.0, np.minimum(up, down))
+    return np.pad(bank, ((0, 0), (0, 1)))  # Nyquist bin gets weight 0
+
+
+def povey_window(n=400):
+    return (0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n) / (n - 1))) ** 0.85
+
+
+def kaldi_num_frames(n_samples, win=400, hop=160):
+    return 0 if n_samples < win else 1 + (n_samples - win) // hop
+
+
+def kaldi_fbank_numpy(wav, num_bins=80):
+    """float64 restatement of Kaldi.fbank(wav[None], num_mel_bins=80) -> (T_k, 80)."""
+    y = np.asarray(wav, dtype=np.float64)
+    tk = kaldi_num_frames(len(y))
+    assert tk > 0, "choose a window size 400 that is [2, len]"
+    fr = y[np.arange(400)[None, :] + 160 * np.arange(tk)[:, None]]
+    fr = fr - fr.mean(axis=1, keepdims=True)
+    prev = np.concatenate([fr[:, :1], fr[:, :-1]], axis=1)
+    fr = (fr - 0.97 * prev) * povey_window()[None, :]
+    fr = np.pad(fr, ((0, 0), (0, 112)))
+    pw = np.abs(np.fft.rfft(fr, axis=1)) ** 2
+    en = pw @ kaldi_mel_banks(num_bins).T
+    return np.log(np.maximum(en, KALDI_EPS)).astype(np.float32)
+
+
+def kaldi_fbank_torchaudio(wav, num_bins=80):
+    import torch
+    import torchaudio.compliance.kaldi as K
+    return K.fbank(torch.as_tensor(np.asarray(wav, dtype=np.float32))[None], num_mel_bins=num_bins).numpy()
+
+
+def campplus_features(wav, use_torchaudio=True):
+    """fbank minus its own column mean (xvector.py:50-51)."""
+    f = kaldi_fbank_torchaudio(wav) if use_torchaudio else kaldi_fbank_numpy(wav)
+    return (f - f.mean(axis=0, keepdims=True)).astype(np.float32)

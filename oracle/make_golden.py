@@ -1,0 +1,76 @@
+"""Oracle (TEST INFRASTRUCTURE): generate tests/golden/*.npz by running the
+VERBATIM reference modules from /root/reference (build container only).
+
+    python -m oracle.make_golden
+
+Inputs are synthetic (chatterbox_embed_b200.synth) and weights are the seeded
+sets of oracle/weights.py, loaded into the reference classes with
+``load_state_dict(strict=True)``; so the GPU box can regenerate the same inputs
+and weights and compare the CUDA path against what the reference itself produced.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from chatterbox_embed_b200 import synth
+from . import refload, weights
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# (clip index, samples, leading quiet samples, trailing quiet samples)
+CLIPS = [(0, 16000, 0, 0), (1, 48000, 0, 0), (2, 50000, 6000, 9000), (3, 160000, 0, 0), (4, 25599, 0, 0)]
+
+
+def golden_wavs():
+    return [synth.with_silence(i, n, a, b) if (a or b) else synth.clip(i, n) for i, n, a, b in CLIPS]
+
+
+def main():
+    assert refload.available(), "reference tree not found"
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    rve = refload.voice_encoder_module()
+    hp = rve.VoiceEncConfig()
+
+    # integer known answers from the reference's own get_num_wins / get_frame_step
+    n_frames = np.arange(1, 4001)
+    wins = np.array([rve.get_num_wins(int(n), 77, 0.8, hp) for n in n_frames], dtype=np.int64)
+    wins80 = np.array([rve.get_num_wins(int(n), 80, 0.8, hp) for n in n_frames], dtype=np.int64)
+    np.savez_compressed(os.path.join(OUT, "ints.npz"), n_frames=n_frames, wins77=wins, wins80=wins80,
+                        step_rate13=rve.get_frame_step(0.5, 1.3, hp), step_none=rve.get_frame_step(0.5, None, hp))
+
+    wavs = golden_wavs()
+    import librosa  # the oracle shim registered by refload
+    trims = np.array([librosa.effects.trim(w, top_db=20)[1] for w in wavs], dtype=np.int64)
+    for kind in ("W0", "W1"):
+        ve = refload.make_voice_encoder(weights.ve_state_dict(kind))
+        cp = refload.make_campplus(weights.campplus_state_dict(kind))
+        out = {"trim": trims}
+        out["ve_emb"] = ve.embeds_from_wavs(wavs, sample_rate=16000)
+        out["ve_emb_notrim"] = ve.embeds_from_wavs(wavs, sample_rate=16000, trim_top_db=None)
+        with torch.inference_mode():
+            out["xv_emb"] = np.concatenate([cp.inference(torch.from_numpy(w)[None]).numpy() for w in wavs])
+            # stage tensors for the 3 s clip (index 1)
+            mel = rve.melspectrogram(wavs[1], hp).T.astype(np.float32)
+            out["mel_1"] = mel
+            n_p, _ = rve.get_num_wins(len(mel), 77, 0.8, hp)
+            padded = np.concatenate([mel, np.zeros((400, 40), np.float32)])
+            parts = np.stack([padded[77 * p: 77 * p + 160] for p in range(n_p)])
+            out["partial_emb_1"] = ve(torch.from_numpy(parts)).numpy()
+            feat, _, _ = refload.xvector_module().extract_feature([torch.from_numpy(wavs[1])])
+            out["fbank_cmn_1"] = feat[0].numpy()
+            fcm = cp.head(feat.permute(0, 2, 1))
+            out["fcm_1"] = fcm[0, :, ::16].numpy()            # (320, T/16) subsample
+            td = cp.xvector.tdnn(fcm)
+            out["tdnn_1"] = td[0, :, ::8].numpy()
+            b1 = cp.xvector.block1(td)
+            out["block1_1"] = b1[0, :, ::16].numpy()
+        np.savez_compressed(os.path.join(OUT, f"ref_{kind}.npz"), **out)
+        print(kind, {k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()
