@@ -1,0 +1,401 @@
+// C ABI of libcbx.so (include/cbx.h): context, weight intake, ragged chunk planning, pipeline driver.
+#include <algorithm>
+#include <cstring>
+
+#include "cbx_internal.h"
+
+using namespace cbx;
+
+static std::string g_create_err;
+
+namespace {
+
+struct Batch {   // host-side description of one cbx_embed call
+  int n;
+  const int64_t* off;
+  int step; double min_cov;
+};
+
+// ---- VoiceEncoder chunk planning ------------------------------------------------------------------------
+struct VeLayout { std::vector<ClipPlan> plan; int mel_rows = 0, slots = 0, trim_blocks = 0; };
+
+VeLayout plan_ve(const Batch& b, int c0, int c1) {
+  VeLayout L;
+  for (int i = c0; i < c1; ++i) {
+    ClipPlan p{};
+    p.pcm_off = b.off[i];
+    p.n_samples = (int32_t)(b.off[i + 1] - b.off[i]);
+    p.out_index = i;
+    int64_t wins, target;
+    ve_num_wins(1 + p.n_samples / kVeHop, b.step, b.min_cov, &wins, &target);
+    p.mel_row = L.mel_rows; p.mel_rows = (int32_t)target;
+    p.slot0 = L.slots; p.slots = (int32_t)wins;
+    p.trim_blk0 = L.trim_blocks;
+    L.mel_rows += p.mel_rows; L.slots += p.slots;
+    L.trim_blocks += (p.n_samples + kTrimHop - 1) / kTrimHop + 1;
+    L.plan.push_back(p);
+  }
+  return L;
+}
+
+VeChunk carve_ve(Carver& cv, const VeLayout& L, cbx_ctx* c) {
+  VeChunk ch{};
+  ch.n_clips = (int)L.plan.size(); ch.mel_rows = L.mel_rows; ch.slots = L.slots; ch.trim_blocks = L.trim_blocks;
+  ch.plan = cv.take<ClipPlan>(ch.n_clips);
+  ch.dyn = cv.take<ClipDyn>(ch.n_clips);
+  ch.trim_scratch = cv.take<float>(L.trim_blocks);
+  ch.mel_row_clip = cv.take<int32_t>(L.mel_rows);
+  ch.slot_clip = cv.take<int32_t>(L.slots);
+  ch.slot_row = cv.take<int32_t>(L.slots);
+  ch.spec = cv.take<float>((int64_t)L.mel_rows * kVeSpecN);
+  ch.mel = cv.take<float>((int64_t)L.mel_rows * kVeMels);
+  ch.xw0 = cv.take<float>((int64_t)L.mel_rows * kVeGates);
+  ch.xw = cv.take<float>((int64_t)L.slots * kVePartial * kVeGates);
+  ch.hseq = cv.take<float>((int64_t)L.slots * kVePartial * kVeHidden);
+  ch.pemb = cv.take<float>((int64_t)L.slots * kVeEmbed);
+  if (cv.base && c) {
+    c->taps["ve_dyn"] = {(char*)ch.dyn - cv.base, ch.n_clips, 6, 6};
+    c->taps["ve_mel"] = {(char*)ch.mel - cv.base, L.mel_rows, kVeMels, kVeMels};
+    c->taps["ve_partial_emb"] = {(char*)ch.pemb - cv.base, L.slots, kVeEmbed, kVeEmbed};
+  }
+  return ch;
+}
+
+// ---- CAMPPlus chunk planning ----------------------------------------------------------------------------
+struct XvLayout { std::vector<ClipPlan> plan; int fb_rows = 0, td_rows = 0, segs = 0, fcm_rows = 0; };
+
+XvLayout plan_xv(const Batch& b, int c0, int c1, int64_t fcm_chunk_rows) {
+  XvLayout L;
+  int td = kGuardTd, seg = 0, longest = 0;
+  for (int i = c0; i < c1; ++i) {
+    ClipPlan p{};
+    p.pcm_off = b.off[i];
+    p.n_samples = (int32_t)(b.off[i + 1] - b.off[i]);
+    p.out_index = i;
+    cbx_clip_plan cp;
+    cbx_plan_clip(p.n_samples, b.step, b.min_cov, &cp);
+    p.xv_frames = (int32_t)cp.xv_frames; p.xv_tdnn = (int32_t)cp.xv_tdnn; p.xv_segs = (int32_t)cp.xv_segments;
+    p.td_row = td; p.fb_row = 2 * td; p.seg0 = seg;
+    td += p.xv_tdnn + kGuardTd; seg += p.xv_segs;
+    longest = std::max(longest, 2 * (p.xv_tdnn + 2 * kGuardTd));
+    L.plan.push_back(p);
+  }
+  L.td_rows = td; L.fb_rows = 2 * td; L.segs = seg;
+  L.fcm_rows = (int)std::min<int64_t>(std::max<int64_t>(fcm_chunk_rows, longest), L.fb_rows);
+  return L;
+}
+
+XvChunk carve_xv(Carver& cv, const XvLayout& L, cbx_ctx* c) {
+  XvChunk ch{};
+  ch.n_clips = (int)L.plan.size(); ch.fb_rows = L.fb_rows; ch.td_rows = L.td_rows; ch.segs = L.segs; ch.fcm_rows = L.fcm_rows;
+  ch.plan = cv.take<ClipPlan>(ch.n_clips);
+  ch.fb_row_clip = cv.take<int32_t>(L.fb_rows);
+  ch.td_row_clip = cv.take<int32_t>(L.td_rows);
+  ch.td_row_seg = cv.take<int32_t>(L.td_rows);
+  ch.seg_clip = cv.take<int32_t>(std::max(L.segs, 1));
+  ch.spec = cv.take<float>((int64_t)L.fcm_rows * kKSpecN);
+  ch.fbank = cv.take<float>((int64_t)L.fb_rows * kKMels);
+  ch.cmn_sum = cv.take<float>((int64_t)ch.n_clips * kKMels);
+  const int64_t pr = L.fcm_rows + 2;     // one pad row in front and one behind
+  ch.b0 = cv.take<float>(pr * 80 * kFcmC);
+  ch.b1 = cv.take<float>(pr * 40 * kFcmC);
+  ch.b2 = cv.take<float>(pr * 40 * kFcmC);
+  ch.b4 = cv.take<float>(pr * 20 * kFcmC);
+  ch.b5 = cv.take<float>(pr * 20 * kFcmC);
+  ch.fcm_out = cv.take<float>((int64_t)L.fb_rows * kFcmOut);
+  ch.cat1 = cv.take<float>((int64_t)L.td_rows * 512);
+  ch.cat2 = cv.take<float>((int64_t)L.td_rows * 1024);
+  ch.cat3 = cv.take<float>((int64_t)L.td_rows * 1024);
+  ch.u = cv.take<float>((int64_t)L.td_rows * kBnC);
+  ch.tr3 = cv.take<float>((int64_t)L.td_rows * kStatsC);
+  ch.seg_sum = cv.take<float>((int64_t)std::max(L.segs, 1) * kBnC);
+  ch.gate = cv.take<float>((int64_t)std::max(L.segs, 1) * kGrowth);
+  ch.stats = cv.take<float>((int64_t)ch.n_clips * 2 * kStatsC);
+  if (cv.base && c) {
+    auto tap = [&](const char* name, float* p, int64_t rows, int64_t cols, int64_t ld) {
+      c->taps[name] = {(char*)p - cv.base, rows, cols, ld};
+    };
+    tap("xv_fbank", ch.fbank, L.fb_rows, kKMels, kKMels);
+    tap("xv_cmn_mean", ch.cmn_sum, ch.n_clips, kKMels, kKMels);
+    tap("xv_fcm", ch.fcm_out, L.fb_rows, kFcmOut, kFcmOut);
+    tap("xv_cat1", ch.cat1, L.td_rows, 512, 512);
+    tap("xv_cat2", ch.cat2, L.td_rows, 1024, 1024);
+    tap("xv_cat3", ch.cat3, L.td_rows, 1024, 1024);
+    tap("xv_tr3", ch.tr3, L.td_rows, kStatsC, kStatsC);
+    tap("xv_stats", ch.stats, ch.n_clips, 2 * kStatsC, 2 * kStatsC);
+  }
+  return ch;
+}
+
+// greedy split of [0,n) into consecutive chunks under a budget
+template <class Cost>
+std::vector<std::pair<int, int>> split_chunks(int n, int64_t budget, Cost cost) {
+  std::vector<std::pair<int, int>> out;
+  int i = 0;
+  while (i < n) {
+    int j = i; int64_t acc = 0;
+    while (j < n) {
+      const int64_t cj = cost(j);
+      if (j > i && acc + cj > budget) break;
+      acc += cj; ++j;
+    }
+    out.push_back({i, j});
+    i = j;
+  }
+  return out;
+}
+
+struct ChunkSets { std::vector<std::pair<int, int>> ve, xv; };
+
+ChunkSets make_chunks(cbx_ctx* c, const Batch& b, int flags) {
+  ChunkSets s;
+  if (flags & CBX_DO_VE)
+    s.ve = split_chunks(b.n, c->lstm_chunk_slots, [&](int i) {
+      int64_t wins, target;
+      ve_num_wins(1 + (b.off[i + 1] - b.off[i]) / kVeHop, b.step, b.min_cov, &wins, &target);
+      return wins;
+    });
+  if (flags & CBX_DO_XV)
+    s.xv = split_chunks(b.n, c->xv_chunk_rows, [&](int i) {
+      cbx_clip_plan cp;
+      cbx_plan_clip(b.off[i + 1] - b.off[i], b.step, b.min_cov, &cp);
+      return 2 * (cp.xv_tdnn + kGuardTd);
+    });
+  return s;
+}
+
+int64_t workspace_bytes_for(cbx_ctx* c, const Batch& b, int flags) {
+  ChunkSets s = make_chunks(c, b, flags);
+  int64_t ve_max = 0, xv_max = 0;
+  for (auto& r : s.ve) { Carver cv(nullptr, 0); carve_ve(cv, plan_ve(b, r.first, r.second), nullptr); ve_max = std::max(ve_max, cv.off); }
+  for (auto& r : s.xv) { Carver cv(nullptr, 0); carve_xv(cv, plan_xv(b, r.first, r.second, c->fcm_chunk_rows), nullptr); xv_max = std::max(xv_max, cv.off); }
+  return ((ve_max + 255) & ~int64_t(255)) + ((xv_max + 255) & ~int64_t(255)) + 1024;
+}
+
+int check_inputs(cbx_ctx* c, const int64_t* off, int n, int step, int flags) {
+  if (!c) return CBX_ERR_ARG;
+  if (n <= 0 || !off) { c->err = "n_clips must be > 0 and offsets non-null"; return CBX_ERR_ARG; }
+  if (step <= 0 || step > kVePartial) { c->err = "ve_step out of range (voice_encoder.py:80)"; return CBX_ERR_ARG; }
+  for (int i = 0; i < n; ++i)
+    if (off[i + 1] < off[i] || off[i + 1] - off[i] > (int64_t)1 << 30) { c->err = "offsets must be non-decreasing"; return CBX_ERR_ARG; }
+  if ((flags & CBX_DO_VE) && !c->ve.loaded) { c->err = "VoiceEncoder weights not loaded"; return CBX_ERR_STATE; }
+  if ((flags & CBX_DO_XV) && !c->xv.loaded) { c->err = "CAMPPlus weights not loaded"; return CBX_ERR_STATE; }
+  return CBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cbx_create(int device, cbx_ctx** out) {
+  if (!out) return CBX_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) { g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e); return CBX_ERR_CUDA; }
+  if (device < 0 || device >= ndev) { g_create_err = "device index out of range"; return CBX_ERR_ARG; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) { g_create_err = "libcbx is built for sm_100a only; found sm_" + std::to_string(prop.major * 10 + prop.minor); return CBX_ERR_CUDA; }
+  cudaSetDevice(device);
+  cbx_ctx* c = new cbx_ctx();
+  c->device = device;
+  int rc = build_frontend_tables(c);
+  if (rc) { g_create_err = c->err; delete c; return rc; }
+  cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  *out = c;
+  return CBX_OK;
+}
+
+void cbx_destroy(cbx_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->ve.blob); cudaFree(c->xv.blob); cudaFree(c->ft.blob);
+  cudaFree(c->own_ws); cudaFree(c->own_pcm); cudaFree(c->own_out);
+  if (c->pin_pcm) cudaFreeHost(c->pin_pcm);
+  if (c->pin_out) cudaFreeHost(c->pin_out);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+const char* cbx_last_error(const cbx_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int cbx_set_option(cbx_ctx* c, const char* key, int64_t v) {
+  if (!c || !key) return CBX_ERR_ARG;
+  std::string k(key);
+  if (k == "xv_chunk_rows" && v >= 64) c->xv_chunk_rows = v;
+  else if (k == "fcm_chunk_rows" && v >= 64) c->fcm_chunk_rows = v;
+  else if (k == "lstm_chunk_partials" && v >= 1) c->lstm_chunk_slots = v;
+  else if (k == "mode" && (v == 0 || v == 1)) c->mode = v;
+  else { c->err = "bad option " + k; return CBX_ERR_ARG; }
+  return CBX_OK;
+}
+
+int64_t cbx_get_option(const cbx_ctx* c, const char* key) {
+  if (!c || !key) return -1;
+  std::string k(key);
+  if (k == "xv_chunk_rows") return c->xv_chunk_rows;
+  if (k == "fcm_chunk_rows") return c->fcm_chunk_rows;
+  if (k == "lstm_chunk_partials") return c->lstm_chunk_slots;
+  if (k == "mode") return c->mode;
+  return -1;
+}
+
+int cbx_load_weights(cbx_ctx* c, int which, int n, const char* const* names, const float* const* data, const int64_t* numel) {
+  if (!c || !names || !data || !numel || n <= 0) return CBX_ERR_ARG;
+  cudaSetDevice(c->device);
+  std::map<std::string, std::pair<const float*, int64_t>> t;
+  for (int i = 0; i < n; ++i) t[names[i]] = {data[i], numel[i]};
+  if (which == 0) return load_ve(c, t);
+  if (which == 1) return load_xv(c, t);
+  c->err = "which must be 0 (VoiceEncoder) or 1 (CAMPPlus)";
+  return CBX_ERR_ARG;
+}
+
+int64_t cbx_workspace_bytes(cbx_ctx* c, int n, const int64_t* lengths, int step, double min_cov, int flags) {
+  if (!c || n <= 0 || !lengths || step <= 0 || step > kVePartial) return CBX_ERR_ARG;
+  std::vector<int64_t> off(n + 1, 0);
+  for (int i = 0; i < n; ++i) { if (lengths[i] < 0) return CBX_ERR_ARG; off[i + 1] = off[i] + lengths[i]; }
+  Batch b{n, off.data(), step, min_cov};
+  return workspace_bytes_for(c, b, flags);
+}
+
+int cbx_embed(cbx_ctx* c, const float* pcm, const int64_t* off, int n, float trim_top_db, int step, double min_cov,
+              float* ve_out, float* xv_out, int32_t* status, void* ws, int64_t ws_bytes, void* stream, int flags) {
+  int rc = check_inputs(c, off, n, step, flags);
+  if (rc) return rc;
+  if (!pcm || !ws || !status || ((flags & CBX_DO_VE) && !ve_out) || ((flags & CBX_DO_XV) && !xv_out)) { c->err = "null device pointer"; return CBX_ERR_ARG; }
+  cudaSetDevice(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  Batch b{n, off, step, min_cov};
+  if (ws_bytes < workspace_bytes_for(c, b, flags)) { c->err = "workspace too small"; return CBX_ERR_WORKSPACE; }
+  ChunkSets cs = make_chunks(c, b, flags);
+  c->taps.clear();
+  c->last_plan.assign(n, ClipPlan{});
+  CBX_CUDA_OK(c, cudaMemsetAsync(status, 0, sizeof(int32_t) * n, st));
+
+  // VE region first, XV region after it
+  int64_t ve_region = 0;
+  for (auto& r : cs.ve) { Carver cv(nullptr, 0); carve_ve(cv, plan_ve(b, r.first, r.second), nullptr); ve_region = std::max(ve_region, cv.off); }
+  ve_region = (ve_region + 255) & ~int64_t(255);
+
+  const bool no_trim = (flags & CBX_NO_TRIM) != 0 || !(trim_top_db > 0.f);
+  for (auto& r : cs.ve) {
+    VeLayout L = plan_ve(b, r.first, r.second);
+    Carver cv(ws, ve_region);
+    VeChunk ch = carve_ve(cv, L, c);
+    CBX_CUDA_OK(c, cudaMemcpyAsync(ch.plan, L.plan.data(), sizeof(ClipPlan) * L.plan.size(), cudaMemcpyHostToDevice, st));
+    run_ve_chunk(c, pcm, ch, trim_top_db, no_trim, step, min_cov, ve_out, status, st);
+    for (size_t i = 0; i < L.plan.size(); ++i) {
+      ClipPlan& lp = c->last_plan[r.first + i];
+      lp.mel_row = L.plan[i].mel_row; lp.mel_rows = L.plan[i].mel_rows; lp.slot0 = L.plan[i].slot0; lp.slots = L.plan[i].slots;
+    }
+    // the host plan vector dies at the end of this iteration; the async copy above reads pageable memory, which the
+    // runtime stages before returning, so this is safe
+  }
+  for (auto& r : cs.xv) {
+    XvLayout L = plan_xv(b, r.first, r.second, c->fcm_chunk_rows);
+    // taps are byte offsets from the start of the caller's workspace
+    Carver cv_abs(ws, ws_bytes); cv_abs.off = ve_region;
+    XvChunk ch = carve_xv(cv_abs, L, c);
+    ch.hplan = L.plan.data();
+    CBX_CUDA_OK(c, cudaMemcpyAsync(ch.plan, L.plan.data(), sizeof(ClipPlan) * L.plan.size(), cudaMemcpyHostToDevice, st));
+    run_xv_chunk(c, pcm, ch, xv_out, status, st);
+    for (size_t i = 0; i < L.plan.size(); ++i) {
+      ClipPlan& lp = c->last_plan[r.first + i];
+      lp.fb_row = L.plan[i].fb_row; lp.td_row = L.plan[i].td_row; lp.xv_frames = L.plan[i].xv_frames; lp.xv_tdnn = L.plan[i].xv_tdnn;
+    }
+  }
+  CBX_CUDA_OK(c, cudaGetLastError());
+  return CBX_OK;
+}
+
+static int grow(cbx_ctx* c, void** p, int64_t* have, int64_t want, bool pinned) {
+  if (*have >= want) return CBX_OK;
+  if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *have = 0; }
+  want = want + want / 8;
+  if (pinned) CBX_CUDA_OK(c, cudaMallocHost(p, want)); else CBX_CUDA_OK(c, cudaMalloc(p, want));
+  *have = want;
+  return CBX_OK;
+}
+
+int cbx_embed_host(cbx_ctx* c, const float* pcm_host, const int64_t* off, int n, float trim_top_db, int step, double min_cov,
+                   float* ve_out_host, float* xv_out_host, int32_t* status_host, int flags) {
+  int rc = check_inputs(c, off, n, step, flags);
+  if (rc) return rc;
+  if (!pcm_host) { c->err = "null pcm"; return CBX_ERR_ARG; }
+  cudaSetDevice(c->device);
+  cudaStream_t st = c->own_stream;
+  const int64_t total = off[n] - off[0];
+  Batch b{n, off, step, min_cov};
+  const int64_t need_ws = workspace_bytes_for(c, b, flags);
+  int64_t bytes;
+  bytes = c->own_ws_bytes; if ((rc = grow(c, &c->own_ws, &bytes, need_ws, false))) return rc; c->own_ws_bytes = bytes;
+  bytes = c->own_pcm_floats * 4; if ((rc = grow(c, (void**)&c->own_pcm, &bytes, (total + 512) * 4, false))) return rc; c->own_pcm_floats = bytes / 4;
+  const int64_t out_floats = (int64_t)n * (kVeEmbed + kXvEmbed + 1);
+  bytes = c->own_out_floats * 4; if ((rc = grow(c, (void**)&c->own_out, &bytes, out_floats * 4, false))) return rc; c->own_out_floats = bytes / 4;
+  bytes = c->pin_pcm_floats * 4; if ((rc = grow(c, (void**)&c->pin_pcm, &bytes, (total + 512) * 4, true))) return rc; c->pin_pcm_floats = bytes / 4;
+  bytes = c->pin_out_floats * 4; if ((rc = grow(c, (void**)&c->pin_out, &bytes, out_floats * 4, true))) return rc; c->pin_out_floats = bytes / 4;
+
+  // offsets relative to the first clip
+  std::vector<int64_t> rel(n + 1);
+  for (int i = 0; i <= n; ++i) rel[i] = off[i] - off[0];
+  std::memcpy(c->pin_pcm, pcm_host + off[0], total * sizeof(float));
+  CBX_CUDA_OK(c, cudaMemcpyAsync(c->own_pcm, c->pin_pcm, total * sizeof(float), cudaMemcpyHostToDevice, st));
+  float* ve_dev = c->own_out;
+  float* xv_dev = c->own_out + (int64_t)n * kVeEmbed;
+  int32_t* st_dev = (int32_t*)(c->own_out + (int64_t)n * (kVeEmbed + kXvEmbed));
+  rc = cbx_embed(c, c->own_pcm, rel.data(), n, trim_top_db, step, min_cov, ve_dev, xv_dev, st_dev, c->own_ws, c->own_ws_bytes, st, flags);
+  if (rc) return rc;
+  CBX_CUDA_OK(c, cudaMemcpyAsync(c->pin_out, c->own_out, out_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CBX_CUDA_OK(c, cudaStreamSynchronize(st));
+  if ((flags & CBX_DO_VE) && ve_out_host) std::memcpy(ve_out_host, c->pin_out, (size_t)n * kVeEmbed * sizeof(float));
+  if ((flags & CBX_DO_XV) && xv_out_host) std::memcpy(xv_out_host, c->pin_out + (int64_t)n * kVeEmbed, (size_t)n * kXvEmbed * sizeof(float));
+  if (status_host) std::memcpy(status_host, c->pin_out + (int64_t)n * (kVeEmbed + kXvEmbed), (size_t)n * sizeof(int32_t));
+  return CBX_OK;
+}
+
+int64_t cbx_ve_forward_workspace_bytes(cbx_ctx* c, int n) {
+  if (!c || n <= 0) return CBX_ERR_ARG;
+  Carver cv(nullptr, 0);
+  cv.take<int32_t>(n);
+  cv.take<float>((int64_t)n * kVePartial * kVeGates);
+  cv.take<float>((int64_t)n * kVePartial * kVeHidden);
+  return cv.off + 1024;
+}
+
+int cbx_ve_forward_partials(cbx_ctx* c, const float* mels, int n, float* out, void* ws, int64_t ws_bytes, void* stream) {
+  if (!c) return CBX_ERR_ARG;
+  if (!mels || !out || !ws || n <= 0) { c->err = "bad argument"; return CBX_ERR_ARG; }
+  if (!c->ve.loaded) { c->err = "VoiceEncoder weights not loaded"; return CBX_ERR_STATE; }
+  if (ws_bytes < cbx_ve_forward_workspace_bytes(c, n)) { c->err = "workspace too small"; return CBX_ERR_WORKSPACE; }
+  cudaSetDevice(c->device);
+  run_ve_forward_partials(c, mels, n, out, ws, (cudaStream_t)stream);
+  CBX_CUDA_OK(c, cudaGetLastError());
+  return CBX_OK;
+}
+
+int cbx_locate(cbx_ctx* c, const char* name, int64_t* byte_offset, int64_t* rows, int64_t* cols, int64_t* ld) {
+  if (!c || !name) return CBX_ERR_ARG;
+  auto it = c->taps.find(name);
+  if (it == c->taps.end()) { c->err = std::string("unknown tap ") + name; return CBX_ERR_ARG; }
+  if (byte_offset) *byte_offset = it->second[0];
+  if (rows) *rows = it->second[1];
+  if (cols) *cols = it->second[2];
+  if (ld) *ld = it->second[3];
+  return CBX_OK;
+}
+
+int cbx_clip_rows(cbx_ctx* c, int clip, int64_t* mel_row, int64_t* slot, int64_t* fb_row, int64_t* td_row) {
+  if (!c || clip < 0 || clip >= (int)c->last_plan.size()) return CBX_ERR_ARG;
+  const ClipPlan& p = c->last_plan[clip];
+  if (mel_row) *mel_row = p.mel_row;
+  if (slot) *slot = p.slot0;
+  if (fb_row) *fb_row = p.fb_row;
+  if (td_row) *td_row = p.td_row;
+  return CBX_OK;
+}
+
+int64_t cbx_launch_count(const cbx_ctx* c) { return c ? c->launches.count : 0; }
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+// Internal declarations shared by the translation units of libcbx.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/cbx.h"
+
+namespace cbx {
+
+// ---- fixed hyper-parameters of the path ------------------------------------------------------
+// VoiceEncConfig (voice_encoder/config.py:1-18)
+constexpr int kSR = 16000;
+constexpr int kVeNfft = 400, kVeHop = 160, kVeBins = 201, kVeMels = 40;
+constexpr int kVePartial = 160, kVeHidden = 256, kVeEmbed = 256, kVeGates = 1024;
+constexpr int kVeSpecN = 2 * kVeBins;      // interleaved re/im columns of the DFT GEMM
+// Kaldi fbank as called by xvector.py:50 (torchaudio kaldi.py defaults, 80 bins)
+constexpr int kKWin = 400, kKHop = 160, kKPad = 512, kKBins = 257, kKMels = 80;
+constexpr int kKSpecN = 2 * kKBins;
+// librosa.effects.trim defaults (voice_encoder.py:267)
+constexpr int kTrimFrame = 2048, kTrimHop = 512;
+// CAMPPlus (xvector.py:340-405)
+constexpr int kFcmC = 32, kFcmOut = 320, kTdnnC = 128, kBnC = 128, kGrowth = 32, kCamHid = 64;
+constexpr int kSegLen = 100, kXvEmbed = 192, kStatsC = 512;
+constexpr int kGuardTd = 2;                // zero guard rows (T' domain) between clips; x2 in the fbank domain
+constexpr float kBnEps = 1e-5f;
+
+// ---- per-clip tables ----------------------------------------------------------------------------
+struct ClipPlan {            // host-computed, uploaded once per chunk
+  int64_t pcm_off;           // first sample in the flat PCM buffer
+  int32_t n_samples;
+  int32_t out_index;         // row of the caller's output arrays
+  // VoiceEncoder, upper bounds from the untrimmed length
+  int32_t mel_row, mel_rows; // first row / rows allocated (= target of the untrimmed length)
+  int32_t slot0, slots;      // first partial slot / slots allocated
+  int32_t trim_blk0;         // first entry of the trim scratch (one float per 512-sample block)
+  // CAMPPlus
+  int32_t xv_frames, xv_tdnn, xv_segs;
+  int32_t fb_row;            // first fbank/FCM row (even), = 2*td_row
+  int32_t td_row;            // first row in the T' domain
+  int32_t seg0;              // first CAM segment
+};
+
+struct ClipDyn {             // device-computed (depends on the trim result)
+  int32_t trim_s, trim_e;    // [start,end) samples kept by librosa.effects.trim
+  int32_t ve_frames;         // 1 + (trim_e-trim_s)/160
+  int32_t ve_frames_eff;     // min(ve_frames, target): rows of mel actually computed
+  int32_t ve_parts;          // partials of the trimmed clip
+  int32_t status;
+};
+
+struct Launches { int64_t count = 0; };
+
+// ---- packed weights (device pointers into one allocation each) ----------------------------------
+struct ConvW { const float* w; const float* bias; int K; };   // w [Cout][K], K-major
+struct DenseLayerW {
+  int cin;
+  const float *a1, *b1;      // BN1 scale/shift on the layer input (prologue)
+  const float *w1, *t2;      // [128][cin] with BN2 scale folded, BN2 shift
+  const float *wl;           // [32][3*128] local conv, k = tap*128 + c
+  const float *wc1, *bc1;    // [64][128], [64]
+  const float *wc2, *bc2;    // [32][64], [32]
+};
+struct TransitW { int cin, cout; const float *a, *b, *w; };
+
+struct VeWeights {
+  bool loaded = false;
+  float* blob = nullptr;
+  const float *wih0, *wih[3], *whhT[3], *bias[3], *wpT, *bp;   // whhT [256][1024], wpT [256][256]
+};
+struct XvWeights {
+  bool loaded = false;
+  float* blob = nullptr;
+  const float *conv1_w, *conv1_b;                 // [32][9], [32]
+  ConvW res[2][2][2];                             // [layer][block][conv]; conv2 of block 0 has the shortcut appended (K=320)
+  ConvW head_conv2;
+  ConvW tdnn;                                     // [128][5*320]
+  DenseLayerW dense[52];
+  TransitW transit[3];
+  const float *out_a, *out_b;                     // out_nonlinear BN
+  const float *fin_w, *fin_b;                     // [192][1024] (BN folded), [192]
+};
+struct FrontendTables {
+  float* blob = nullptr;
+  const float *ve_dft;     // [402][400]  window folded
+  const float *ve_mel;     // [40][201]
+  const float *k_dft;      // [514][400]  dc-removal, pre-emphasis, povey window folded
+  const float *k_mel;      // [80][257]
+};
+
+}  // namespace cbx
+
+struct cbx_ctx {
+  int device = 0;
+  std::string err;
+  cbx::VeWeights ve;
+  cbx::XvWeights xv;
+  cbx::FrontendTables ft;
+  cbx::Launches launches;
+  // options
+  int64_t xv_chunk_rows = 36000;      // fbank rows per CAMPPlus chunk
+  int64_t fcm_chunk_rows = 4096;      // fbank rows per FCM sub-chunk
+  int64_t lstm_chunk_slots = 2048;    // partial slots per VoiceEncoder chunk
+  int64_t mode = 0;
+  // buffers owned by the library (cbx_embed_host)
+  void* own_ws = nullptr; int64_t own_ws_bytes = 0;
+  float* own_pcm = nullptr; int64_t own_pcm_floats = 0;
+  float* own_out = nullptr; int64_t own_out_floats = 0;
+  float* pin_pcm = nullptr; int64_t pin_pcm_floats = 0;
+  float* pin_out = nullptr; int64_t pin_out_floats = 0;
+  cudaStream_t own_stream = nullptr;
+  // last-run bookkeeping for the stage taps
+  std::vector<cbx::ClipPlan> last_plan;
+  std::map<std::string, std::vector<int64_t>> taps;   // name -> {byte_offset, rows, cols, ld}
+};
+
+namespace cbx {
+
+// host integer logic (host_plan.cpp)
+int ve_frame_step(double overlap, double rate);
+void ve_num_wins(int64_t n_frames, int step, double min_cov, int64_t* n, int64_t* target);
+
+// weights.cu
+int load_ve(cbx_ctx* c, const std::map<std::string, std::pair<const float*, int64_t>>& t);
+int load_xv(cbx_ctx* c, const std::map<std::string, std::pair<const float*, int64_t>>& t);
+int build_frontend_tables(cbx_ctx* c);
+
+// ---- workspace carving ------------------------------------------------------------------------
+struct Carver {
+  char* base; int64_t off = 0; int64_t cap;
+  Carver(void* b, int64_t c) : base((char*)b), cap(c) {}
+  template <class T> T* take(int64_t n) {
+    off = (off + 255) & ~int64_t(255);
+    T* p = (T*)(base ? base + off : nullptr);
+    off += n * (int64_t)sizeof(T);
+    return p;
+  }
+};
+
+struct VeChunk {            // device buffers of one VoiceEncoder chunk
+  int n_clips; int mel_rows; int slots; int trim_blocks;
+  ClipPlan* plan; ClipDyn* dyn;
+  float* trim_scratch;
+  int32_t* mel_row_clip;    // [mel_rows]
+  int32_t* slot_clip;       // [slots]  clip of the slot, -1 if unused
+  int32_t* slot_row;        // [slots]  first mel row of the partial
+  float* spec;              // [mel_rows][402]
+  float* mel;               // [mel_rows][40]
+  float* xw0;               // [mel_rows][1024]
+  float* xw;                // [slots*160][1024]
+  float* hseq;              // [slots*160][256]
+  float* pemb;              // [slots][256]
+};
+
+struct XvChunk {
+  int n_clips; int fb_rows; int td_rows; int segs; int fcm_rows;   // fcm_rows: rows of the FCM sub-chunk buffers
+  ClipPlan* plan;             // device copy
+  const ClipPlan* hplan;      // host copy (sub-chunk planning)
+  int32_t* fb_row_clip;     // [fb_rows] clip or -1 (guard)
+  int32_t* td_row_clip;     // [td_rows]
+  int32_t* td_row_seg;      // [td_rows] global segment index or -1
+  int32_t* seg_clip;        // [segs]
+  float* spec;              // [fcm_rows][514]   (sub-chunk)
+  float* fbank;             // [fb_rows][80]
+  float* cmn_sum;           // [n_clips][80]
+  float *b0, *b1, *b2, *b4, *b5;   // FCM activations of one sub-chunk
+  float* fcm_out;           // [fb_rows][320]
+  float *cat1, *cat2, *cat3;   // [td_rows][512|1024|1024]
+  float* u;                 // [td_rows][128]
+  float* tr3;               // [td_rows][512]
+  float* seg_sum;           // [segs][128]
+  float* gate;              // [segs][32]
+  float* stats;             // [n_clips][1024]
+};
+
+// kernels (frontend.cu / lstm.cu / campplus.cu)
+void run_ve_chunk(cbx_ctx* c, const float* pcm, const VeChunk& ch, float trim_top_db, bool no_trim, int step,
+                  double min_cov, float* ve_out, int32_t* status, cudaStream_t st);
+void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st);   // xw0 .. pemb
+void run_ve_forward_partials(cbx_ctx* c, const float* mels, int n, float* out, void* ws, cudaStream_t st);
+void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out, int32_t* status, cudaStream_t st);
+
+}  // namespace cbx
+
+#define CBX_CUDA_OK(ctx, expr)                                                              \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                      \
+      return CBX_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)

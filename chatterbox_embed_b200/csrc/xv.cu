@@ -1,0 +1,353 @@
+// CAMPPlus path: Kaldi 80-bin log-fbank + CMN -> FCM 2-D ResNet head -> TDNN(k5,s2) -> 3 CAM-dense-TDNN blocks
+// + transits -> BN/ReLU -> statistics pooling -> dense + BN.   Reference: xvector.py:45-58, 61-127, 146-428.
+//
+// Layout: every activation is time-major with channels contiguous.  Clips are laid back to back on one row
+// axis, separated by zero "guard" rows (kGuardTd rows in the T' domain, twice that in the fbank domain), so a
+// time-shifted read implements the convolutions' zero padding and no kernel needs per-clip bounds.
+#include <math.h>
+
+#include "cbx_internal.h"
+#include "sgemm.cuh"
+
+namespace cbx {
+
+// ---- row maps ------------------------------------------------------------------------------------------
+__global__ void xv_maps_kernel(const ClipPlan* __restrict__ plan, int32_t* __restrict__ fb_row_clip,
+                               int32_t* __restrict__ td_row_clip, int32_t* __restrict__ td_row_seg,
+                               int32_t* __restrict__ seg_clip) {
+  const int c = blockIdx.x;
+  const ClipPlan cp = plan[c];
+  for (int t = threadIdx.x; t < cp.xv_frames; t += blockDim.x) fb_row_clip[cp.fb_row + t] = c;
+  for (int t = threadIdx.x; t < cp.xv_tdnn; t += blockDim.x) {
+    td_row_clip[cp.td_row + t] = c;
+    td_row_seg[cp.td_row + t] = cp.seg0 + t / kSegLen;
+  }
+  for (int s = threadIdx.x; s < cp.xv_segs; s += blockDim.x) seg_clip[cp.seg0 + s] = c;
+}
+
+// ---- K9: Kaldi fbank.  Frames are raw 400-sample windows (snip_edges); DC removal, pre-emphasis and the Povey
+// window are folded into the [514][400] DFT matrix, so the GEMM reads PCM directly. ---------------------------
+struct KaldiFrameGather {
+  const float* pcm; const ClipPlan* plan; const int32_t* row_clip; int row0;
+  __device__ float operator()(int m, int k) const {
+    const int r = row0 + m;
+    const int c = row_clip[r];
+    if (c < 0) return 0.f;
+    return __ldg(pcm + plan[c].pcm_off + (size_t)(r - plan[c].fb_row) * kKHop + k);
+  }
+};
+struct StoreRM {
+  float* out; int ld;
+  __device__ void operator()(int m, int n, float v) const { out[(size_t)m * ld + n] = v; }
+};
+
+__global__ void __launch_bounds__(256) fbank_from_spec_kernel(const float* __restrict__ spec, const float* __restrict__ bank,
+                                                              const int32_t* __restrict__ row_clip, float* __restrict__ fbank,
+                                                              int row0, int rows) {
+  __shared__ float pw[8][kKBins + 3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lr = blockIdx.x * 8 + warp;
+  if (lr >= rows) return;
+  const int r = row0 + lr;
+  if (row_clip[r] < 0) {
+    for (int m = lane; m < kKMels; m += 32) fbank[(size_t)r * kKMels + m] = 0.f;
+    return;
+  }
+  const float2* sp = reinterpret_cast<const float2*>(spec + (size_t)lr * kKSpecN);
+  for (int k = lane; k < kKBins; k += 32) { float2 v = sp[k]; pw[warp][k] = v.x * v.x + v.y * v.y; }
+  __syncwarp();
+  for (int m = lane; m < kKMels; m += 32) {
+    const float* b = bank + (size_t)m * kKBins;
+    float a = 0.f;
+    for (int k = 0; k < kKBins; ++k) a = fmaf(__ldg(b + k), pw[warp][k], a);
+    fbank[(size_t)r * kKMels + m] = logf(fmaxf(a, 1.1920928955078125e-07f));
+  }
+}
+
+// K10: per-clip column mean of the log-fbank (xvector.py:51); deterministic two-level sum.
+__global__ void __launch_bounds__(320) cmn_mean_kernel(const float* __restrict__ fbank, const ClipPlan* __restrict__ plan,
+                                                       float* __restrict__ cmn_mean) {
+  __shared__ float part[4][kKMels];
+  const ClipPlan cp = plan[blockIdx.x];
+  const int col = threadIdx.x % kKMels, stripe = threadIdx.x / kKMels;
+  float a = 0.f;
+  for (int t = stripe; t < cp.xv_frames; t += 4) a += fbank[(size_t)(cp.fb_row + t) * kKMels + col];
+  part[stripe][col] = a;
+  __syncthreads();
+  if (stripe == 0) {
+    const float s = (part[0][col] + part[1][col]) + (part[2][col] + part[3][col]);
+    cmn_mean[blockIdx.x * kKMels + col] = cp.xv_frames > 0 ? s / (float)cp.xv_frames : 0.f;
+  }
+}
+
+// ---- K11: FCM head -------------------------------------------------------------------------------------
+// conv1: Conv2d(1->32, 3x3, pad 1) + BN + ReLU on the CMN'd fbank.  One warp = the 32 channels of one (row, f).
+__global__ void __launch_bounds__(256) fcm_conv1_kernel(const float* __restrict__ fbank, const float* __restrict__ cmn_mean,
+                                                        const int32_t* __restrict__ row_clip, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ out,
+                                                        int row0, int rows, int fb_rows) {
+  const int co = threadIdx.x & 31;
+  const long long pos = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (pos >= (long long)rows * kKMels) return;
+  const int lr = (int)(pos / kKMels), f = (int)(pos - (long long)lr * kKMels);
+  const int r = row0 + lr;
+  float v = 0.f;
+  if (row_clip[r] >= 0) {
+    float acc = __ldg(bias + co);
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int rr = r + kw - 1;
+      if (rr < 0 || rr >= fb_rows) continue;
+      const int cc = row_clip[rr];
+      if (cc < 0) continue;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ff = f + kh - 1;
+        if (ff < 0 || ff >= kKMels) continue;
+        const float x = fbank[(size_t)rr * kKMels + ff] - cmn_mean[cc * kKMels + ff];
+        acc = fmaf(x, __ldg(w + co * 9 + kh * 3 + kw), acc);
+      }
+    }
+    v = fmaxf(acc, 0.f);
+  }
+  out[((size_t)lr * kKMels + f) * kFcmC + co] = v;
+}
+
+// 3x3 conv over [row][F_in][32] as an implicit GEMM (k = (kh*3+kw)*32 + ci), optionally with the block's
+// 1x1 stride-2 shortcut conv appended as 32 extra K columns (k >= 288).
+struct FcmConvA {
+  const float* in; int F_in, F_out, sf;
+  const float* sc; int F_sc;
+  __device__ float operator()(int m, int k) const {
+    const int lr = m / F_out, f = m - lr * F_out;
+    if (k < 288) {
+      const int tap = k >> 5, ci = k & 31;
+      const int kh = tap / 3, kw = tap - kh * 3;
+      const int fi = f * sf + kh - 1;
+      if (fi < 0 || fi >= F_in) return 0.f;
+      return in[((long long)(lr + kw - 1) * F_in + fi) * kFcmC + ci];     // lr-1 / lr+1 hit the buffer's pad rows at the ends
+    }
+    return sc[((long long)lr * F_sc + 2 * f) * kFcmC + (k - 288)];
+  }
+};
+struct FcmEpi {
+  float* out; const float* bias; const float* res; const int32_t* row_clip; int F_out;
+  __device__ void operator()(int m, int n, float acc) const {
+    const int lr = m / F_out;
+    float v = acc + __ldg(bias + n);
+    if (res) v += res[(size_t)m * kFcmC + n];
+    v = fmaxf(v, 0.f);
+    out[(size_t)m * kFcmC + n] = row_clip[lr] >= 0 ? v : 0.f;
+  }
+};
+
+// ---- K12: TDNN Conv1d(320->128, k5, stride 2, pad 2) + BN + ReLU ---------------------------------------------
+struct TdnnA {
+  const float* fcm; int fb_rows;
+  __device__ float operator()(int m, int k) const {
+    const int tap = k / kFcmOut, j = k - tap * kFcmOut;
+    const int r = 2 * m + tap - 2;
+    if (r < 0 || r >= fb_rows) return 0.f;
+    return fcm[(size_t)r * kFcmOut + j];
+  }
+};
+struct BiasReluMaskEpi {
+  float* out; int ld; const float* bias; const int32_t* row_clip;
+  __device__ void operator()(int m, int n, float acc) const {
+    out[(size_t)m * ld + n] = row_clip[m] >= 0 ? fmaxf(acc + __ldg(bias + n), 0.f) : 0.f;
+  }
+};
+
+// ---- K13: CAM dense TDNN layer ---------------------------------------------------------------------------
+struct BnReluA {   // BN + ReLU applied while gathering the A operand (pre-activation order, xvector.py:266-271)
+  const float* x; int ld; const float* a; const float* b;
+  __device__ float operator()(int m, int k) const { return fmaxf(fmaf(x[(size_t)m * ld + k], __ldg(a + k), __ldg(b + k)), 0.f); }
+};
+struct MaskEpi {
+  float* out; int ld; const int32_t* row_clip;
+  __device__ void operator()(int m, int n, float acc) const { out[(size_t)m * ld + n] = row_clip[m] >= 0 ? acc : 0.f; }
+};
+
+// per-segment column sums of u (seg_pooling, xvector.py:221-231): one CTA per 100-frame segment
+__global__ void __launch_bounds__(128) seg_sum_kernel(const float* __restrict__ u, const ClipPlan* __restrict__ plan,
+                                                      const int32_t* __restrict__ seg_clip, float* __restrict__ seg_sum) {
+  const int s = blockIdx.x, ch = threadIdx.x;
+  const ClipPlan cp = plan[seg_clip[s]];
+  const int t0 = (s - cp.seg0) * kSegLen, t1 = min(t0 + kSegLen, cp.xv_tdnn);
+  float a = 0.f;
+  for (int t = t0; t < t1; ++t) a += u[(size_t)(cp.td_row + t) * kBnC + ch];
+  seg_sum[(size_t)s * kBnC + ch] = a;
+}
+
+// gate m = sigmoid(W2 relu(W1 (mean_T u + segmean u) + b1) + b2), constant over a segment (xvector.py:214-219)
+__global__ void __launch_bounds__(128) cam_gate_kernel(const float* __restrict__ seg_sum, const ClipPlan* __restrict__ plan,
+                                                       const int32_t* __restrict__ seg_clip, DenseLayerW L,
+                                                       float* __restrict__ gate) {
+  __shared__ float ctx[kBnC];
+  __shared__ float hid[kCamHid];
+  const int s = blockIdx.x, ch = threadIdx.x;
+  const ClipPlan cp = plan[seg_clip[s]];
+  float tot = 0.f;
+  for (int i = 0; i < cp.xv_segs; ++i) tot += seg_sum[(size_t)(cp.seg0 + i) * kBnC + ch];
+  const int t0 = (s - cp.seg0) * kSegLen, len = min(kSegLen, cp.xv_tdnn - t0);
+  ctx[ch] = tot / (float)cp.xv_tdnn + seg_sum[(size_t)s * kBnC + ch] / (float)len;
+  __syncthreads();
+  if (ch < kCamHid) {
+    float a = __ldg(L.bc1 + ch);
+    for (int k = 0; k < kBnC; ++k) a = fmaf(__ldg(L.wc1 + ch * kBnC + k), ctx[k], a);
+    hid[ch] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  if (ch < kGrowth) {
+    float a = __ldg(L.bc2 + ch);
+    for (int k = 0; k < kCamHid; ++k) a = fmaf(__ldg(L.wc2 + ch * kCamHid + k), hid[k], a);
+    gate[(size_t)s * kGrowth + ch] = 1.f / (1.f + expf(-a));
+  }
+}
+
+struct LocalConvA {   // Conv1d(128->32, k3, dilation d, zero pad d): k = tap*128 + c
+  const float* u; int dil; int td_rows;
+  __device__ float operator()(int m, int k) const {
+    const int tap = k >> 7, c = k & 127;
+    const int r = m + (tap - 1) * dil;
+    if (r < 0 || r >= td_rows) return 0.f;
+    return u[(size_t)r * kBnC + c];
+  }
+};
+struct GateEpi {
+  float* out; int ld; int col0; const float* gate; const int32_t* row_seg;
+  __device__ void operator()(int m, int n, float acc) const {
+    const int s = row_seg[m];
+    out[(size_t)m * ld + col0 + n] = s >= 0 ? acc * gate[(size_t)s * kGrowth + n] : 0.f;
+  }
+};
+
+// ---- K15/K16: out_nonlinear BN+ReLU, statistics pooling (mean, unbiased std), dense + BN -----------------
+__global__ void __launch_bounds__(512) stats_pool_kernel(const float* __restrict__ x, const ClipPlan* __restrict__ plan,
+                                                         const float* __restrict__ a, const float* __restrict__ b,
+                                                         float* __restrict__ stats) {
+  const ClipPlan cp = plan[blockIdx.x];
+  const int ch = threadIdx.x;
+  const float sa = a[ch], sb = b[ch];
+  const int T = cp.xv_tdnn;
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += fmaxf(fmaf(x[(size_t)(cp.td_row + t) * kStatsC + ch], sa, sb), 0.f);
+  const float mean = T > 0 ? s / (float)T : nanf("");
+  float q = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float d = fmaxf(fmaf(x[(size_t)(cp.td_row + t) * kStatsC + ch], sa, sb), 0.f) - mean;
+    q = fmaf(d, d, q);
+  }
+  stats[(size_t)blockIdx.x * 2 * kStatsC + ch] = mean;
+  stats[(size_t)blockIdx.x * 2 * kStatsC + kStatsC + ch] = sqrtf(q / (float)(T - 1));   // T'=1 -> 0/0 = NaN like torch.std
+}
+
+__global__ void __launch_bounds__(256) xv_final_kernel(const float* __restrict__ stats, const ClipPlan* __restrict__ plan,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       float* __restrict__ xv_out, int32_t* __restrict__ status) {
+  __shared__ float st[2 * kStatsC];
+  const ClipPlan cp = plan[blockIdx.x];
+  for (int i = threadIdx.x; i < 2 * kStatsC; i += 256) st[i] = stats[(size_t)blockIdx.x * 2 * kStatsC + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int n = warp; n < kXvEmbed; n += 8) {
+    float acc = 0.f;
+    for (int k = lane; k < 2 * kStatsC; k += 32) acc = fmaf(__ldg(w + (size_t)n * 2 * kStatsC + k), st[k], acc);
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) xv_out[(size_t)cp.out_index * kXvEmbed + n] = cp.xv_frames > 0 ? acc + __ldg(bias + n) : nanf("");
+  }
+  if (threadIdx.x == 0 && status && cp.xv_frames <= 0) atomicOr(status + cp.out_index, CBX_CLIP_XV_TOO_SHORT);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out, int32_t* status, cudaStream_t st) {
+  const XvWeights& W = c->xv;
+  Launches& L = c->launches;
+  const ClipPlan* hp = ch.hplan;
+
+  cudaMemsetAsync(ch.fb_row_clip, 0xff, sizeof(int32_t) * ch.fb_rows, st);
+  cudaMemsetAsync(ch.td_row_clip, 0xff, sizeof(int32_t) * ch.td_rows, st);
+  cudaMemsetAsync(ch.td_row_seg, 0xff, sizeof(int32_t) * ch.td_rows, st);
+  xv_maps_kernel<<<ch.n_clips, 256, 0, st>>>(ch.plan, ch.fb_row_clip, ch.td_row_clip, ch.td_row_seg, ch.seg_clip); L.count++;
+
+  // sub-chunks of whole clips, each covering its leading guard rows too
+  struct Sub { int r0, r1; };
+  std::vector<Sub> subs;
+  {
+    int i = 0;
+    while (i < ch.n_clips) {
+      const int r0 = hp[i].fb_row - 2 * kGuardTd;
+      int j = i, r1 = r0;
+      while (j < ch.n_clips) {
+        const int end = hp[j].fb_row + 2 * (hp[j].xv_tdnn + kGuardTd);
+        if (j > i && end - r0 > ch.fcm_rows) break;
+        r1 = end; ++j;
+      }
+      subs.push_back({r0, r1});
+      i = j;
+    }
+  }
+  for (const Sub& s : subs) {
+    const int rows = s.r1 - s.r0;
+    sgemm(L, st, rows, kKSpecN, kKWin, KaldiFrameGather{pcm, ch.plan, ch.fb_row_clip, s.r0}, c->ft.k_dft, kKWin, StoreRM{ch.spec, kKSpecN});
+    fbank_from_spec_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ch.spec, c->ft.k_mel, ch.fb_row_clip, ch.fbank, s.r0, rows); L.count++;
+  }
+  cmn_mean_kernel<<<ch.n_clips, 320, 0, st>>>(ch.fbank, ch.plan, ch.cmn_sum); L.count++;
+
+  for (const Sub& s : subs) {
+    const int rows = s.r1 - s.r0;
+    const int32_t* rc = ch.fb_row_clip + s.r0;
+    // every sub-chunk buffer has one pad row in front (index -1 is readable)
+    float* b0 = ch.b0 + 80 * kFcmC; float* b1 = ch.b1 + 40 * kFcmC; float* b2 = ch.b2 + 40 * kFcmC;
+    float* b4 = ch.b4 + 20 * kFcmC; float* b5 = ch.b5 + 20 * kFcmC;
+    {
+      const long long npos = (long long)rows * kKMels;
+      fcm_conv1_kernel<<<(unsigned)((npos + 7) / 8), 256, 0, st>>>(ch.fbank, ch.cmn_sum, ch.fb_row_clip, W.conv1_w, W.conv1_b, b0, s.r0, rows, ch.fb_rows); L.count++;
+    }
+    auto conv = [&](const ConvW& w, const float* in, int F_in, int F_out, int sf, const float* sc, int F_sc, const float* res, float* out) {
+      sgemm(L, st, rows * F_out, kFcmC, w.K, FcmConvA{in, F_in, F_out, sf, sc, F_sc}, w.w, w.K, FcmEpi{out, w.bias, res, rc, F_out});
+    };
+    // layer1: 80 -> 40
+    conv(W.res[0][0][0], b0, 80, 40, 2, nullptr, 0, nullptr, b1);
+    conv(W.res[0][0][1], b1, 40, 40, 1, b0, 80, nullptr, b2);
+    conv(W.res[0][1][0], b2, 40, 40, 1, nullptr, 0, nullptr, b1);
+    conv(W.res[0][1][1], b1, 40, 40, 1, nullptr, 0, b2, b2);
+    // layer2: 40 -> 20
+    conv(W.res[1][0][0], b2, 40, 20, 2, nullptr, 0, nullptr, b4);
+    conv(W.res[1][0][1], b4, 20, 20, 1, b2, 40, nullptr, b5);
+    conv(W.res[1][1][0], b5, 20, 20, 1, nullptr, 0, nullptr, b4);
+    conv(W.res[1][1][1], b4, 20, 20, 1, nullptr, 0, b5, b5);
+    // head.conv2: 20 -> 10, written straight into the chunk-level [row][f*32+c] buffer
+    conv(W.head_conv2, b5, 20, 10, 2, nullptr, 0, nullptr, ch.fcm_out + (size_t)s.r0 * kFcmOut);
+  }
+
+  const int M = ch.td_rows;
+  sgemm(L, st, M, kTdnnC, W.tdnn.K, TdnnA{ch.fcm_out, ch.fb_rows}, W.tdnn.w, W.tdnn.K, BiasReluMaskEpi{ch.cat1, 512, W.tdnn.bias, ch.td_row_clip});
+
+  static const int kLayers[3] = {12, 24, 16};
+  static const int kDil[3] = {1, 2, 2};
+  float* cats[3] = {ch.cat1, ch.cat2, ch.cat3};
+  const int lds[3] = {512, 1024, 1024};
+  int li = 0;
+  for (int b = 0; b < 3; ++b) {
+    float* cat = cats[b];
+    const int ld = lds[b];
+    for (int i = 0; i < kLayers[b]; ++i, ++li) {
+      const DenseLayerW& D = W.dense[li];
+      sgemm(L, st, M, kBnC, D.cin, BnReluA{cat, ld, D.a1, D.b1}, D.w1, D.cin, BiasReluMaskEpi{ch.u, kBnC, D.t2, ch.td_row_clip});
+      if (ch.segs > 0) {
+        seg_sum_kernel<<<ch.segs, 128, 0, st>>>(ch.u, ch.plan, ch.seg_clip, ch.seg_sum); L.count++;
+        cam_gate_kernel<<<ch.segs, 128, 0, st>>>(ch.seg_sum, ch.plan, ch.seg_clip, D, ch.gate); L.count++;
+      }
+      sgemm(L, st, M, kGrowth, 3 * kBnC, LocalConvA{ch.u, kDil[b], M}, D.wl, 3 * kBnC, GateEpi{cat, ld, D.cin, ch.gate, ch.td_row_seg});
+    }
+    const TransitW& T = W.transit[b];
+    float* out = b == 0 ? ch.cat2 : (b == 1 ? ch.cat3 : ch.tr3);
+    const int ldo = b == 2 ? kStatsC : 1024;
+    sgemm(L, st, M, T.cout, T.cin, BnReluA{cat, ld, T.a, T.b}, T.w, T.cin, MaskEpi{out, ldo, ch.td_row_clip});
+  }
+  stats_pool_kernel<<<ch.n_clips, 512, 0, st>>>(ch.tr3, ch.plan, W.out_a, W.out_b, ch.stats); L.count++;
+  xv_final_kernel<<<ch.n_clips, 256, 0, st>>>(ch.stats, ch.plan, W.fin_w, W.fin_b, xv_out, status); L.count++;
+}
+
+}  // namespace cbx

@@ -1,0 +1,134 @@
+/*
+ * cbx.h -- C ABI of libcbx.so: the B200-native speaker-embedding path.
+ *
+ * This is the drop-in boundary for the voice-clone conditioning hot path of
+ * chrijaque/chatterbox_embed.  The reference has no FFI of its own (it is 100 %
+ * Python); the boundary it exposes is the Python method surface
+ *   VoiceEncoder.embeds_from_wavs   src/chatterbox/models/voice_encoder/voice_encoder.py:246-274
+ *   VoiceEncoder.inference/forward  voice_encoder.py:139-199
+ *   CAMPPlus.inference              src/chatterbox/models/s3gen/xvector.py:425-428
+ *   S3Token2Mel.save_voice_clone    src/chatterbox/models/s3gen/s3gen.py:107-119
+ * The Python classes in chatterbox_embed_b200/ keep those signatures and bind the
+ * entry points below through ctypes (see INTEGRATION.md for the stub).
+ *
+ * Conventions: plain pointers and sizes only; every function returning int
+ * returns 0 on success and a negative code on failure with a message available
+ * from cbx_last_error(); device pointers are caller-owned; work is stream
+ * ordered on the stream passed in (a cudaStream_t cast to void*; NULL = the
+ * legacy default stream) and the calls do not synchronise unless stated; one
+ * context per GPU, not thread-safe.  There is NO CPU fallback: every compute
+ * entry point fails with CBX_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef CBX_H_
+#define CBX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBX_OK 0
+#define CBX_ERR_ARG (-1)
+#define CBX_ERR_CUDA (-2)
+#define CBX_ERR_STATE (-3)
+#define CBX_ERR_WORKSPACE (-4)
+
+/* per-clip status bits written next to the embeddings */
+#define CBX_CLIP_OK 0
+#define CBX_CLIP_VE_TOO_SHORT 1   /* < 201 samples left after trim: librosa reflect-pad cannot be formed (melspec.py:57-64) */
+#define CBX_CLIP_XV_TOO_SHORT 2   /* < 400 samples: Kaldi window does not fit (torchaudio kaldi.py:142-144) */
+#define CBX_CLIP_VE_NAN 4         /* all-zero post-ReLU projection -> 0/0, as in voice_encoder.py:160 */
+
+/* flags for cbx_embed* */
+#define CBX_DO_VE 1        /* VoiceEncoder 256-d embedding */
+#define CBX_DO_XV 2        /* CAMPPlus 192-d x-vector      */
+#define CBX_NO_TRIM 4      /* trim_top_db=None (voice_encoder.py:266) */
+
+typedef struct cbx_ctx cbx_ctx;
+
+/* Integer plan of one clip of n_samples at 16 kHz (header formulas).
+ * VoiceEncoder side: melspec.py:50 (T_ve), voice_encoder.py:54-66 (partials).
+ * CAMPPlus side: torchaudio kaldi.py:63-67 (T_k), xvector.py:364-372 (stride-2 TDNN),
+ * xvector.py:221-231 (100-frame CAM segments). */
+typedef struct cbx_clip_plan {
+  int64_t n_samples;
+  int64_t ve_frames;     /* 1 + n/160                                   */
+  int64_t ve_partials;   /* get_num_wins(ve_frames, step, min_coverage) */
+  int64_t ve_target;     /* 160 + step*(partials-1)                      */
+  int64_t xv_frames;     /* 1 + (n-400)/160, 0 if n < 400                */
+  int64_t xv_tdnn;       /* (xv_frames-1)/2 + 1                          */
+  int64_t xv_segments;   /* ceil(xv_tdnn/100)                            */
+} cbx_clip_plan;
+
+/* ---- integer host logic (no GPU needed) ------------------------------------------------ */
+/* voice_encoder.py:69-81; rate <= 0 means rate=None (use overlap). Returns the step or <0. */
+int cbx_ve_frame_step(double overlap, double rate);
+/* voice_encoder.py:54-66 */
+int cbx_ve_num_wins(int64_t n_frames, int step, double min_coverage, int64_t* n_wins, int64_t* target_n);
+int cbx_plan_clip(int64_t n_samples, int step, double min_coverage, cbx_clip_plan* out);
+/* librosa.effects.trim frame arithmetic used at voice_encoder.py:267: number of RMS frames. */
+int64_t cbx_trim_num_frames(int64_t n_samples);
+/* Cost model for rank balancing, in FLOP. */
+double cbx_clip_cost(int64_t n_samples);
+
+/* ---- context --------------------------------------------------------------------------- */
+int cbx_create(int device, cbx_ctx** out);
+void cbx_destroy(cbx_ctx* ctx);
+const char* cbx_last_error(const cbx_ctx* ctx);   /* ctx may be NULL: last error of cbx_create */
+const char* cbx_version(void);
+
+/* Tuning: key in {"xv_chunk_rows","fcm_chunk_rows","lstm_chunk_partials","mode"}.  mode: 0 = strict fp32
+ * SIMT kernels everywhere, 1 = tensor-core (tcgen05) kernels where available. */
+int cbx_set_option(cbx_ctx* ctx, const char* key, int64_t value);
+int64_t cbx_get_option(const cbx_ctx* ctx, const char* key);
+
+/* ---- weights: reference state_dict tensors, fp32, host memory, C-contiguous ------------ */
+/* Generic name -> tensor table (keys exactly as in the reference state_dict).
+ * which = 0: VoiceEncoder (ve.safetensors keys), 1: CAMPPlus (speaker_encoder.* keys without prefix).
+ * BatchNorm folding, gate re-layout and DFT/mel tables are built once here. */
+int cbx_load_weights(cbx_ctx* ctx, int which, int n_tensors, const char* const* names,
+                     const float* const* data, const int64_t* numel);
+
+/* ---- batched embedding ------------------------------------------------------------------ */
+/* Bytes of device workspace cbx_embed needs for these clips (lengths in samples) with this partial step. */
+int64_t cbx_workspace_bytes(cbx_ctx* ctx, int n_clips, const int64_t* lengths, int ve_step, double min_coverage, int flags);
+
+/* pcm_dev: all clips back to back, fp32 16 kHz mono in device memory; offsets_host[n_clips+1] (in
+ * samples, host memory).  ve_out_dev [n_clips,256], xv_out_dev [n_clips,192], status_dev [n_clips]
+ * int32 (CBX_CLIP_* bits) are device buffers (either output may be NULL if its flag is off).
+ * trim_top_db as in embeds_from_wavs (ignored with CBX_NO_TRIM); ve_step / min_coverage as in
+ * VoiceEncoder.inference (77 / 0.8 for the reference's callers). */
+int cbx_embed(cbx_ctx* ctx, const float* pcm_dev, const int64_t* offsets_host, int n_clips,
+              float trim_top_db, int ve_step, double min_coverage,
+              float* ve_out_dev, float* xv_out_dev, int32_t* status_dev,
+              void* workspace_dev, int64_t workspace_bytes, void* stream, int flags);
+
+/* Same through HOST buffers: copies pcm host->device, runs, copies results back, synchronises.
+ * The library owns the staging and workspace buffers (grown on demand). */
+int cbx_embed_host(cbx_ctx* ctx, const float* pcm_host, const int64_t* offsets_host, int n_clips,
+                   float trim_top_db, int ve_step, double min_coverage,
+                   float* ve_out_host, float* xv_out_host, int32_t* status_host, int flags);
+
+/* VoiceEncoder.forward on already-cut partials (voice_encoder.py:139-160):
+ * mels_dev [n_partials,160,40] -> out_dev [n_partials,256] (L2-normed). */
+int cbx_ve_forward_partials(cbx_ctx* ctx, const float* mels_dev, int n_partials, float* out_dev,
+                            void* workspace_dev, int64_t workspace_bytes, void* stream);
+int64_t cbx_ve_forward_workspace_bytes(cbx_ctx* ctx, int n_partials);
+
+/* ---- stage taps for parity tests --------------------------------------------------------- */
+/* After cbx_embed (single chunk), locate an intermediate inside the caller's workspace.
+ * name in {"ve_trim","ve_mel","ve_partial_emb","xv_fbank","xv_fcm","xv_cat1","xv_cat2","xv_cat3","xv_stats",...};
+ * returns byte offset, row count, row length (floats) and leading dimension (floats). */
+int cbx_locate(cbx_ctx* ctx, const char* name, int64_t* byte_offset, int64_t* rows, int64_t* cols, int64_t* ld);
+/* Row offsets of clip i inside the stage buffers of the last cbx_embed call. */
+int cbx_clip_rows(cbx_ctx* ctx, int clip, int64_t* ve_mel_row, int64_t* ve_partial_slot,
+                  int64_t* xv_fbank_row, int64_t* xv_tdnn_row);
+
+/* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
+int64_t cbx_launch_count(const cbx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBX_H_ */
