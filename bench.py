@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Benchmark of the speaker-embedding hot path (BASELINE.json metric: speaker embeddings/s on 10 s clips).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode 0|1]
+
+A "step" is one pass of VoiceEncoder + CAMPPlus over one batch of 256 synthetic ten-second 16 kHz clips per GPU
+(BASELINE.json configs[1]).  `value` = whole-job clips/s with the PCM already resident in HBM; `e2e` = the same through
+cbx_embed_host with HOST buffers (host->device copy of the PCM and device->host read of the embeddings inside the timed
+region).  N>1 (torchrun): weak scaling, every rank embeds its own batch, then ONE all-gather of the (256, 448) block.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLIPS = 256
+CLIP_SAMPLES = 160000
+WORKLOAD = "256 x 10 s 16 kHz clips per GPU, VoiceEncoder(256-d)+CAMPPlus(192-d), random-init weights (BASELINE configs[1])"
+# algorithmic FLOPs per 10 s clip
+FLOPS_PER_CLIP = 5190451200 + 1572864 + 11234711552 + 338017680 + 451415360
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sus=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_batch(rank: int):
+    from chatterbox_embed_b200 import synth
+    wavs = [synth.clip(rank * CLIPS + i, CLIP_SAMPLES) for i in range(CLIPS)]
+    off = np.arange(CLIPS + 1, dtype=np.int64) * CLIP_SAMPLES
+    return wavs, off
+
+
+def cpu_baseline(n_clips: int, threads: int):
+    """Oracle port of the reference path, timed on the host cores (B=1 loop, the reference's real usage)."""
+    import torch
+    from chatterbox_embed_b200 import synth
+    from oracle import nets, weights
+    torch.set_num_threads(threads)
+    sdv, sdc = weights.ve_state_dict("W0"), weights.campplus_state_dict("W0")
+    wavs = [synth.clip(i, CLIP_SAMPLES) for i in range(n_clips)]
+    nets.ve_embed_wavs(sdv, wavs[:1]); nets.campplus_embed_wavs(sdc, wavs[:1])      # warm-up
+    t0 = time.perf_counter()
+    nets.ve_embed_wavs(sdv, wavs)
+    nets.campplus_embed_wavs(sdc, wavs)
+    dt = time.perf_counter() - t0
+    return n_clips / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = 8
+    for _ in range(max(args.warmup, 1) - 1):
+        cpu_baseline(2, threads)
+    vals, t_total = [], 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_baseline(per_step, threads)
+        vals.append(v); t_total += dt
+    value = per_step * args.steps / t_total
+    line = {"impl": "reference", "metric": "speaker embeddings/sec (10 s clips)", "value": value, "unit": "clips/s",
+            "audio_s_per_s": value * 10.0, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "clips_per_step": per_step},
+            "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port",
+                             "sample": f"{per_step} of the 256 ten-second clips per step, B=1 loop, oracle port of the reference "
+                                       "(torch CPU fp32); the verbatim reference cannot travel to the GPU box"},
+            "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--mode", type=int, default=int(os.environ.get("CBX_MODE", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from chatterbox_embed_b200 import CAMPPlus, VoiceEncoder, _lib, scheduler
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    torch.manual_seed(0)                       # random-init weights of the same architecture (no checkpoints offline)
+    ve = VoiceEncoder().to(dev).eval()
+    cp = CAMPPlus().to(dev).eval()
+    emb = scheduler.SpeakerEmbedder(ve, cp)
+    ctx = emb.ctx()
+    ctx.set_option("mode", args.mode)
+
+    wavs, off = make_batch(rank)
+    host = torch.empty(CLIPS * CLIP_SAMPLES, dtype=torch.float32).pin_memory()
+    host_np = host.numpy()
+    for i, w in enumerate(wavs):
+        host_np[off[i]:off[i + 1]] = w
+    pcm = host.to(dev)
+    shards = [np.arange(CLIPS) + r * CLIPS for r in range(world)]
+    gathered = torch.empty((world * CLIPS, scheduler.EMB), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step_device():
+        ve_o, xv_o, status = emb.embed_device(pcm, off)
+        if world > 1:
+            block = torch.cat([ve_o, xv_o], dim=1)
+            dist.all_gather_into_tensor(gathered, block)
+        return ve_o, xv_o
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        return ms, wall
+
+    # ---- device-resident throughput -----------------------------------------------------------------------------
+    for _ in range(W):
+        step_device()
+    sync_all()
+    l0 = ctx.launch_count()
+    with ClockSampler(local) as clk:
+        ms, _ = timed(step_device, K)
+    launches = ctx.launch_count() - l0
+    clocks = clk.summary()
+    value = world * CLIPS * K / (ms / 1e3)
+
+    # ---- end to end through host buffers (cbx_embed_host) -------------------------------------------------------
+    flags_pinned = _lib.DO_VE | _lib.DO_XV | _lib.PCM_PINNED
+    out_holder = {}
+
+    def step_host():
+        ve_o, xv_o, status = ctx.embed_host(host_np, off, 20.0, 77, 0.8, flags_pinned)
+        out_holder["ve"], out_holder["xv"] = ve_o, xv_o
+
+    for _ in range(2):
+        step_host()
+    _, wall = timed(step_host, K)
+    e2e_value = world * CLIPS * K / wall
+
+    # ---- per-kernel device times (CUDA events on the launching stream), separate profiled steps ------------------
+    ctx.profile_enable(True)
+    prof_steps = min(K, 2)
+    for _ in range(prof_steps):
+        step_device()
+    torch.cuda.synchronize()
+    prof = ctx.profile_report()
+    ctx.profile_enable(False)
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    pk = peaks()
+    tname, t = top
+    tensor_peak = pk["bf16_sus"] / 2.0         # TF32 dense = half the bf16 rate; bf16 sustained peak is measured
+    if t["flops"] > 0:
+        achieved = t["flops"] / (t["ms"] / 1e3) / 1e12
+        roof = {"kernel": tname, "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                "frac": achieved / tensor_peak, "traffic": None,
+                "peak_source": f"{pk['src']} bf16 sustained / 2 (TF32 runs at half the bf16 rate; no TF32 peak is measured)",
+                "share_of_step": t["ms"] / tot_ms, "avg_launch_ms": t["ms"] / t["launches"], "launches_per_step": t["launches"] / prof_steps}
+    else:
+        roof = {"kernel": tname, "bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None, "traffic": None}
+    kernels = {k: {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] / prof_steps,
+                   "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["flops"] > 0 and v["ms"] > 0 else None}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n_s = 16
+            v, dt = cpu_baseline(n_s, threads)
+            cpu = {"value": v, "unit": "clips/s", "cores": threads, "kind": "port",
+                   "sample": f"{n_s} of the {CLIPS} ten-second clips, B=1 loop, {dt:.1f} s of CPU work (oracle port, torch CPU fp32)"}
+        line = {
+            "metric": "speaker embeddings/sec (10 s clips)", "value": value, "unit": "clips/s",
+            "audio_s_per_s": value * 10.0, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.mode == 0 else "tf32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "mode": "strict-fp32 SIMT" if args.mode == 0 else "tcgen05 TF32",
+                       "l2": "inputs (164 MB PCM per step) and activations exceed the 126 MB L2; no flush needed",
+                       "parallelism": f"dp{world}", "clips_per_gpu": CLIPS},
+            "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": CLIPS * CLIP_SAMPLES * 4,
+                    "d2h_bytes_per_step": CLIPS * (256 + 192 + 1) * 4},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "algorithmic_tflops": value * FLOPS_PER_CLIP / 1e12, "kernels": kernels,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

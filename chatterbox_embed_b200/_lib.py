@@ -12,7 +12,7 @@ from . import build as _build
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_WORKSPACE = 0, -1, -2, -3, -4
 CLIP_VE_TOO_SHORT, CLIP_XV_TOO_SHORT, CLIP_VE_NAN = 1, 2, 4
-DO_VE, DO_XV, NO_TRIM = 1, 2, 4
+DO_VE, DO_XV, NO_TRIM, PCM_PINNED = 1, 2, 4, 8
 
 _lib: Optional[C.CDLL] = None
 
@@ -50,6 +50,8 @@ _SIGS = {
     "cbx_locate": (C.c_int, [C.c_void_p, C.c_char_p, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64), _P(C.c_int64)]),
     "cbx_clip_rows": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64), _P(C.c_int64)]),
     "cbx_launch_count": (C.c_int64, [C.c_void_p]),
+    "cbx_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "cbx_profile_report": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int64]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -151,6 +153,7 @@ class Context:
                                     ve_ptr, xv_ptr, status_ptr, ws_ptr, ws_bytes, stream, flags), "cbx_embed")
 
     def embed_host(self, pcm: np.ndarray, offsets: np.ndarray, trim_top_db: float, step: int, min_cov: float, flags: int):
+        """pcm: flat float32 numpy array (may be a view of page-locked memory: pass PCM_PINNED in flags)."""
         n = len(offsets) - 1
         assert pcm.dtype == np.float32 and pcm.flags.c_contiguous
         off = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -181,6 +184,20 @@ class Context:
 
     def launch_count(self) -> int:
         return lib().cbx_launch_count(self._h)
+
+    def profile_enable(self, on: bool):
+        self._check(lib().cbx_profile_enable(self._h, 1 if on else 0), "cbx_profile_enable")
+
+    def profile_report(self):
+        """{tag: dict(launches, ms, flops, bytes)} for everything launched since profile_enable(True)."""
+        n = lib().cbx_profile_report(self._h, None, 0)
+        buf = C.create_string_buffer(int(n) + 16)
+        lib().cbx_profile_report(self._h, buf, len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            tag, cnt, ms, fl, by = line.split()
+            out[tag] = dict(launches=int(cnt), ms=float(ms), flops=float(fl), bytes=float(by))
+        return out
 
 
 _contexts: Dict[int, Context] = {}

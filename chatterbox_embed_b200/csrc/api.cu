@@ -1,5 +1,6 @@
 // C ABI of libcbx.so (include/cbx.h): context, weight intake, ragged chunk planning, pipeline driver.
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 
 #include "cbx_internal.h"
@@ -334,14 +335,16 @@ int cbx_embed_host(cbx_ctx* c, const float* pcm_host, const int64_t* off, int n,
   bytes = c->own_pcm_floats * 4; if ((rc = grow(c, (void**)&c->own_pcm, &bytes, (total + 512) * 4, false))) return rc; c->own_pcm_floats = bytes / 4;
   const int64_t out_floats = (int64_t)n * (kVeEmbed + kXvEmbed + 1);
   bytes = c->own_out_floats * 4; if ((rc = grow(c, (void**)&c->own_out, &bytes, out_floats * 4, false))) return rc; c->own_out_floats = bytes / 4;
-  bytes = c->pin_pcm_floats * 4; if ((rc = grow(c, (void**)&c->pin_pcm, &bytes, (total + 512) * 4, true))) return rc; c->pin_pcm_floats = bytes / 4;
+  const bool pinned_in = (flags & CBX_PCM_PINNED) != 0;
+  if (!pinned_in) { bytes = c->pin_pcm_floats * 4; if ((rc = grow(c, (void**)&c->pin_pcm, &bytes, (total + 512) * 4, true))) return rc; c->pin_pcm_floats = bytes / 4; }
   bytes = c->pin_out_floats * 4; if ((rc = grow(c, (void**)&c->pin_out, &bytes, out_floats * 4, true))) return rc; c->pin_out_floats = bytes / 4;
 
   // offsets relative to the first clip
   std::vector<int64_t> rel(n + 1);
   for (int i = 0; i <= n; ++i) rel[i] = off[i] - off[0];
-  std::memcpy(c->pin_pcm, pcm_host + off[0], total * sizeof(float));
-  CBX_CUDA_OK(c, cudaMemcpyAsync(c->own_pcm, c->pin_pcm, total * sizeof(float), cudaMemcpyHostToDevice, st));
+  const float* src = pcm_host + off[0];
+  if (!pinned_in) { std::memcpy(c->pin_pcm, src, total * sizeof(float)); src = c->pin_pcm; }
+  CBX_CUDA_OK(c, cudaMemcpyAsync(c->own_pcm, src, total * sizeof(float), cudaMemcpyHostToDevice, st));
   float* ve_dev = c->own_out;
   float* xv_dev = c->own_out + (int64_t)n * kVeEmbed;
   int32_t* st_dev = (int32_t*)(c->own_out + (int64_t)n * (kVeEmbed + kXvEmbed));
@@ -397,5 +400,39 @@ int cbx_clip_rows(cbx_ctx* c, int clip, int64_t* mel_row, int64_t* slot, int64_t
 }
 
 int64_t cbx_launch_count(const cbx_ctx* c) { return c ? c->launches.count : 0; }
+
+int cbx_profile_enable(cbx_ctx* c, int on) {
+  if (!c) return CBX_ERR_ARG;
+  for (auto& r : c->launches.recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  c->launches.recs.clear();
+  c->launches.prof = on != 0;
+  return CBX_OK;
+}
+
+int64_t cbx_profile_report(cbx_ctx* c, char* buf, int64_t cap) {
+  if (!c) return CBX_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  struct Acc { int64_t n = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Acc> acc;
+  for (auto& r : c->launches.recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+    Acc& a = acc[r.tag];
+    a.n++; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+  }
+  std::string out;
+  char line[256];
+  for (auto& kv : acc) {
+    snprintf(line, sizeof line, "%s %lld %.6f %.6e %.6e\n", kv.first.c_str(), (long long)kv.second.n, kv.second.ms, kv.second.flops, kv.second.bytes);
+    out += line;
+  }
+  if (buf && cap > 0) {
+    const int64_t n = std::min<int64_t>(cap - 1, (int64_t)out.size());
+    std::memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)out.size() + 1;
+}
 
 }  // extern "C"

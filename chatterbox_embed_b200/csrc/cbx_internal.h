@@ -52,7 +52,28 @@ struct ClipDyn {             // device-computed (depends on the trim result)
   int32_t status;
 };
 
-struct Launches { int64_t count = 0; };
+// Launch accounting; with profiling on, every launch is bracketed by CUDA events on its own stream.
+struct ProfRec { const char* tag; double flops; double bytes; cudaEvent_t e0, e1; };
+struct Launches {
+  int64_t count = 0;
+  bool prof = false;
+  std::vector<ProfRec> recs;
+};
+struct Scope {
+  Launches& L; cudaStream_t st; bool on;
+  Scope(Launches& l, cudaStream_t s, const char* tag, double flops = 0.0, double bytes = 0.0) : L(l), st(s), on(l.prof) {
+    if (on) {
+      ProfRec r{tag, flops, bytes, nullptr, nullptr};
+      cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+      cudaEventRecord(r.e0, st);
+      L.recs.push_back(r);
+    }
+  }
+  ~Scope() {
+    if (on) cudaEventRecord(L.recs.back().e1, st);
+    L.count++;
+  }
+};
 
 // ---- packed weights (device pointers into one allocation each) ----------------------------------
 struct ConvW { const float* w; const float* bias; int K; };   // w [Cout][K], K-major

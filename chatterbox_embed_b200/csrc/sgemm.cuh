@@ -59,11 +59,11 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, AF af, 
 }
 
 template <class AF, class EF>
-inline void sgemm(Launches& L, cudaStream_t st, int M, int N, int K, AF af, const float* W, int ldw, EF ef) {
+inline void sgemm(Launches& L, cudaStream_t st, const char* tag, int M, int N, int K, AF af, const float* W, int ldw, EF ef) {
   if (M <= 0 || N <= 0) return;
   dim3 grid((M + SG_BM - 1) / SG_BM, (N + SG_BN - 1) / SG_BN);
+  Scope sc(L, st, tag, 2.0 * M * N * K);
   sgemm_kernel<AF, EF><<<grid, 256, 0, st>>>(M, N, K, af, W, ldw, ef);
-  L.count++;
 }
 
 }  // namespace cbx

@@ -275,26 +275,26 @@ void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st) {
   const int rows = ch.slots * kVePartial;
   const int nb = (ch.slots + LSTM_MT - 1) / LSTM_MT;
   // layer 0: projection once per mel frame (partials overlap: hop 77 < 160), then the recurrence gathers rows
-  sgemm(L, st, ch.mel_rows, kVeGates, kVeMels, PlainA{ch.mel, kVeMels}, W.wih0, kVeMels, StoreBias{ch.xw0, kVeGates, W.bias[0]});
-  lstm_rec_kernel<true><<<nb, 256, 0, st>>>(ch.xw0, ch.slot_row, W.whhT[0], ch.hseq, ch.slots); L.count++;
+  sgemm(L, st, "lstm_xw0_gemm", ch.mel_rows, kVeGates, kVeMels, PlainA{ch.mel, kVeMels}, W.wih0, kVeMels, StoreBias{ch.xw0, kVeGates, W.bias[0]});
+  { Scope sc(L, st, "lstm_rec_kernel", 2.0 * ch.slots * kVePartial * kVeHidden * kVeGates); lstm_rec_kernel<true><<<nb, 256, 0, st>>>(ch.xw0, ch.slot_row, W.whhT[0], ch.hseq, ch.slots); }
   for (int l = 1; l < 3; ++l) {
-    sgemm(L, st, rows, kVeGates, kVeHidden, PlainA{ch.hseq, kVeHidden}, W.wih[l], kVeHidden, StoreBias{ch.xw, kVeGates, W.bias[l]});
-    lstm_rec_kernel<false><<<nb, 256, 0, st>>>(ch.xw, ch.slot_row, W.whhT[l], ch.hseq, ch.slots); L.count++;
+    sgemm(L, st, "lstm_xw_gemm", rows, kVeGates, kVeHidden, PlainA{ch.hseq, kVeHidden}, W.wih[l], kVeHidden, StoreBias{ch.xw, kVeGates, W.bias[l]});
+    { Scope sc(L, st, "lstm_rec_kernel", 2.0 * ch.slots * kVePartial * kVeHidden * kVeGates); lstm_rec_kernel<false><<<nb, 256, 0, st>>>(ch.xw, ch.slot_row, W.whhT[l], ch.hseq, ch.slots); }
   }
-  ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hseq, W.wpT, W.bp, ch.pemb); L.count++;
+  { Scope sc(L, st, "ve_proj_kernel"); ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hseq, W.wpT, W.bp, ch.pemb); }
 }
 
 void run_ve_chunk(cbx_ctx* c, const float* pcm, const VeChunk& ch, float trim_top_db, bool no_trim, int step,
                   double min_cov, float* ve_out, int32_t* status, cudaStream_t st) {
   Launches& L = c->launches;
-  trim_plan_kernel<<<ch.n_clips, 256, 0, st>>>(pcm, ch.plan, ch.dyn, ch.trim_scratch, trim_top_db, no_trim ? 1 : 0, step, min_cov); L.count++;
+  { Scope sc(L, st, "trim_plan_kernel"); trim_plan_kernel<<<ch.n_clips, 256, 0, st>>>(pcm, ch.plan, ch.dyn, ch.trim_scratch, trim_top_db, no_trim ? 1 : 0, step, min_cov); }
   cudaMemsetAsync(ch.mel_row_clip, 0xff, sizeof(int32_t) * ch.mel_rows, st);
-  ve_maps_kernel<<<ch.n_clips, 256, 0, st>>>(ch.plan, ch.dyn, step, ch.mel_row_clip, ch.slot_clip, ch.slot_row); L.count++;
-  sgemm(L, st, ch.mel_rows, kVeSpecN, kVeNfft, VeFrameGather{pcm, ch.plan, ch.dyn, ch.mel_row_clip}, c->ft.ve_dft, kVeNfft,
+  { Scope sc(L, st, "ve_maps_kernel"); ve_maps_kernel<<<ch.n_clips, 256, 0, st>>>(ch.plan, ch.dyn, step, ch.mel_row_clip, ch.slot_clip, ch.slot_row); }
+  sgemm(L, st, "ve_dft_gemm", ch.mel_rows, kVeSpecN, kVeNfft, VeFrameGather{pcm, ch.plan, ch.dyn, ch.mel_row_clip}, c->ft.ve_dft, kVeNfft,
         StoreRowMajor{ch.spec, kVeSpecN});
-  ve_mel_kernel<<<(ch.mel_rows + 7) / 8, 256, 0, st>>>(ch.spec, c->ft.ve_mel, ch.plan, ch.dyn, ch.mel_row_clip, ch.mel, ch.mel_rows); L.count++;
+  { Scope sc(L, st, "ve_mel_kernel"); ve_mel_kernel<<<(ch.mel_rows + 7) / 8, 256, 0, st>>>(ch.spec, c->ft.ve_mel, ch.plan, ch.dyn, ch.mel_row_clip, ch.mel, ch.mel_rows); }
   run_ve_lstm(c, ch, st);
-  ve_clip_mean_kernel<<<ch.n_clips, 256, 0, st>>>(ch.pemb, ch.plan, ch.dyn, ve_out, status); L.count++;
+  { Scope sc(L, st, "ve_clip_mean_kernel"); ve_clip_mean_kernel<<<ch.n_clips, 256, 0, st>>>(ch.pemb, ch.plan, ch.dyn, ve_out, status); }
 }
 
 // VoiceEncoder.forward on pre-cut partials: every partial is its own 160-row "clip".
@@ -313,7 +313,7 @@ void run_ve_forward_partials(cbx_ctx* c, const float* mels, int n, float* out, v
   ch.xw = ch.xw0;                       // layer-0 rows are exactly slot*160+t here, so one buffer serves both
   ch.hseq = cv.take<float>((int64_t)ch.mel_rows * kVeHidden);
   ch.pemb = out;
-  ve_identity_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(ch.slot_row, n); c->launches.count++;
+  { Scope sc(c->launches, st, "ve_identity_slots_kernel"); ve_identity_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(ch.slot_row, n); }
   run_ve_lstm(c, ch, st);
 }
 

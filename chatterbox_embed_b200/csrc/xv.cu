@@ -268,7 +268,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
   cudaMemsetAsync(ch.fb_row_clip, 0xff, sizeof(int32_t) * ch.fb_rows, st);
   cudaMemsetAsync(ch.td_row_clip, 0xff, sizeof(int32_t) * ch.td_rows, st);
   cudaMemsetAsync(ch.td_row_seg, 0xff, sizeof(int32_t) * ch.td_rows, st);
-  xv_maps_kernel<<<ch.n_clips, 256, 0, st>>>(ch.plan, ch.fb_row_clip, ch.td_row_clip, ch.td_row_seg, ch.seg_clip); L.count++;
+  { Scope sc(L, st, "xv_maps_kernel"); xv_maps_kernel<<<ch.n_clips, 256, 0, st>>>(ch.plan, ch.fb_row_clip, ch.td_row_clip, ch.td_row_seg, ch.seg_clip); }
 
   // sub-chunks of whole clips, each covering its leading guard rows too
   struct Sub { int r0, r1; };
@@ -289,10 +289,10 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
   }
   for (const Sub& s : subs) {
     const int rows = s.r1 - s.r0;
-    sgemm(L, st, rows, kKSpecN, kKWin, KaldiFrameGather{pcm, ch.plan, ch.fb_row_clip, s.r0}, c->ft.k_dft, kKWin, StoreRM{ch.spec, kKSpecN});
-    fbank_from_spec_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ch.spec, c->ft.k_mel, ch.fb_row_clip, ch.fbank, s.r0, rows); L.count++;
+    sgemm(L, st, "kaldi_dft_gemm", rows, kKSpecN, kKWin, KaldiFrameGather{pcm, ch.plan, ch.fb_row_clip, s.r0}, c->ft.k_dft, kKWin, StoreRM{ch.spec, kKSpecN});
+    { Scope sc(L, st, "fbank_from_spec_kernel"); fbank_from_spec_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ch.spec, c->ft.k_mel, ch.fb_row_clip, ch.fbank, s.r0, rows); }
   }
-  cmn_mean_kernel<<<ch.n_clips, 320, 0, st>>>(ch.fbank, ch.plan, ch.cmn_sum); L.count++;
+  { Scope sc(L, st, "cmn_mean_kernel"); cmn_mean_kernel<<<ch.n_clips, 320, 0, st>>>(ch.fbank, ch.plan, ch.cmn_sum); }
 
   for (const Sub& s : subs) {
     const int rows = s.r1 - s.r0;
@@ -302,10 +302,10 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     float* b4 = ch.b4 + 20 * kFcmC; float* b5 = ch.b5 + 20 * kFcmC;
     {
       const long long npos = (long long)rows * kKMels;
-      fcm_conv1_kernel<<<(unsigned)((npos + 7) / 8), 256, 0, st>>>(ch.fbank, ch.cmn_sum, ch.fb_row_clip, W.conv1_w, W.conv1_b, b0, s.r0, rows, ch.fb_rows); L.count++;
+      { Scope sc(L, st, "fcm_conv1_kernel"); fcm_conv1_kernel<<<(unsigned)((npos + 7) / 8), 256, 0, st>>>(ch.fbank, ch.cmn_sum, ch.fb_row_clip, W.conv1_w, W.conv1_b, b0, s.r0, rows, ch.fb_rows); }
     }
     auto conv = [&](const ConvW& w, const float* in, int F_in, int F_out, int sf, const float* sc, int F_sc, const float* res, float* out) {
-      sgemm(L, st, rows * F_out, kFcmC, w.K, FcmConvA{in, F_in, F_out, sf, sc, F_sc}, w.w, w.K, FcmEpi{out, w.bias, res, rc, F_out});
+      sgemm(L, st, "fcm_conv_gemm", rows * F_out, kFcmC, w.K, FcmConvA{in, F_in, F_out, sf, sc, F_sc}, w.w, w.K, FcmEpi{out, w.bias, res, rc, F_out});
     };
     // layer1: 80 -> 40
     conv(W.res[0][0][0], b0, 80, 40, 2, nullptr, 0, nullptr, b1);
@@ -322,7 +322,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
   }
 
   const int M = ch.td_rows;
-  sgemm(L, st, M, kTdnnC, W.tdnn.K, TdnnA{ch.fcm_out, ch.fb_rows}, W.tdnn.w, W.tdnn.K, BiasReluMaskEpi{ch.cat1, 512, W.tdnn.bias, ch.td_row_clip});
+  sgemm(L, st, "tdnn_gemm", M, kTdnnC, W.tdnn.K, TdnnA{ch.fcm_out, ch.fb_rows}, W.tdnn.w, W.tdnn.K, BiasReluMaskEpi{ch.cat1, 512, W.tdnn.bias, ch.td_row_clip});
 
   static const int kLayers[3] = {12, 24, 16};
   static const int kDil[3] = {1, 2, 2};
@@ -334,20 +334,20 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     const int ld = lds[b];
     for (int i = 0; i < kLayers[b]; ++i, ++li) {
       const DenseLayerW& D = W.dense[li];
-      sgemm(L, st, M, kBnC, D.cin, BnReluA{cat, ld, D.a1, D.b1}, D.w1, D.cin, BiasReluMaskEpi{ch.u, kBnC, D.t2, ch.td_row_clip});
+      sgemm(L, st, "dense_bottleneck_gemm", M, kBnC, D.cin, BnReluA{cat, ld, D.a1, D.b1}, D.w1, D.cin, BiasReluMaskEpi{ch.u, kBnC, D.t2, ch.td_row_clip});
       if (ch.segs > 0) {
-        seg_sum_kernel<<<ch.segs, 128, 0, st>>>(ch.u, ch.plan, ch.seg_clip, ch.seg_sum); L.count++;
-        cam_gate_kernel<<<ch.segs, 128, 0, st>>>(ch.seg_sum, ch.plan, ch.seg_clip, D, ch.gate); L.count++;
+        { Scope sc(L, st, "seg_sum_kernel"); seg_sum_kernel<<<ch.segs, 128, 0, st>>>(ch.u, ch.plan, ch.seg_clip, ch.seg_sum); }
+        { Scope sc(L, st, "cam_gate_kernel"); cam_gate_kernel<<<ch.segs, 128, 0, st>>>(ch.seg_sum, ch.plan, ch.seg_clip, D, ch.gate); }
       }
-      sgemm(L, st, M, kGrowth, 3 * kBnC, LocalConvA{ch.u, kDil[b], M}, D.wl, 3 * kBnC, GateEpi{cat, ld, D.cin, ch.gate, ch.td_row_seg});
+      sgemm(L, st, "dense_local_gemm", M, kGrowth, 3 * kBnC, LocalConvA{ch.u, kDil[b], M}, D.wl, 3 * kBnC, GateEpi{cat, ld, D.cin, ch.gate, ch.td_row_seg});
     }
     const TransitW& T = W.transit[b];
     float* out = b == 0 ? ch.cat2 : (b == 1 ? ch.cat3 : ch.tr3);
     const int ldo = b == 2 ? kStatsC : 1024;
-    sgemm(L, st, M, T.cout, T.cin, BnReluA{cat, ld, T.a, T.b}, T.w, T.cin, MaskEpi{out, ldo, ch.td_row_clip});
+    sgemm(L, st, "transit_gemm", M, T.cout, T.cin, BnReluA{cat, ld, T.a, T.b}, T.w, T.cin, MaskEpi{out, ldo, ch.td_row_clip});
   }
-  stats_pool_kernel<<<ch.n_clips, 512, 0, st>>>(ch.tr3, ch.plan, W.out_a, W.out_b, ch.stats); L.count++;
-  xv_final_kernel<<<ch.n_clips, 256, 0, st>>>(ch.stats, ch.plan, W.fin_w, W.fin_b, xv_out, status); L.count++;
+  { Scope sc(L, st, "stats_pool_kernel"); stats_pool_kernel<<<ch.n_clips, 512, 0, st>>>(ch.tr3, ch.plan, W.out_a, W.out_b, ch.stats); }
+  { Scope sc(L, st, "xv_final_kernel"); xv_final_kernel<<<ch.n_clips, 256, 0, st>>>(ch.stats, ch.plan, W.fin_w, W.fin_b, xv_out, status); }
 }
 
 }  // namespace cbx

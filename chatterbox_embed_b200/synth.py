@@ -32,6 +32,13 @@ def clip(idx: int, n: int) -> np.ndarray:
     return noise(idx, n) if idx % 2 == 0 else chirp(idx, n)
 
 
+def mixed(idx: int, n: int) -> np.ndarray:
+    """Chirp over a -34 dB noise floor (no numerically empty spectral bins), or plain noise for even indices."""
+    if idx % 2 == 0:
+        return noise(idx, n)
+    return (chirp(idx, n) + 0.1 * noise(idx, n)).astype(np.float32)
+
+
 def ragged_lengths(n_clips: int, lo_s: float = 3.0, hi_s: float = 30.0, seed: int = 2024) -> np.ndarray:
     rng = np.random.RandomState(seed)
     return np.round(SR * rng.uniform(lo_s, hi_s, size=n_clips)).astype(np.int64)

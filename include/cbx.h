@@ -44,6 +44,7 @@ extern "C" {
 #define CBX_DO_VE 1        /* VoiceEncoder 256-d embedding */
 #define CBX_DO_XV 2        /* CAMPPlus 192-d x-vector      */
 #define CBX_NO_TRIM 4      /* trim_top_db=None (voice_encoder.py:266) */
+#define CBX_PCM_PINNED 8   /* cbx_embed_host: pcm_host is page-locked already, copy straight from it */
 
 typedef struct cbx_ctx cbx_ctx;
 
@@ -127,6 +128,12 @@ int cbx_clip_rows(cbx_ctx* ctx, int clip, int64_t* ve_mel_row, int64_t* ve_parti
 
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t cbx_launch_count(const cbx_ctx* ctx);
+
+/* Per-kernel timing: with profiling on, every launch is bracketed by CUDA events on its stream.
+ * cbx_profile_report synchronises the device and writes one line per kernel family:
+ *   "<tag> <launches> <total_ms> <flops> <bytes>\n"; returns the bytes needed (call with buf=NULL to size). */
+int cbx_profile_enable(cbx_ctx* ctx, int on);
+int64_t cbx_profile_report(cbx_ctx* ctx, char* buf, int64_t cap);
 
 #ifdef __cplusplus
 }

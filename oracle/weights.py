@@ -135,7 +135,7 @@ def calibrate_campplus(sd, wavs=None):
     from chatterbox_embed_b200 import synth
     from . import frontend
     if wavs is None:
-        wavs = [synth.clip(i, 32000) for i in range(4)]
+        wavs = [synth.mixed(100 + i, 24000) for i in range(16)]
     feats = torch.from_numpy(np.stack([frontend.campplus_features(w) for w in wavs]))
     orig = nets._bn
 

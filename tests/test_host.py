@@ -1,0 +1,86 @@
+"""CPU tests of the host logic and the C-ABI surface (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from chatterbox_embed_b200 import CAMPPlus, VoiceEncoder, VoiceEncConfig, _lib, scheduler, synth
+from oracle import nets, weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "cbx.h")).read()
+    declared = set(re.findall(r"\b(cbx_[a-z_0-9]+)\s*\(", hdr))
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_lib.EXPORTS)
+
+
+def test_num_wins_and_step_match_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ints.npz"))
+    for n, (w, t) in zip(g["n_frames"], g["wins77"]):
+        assert _lib.num_wins(int(n), 77, 0.8) == (int(w), int(t))
+    for n, (w, t) in zip(g["n_frames"], g["wins80"]):
+        assert _lib.num_wins(int(n), 80, 0.8) == (int(w), int(t))
+    assert _lib.frame_step(0.5, 1.3) == 77 and _lib.frame_step(0.5, None) == 80
+    for rate in (0.7, 1.0, 1.3, 2.0, 3.3):
+        assert _lib.frame_step(0.5, rate) == nets.frame_step(0.5, rate)
+    for ov in (0.0, 0.25, 0.5, 0.9):
+        assert _lib.frame_step(ov, None) == nets.frame_step(ov, None)
+
+
+@pytest.mark.parametrize("n,want", [(160000, (1001, 12, 1007, 998, 499, 5)), (48000, (301, 3, 314, 298, 149, 2)),
+                                     (480000, (3001, 38, 3009, 2998, 1499, 15)), (720, (5, 1, 160, 3, 2, 1)),
+                                     (399, (3, 1, 160, 0, 0, 0))])
+def test_plan_clip(n, want):
+    p = _lib.plan_clip(n)
+    assert (p.ve_frames, p.ve_partials, p.ve_target, p.xv_frames, p.xv_tdnn, p.xv_segments) == want
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(_lib.CbxError):
+        _lib.Context(0)
+    ve = VoiceEncoder()
+    with pytest.raises(_lib.CbxError):
+        ve.embeds_from_wavs([synth.clip(0, 16000)], 16000)
+    with pytest.raises(_lib.CbxError):
+        CAMPPlus().inference([np.zeros(16000, np.float32)])
+
+
+def test_state_dict_compat():
+    ve = VoiceEncoder(VoiceEncConfig())
+    ve.load_state_dict(weights.ve_state_dict("W0"), strict=True)
+    cp = CAMPPlus()
+    sd = weights.campplus_state_dict("W1")
+    cp.load_state_dict(sd, strict=True)
+    assert len(cp.state_dict()) == 937
+    assert sum(v.numel() for k, v in cp.state_dict().items() if v.dtype.is_floating_point and "running" not in k) > 6.8e6
+
+
+def test_baked_config_is_enforced():
+    class HP(VoiceEncConfig):
+        num_mels = 80
+    with pytest.raises(ValueError):
+        VoiceEncoder(HP())
+    with pytest.raises(ValueError):
+        CAMPPlus(embedding_size=256)
+
+
+def test_scheduler_partition_balances_and_inverts():
+    lens = synth.ragged_lengths(1024)
+    for world in (1, 2, 4, 8):
+        shards = scheduler.partition(lens, world)
+        allidx = np.concatenate([s for s in shards])
+        assert sorted(allidx.tolist()) == list(range(len(lens)))
+        sizes = {len(s) for s in shards}
+        assert max(sizes) - min(sizes) <= 1
+        costs = [sum(_lib.clip_cost(int(lens[i])) for i in s) for s in shards]
+        assert max(costs) / (sum(costs) / world) < 1.03
+        inv = scheduler.inverse_permutation(shards, len(lens))
+        gathered = np.concatenate([np.pad(s, (0, max(sizes) - len(s)), constant_values=-1) for s in shards])
+        assert (gathered[inv] == np.arange(len(lens))).all()

@@ -1,0 +1,132 @@
+"""CPU tests: the oracle against the golden vectors (produced by the verbatim reference, oracle/make_golden.py), against
+torchaudio / torch.stft cross-checks, and -- when /root/reference is present -- against the reference modules live."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from chatterbox_embed_b200 import synth
+from oracle import frontend, make_golden, nets, refload, weights
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_num_wins_matches_reference_table(golden_dir):
+    g = _load(golden_dir, "ints.npz")
+    for n, (w, t) in zip(g["n_frames"], g["wins77"]):
+        assert nets.num_wins(int(n), 77, 0.8) == (int(w), int(t))
+    for n, (w, t) in zip(g["n_frames"], g["wins80"]):
+        assert nets.num_wins(int(n), 80, 0.8) == (int(w), int(t))
+    assert nets.frame_step(0.5, 1.3) == int(g["step_rate13"]) == 77
+    assert nets.frame_step(0.5, None) == int(g["step_none"]) == 80
+
+
+def test_survey_known_answers():
+    table = {1: (1, 160), 159: (1, 160), 160: (1, 160), 161: (1, 160), 236: (2, 237), 237: (2, 237), 300: (3, 314),
+             301: (3, 314), 1001: (12, 1007), 3001: (38, 3009)}
+    for n, want in table.items():
+        assert nets.num_wins(n, 77, 0.8) == want
+
+
+def test_mel_basis_matches_torchaudio_slaney():
+    import torchaudio
+    fb = torchaudio.functional.melscale_fbanks(201, 0., 8000., 40, 16000, norm="slaney", mel_scale="slaney").T.numpy()
+    assert np.abs(fb - frontend.ve_mel_basis()).max() < 1e-7
+
+
+def test_stft_matches_torch_stft():
+    w = synth.clip(1, 20000)
+    a = frontend.stft(w, 400, 160, 400, True, "reflect")
+    b = torch.stft(torch.from_numpy(w), 400, 160, 400, torch.hann_window(400), center=True, pad_mode="reflect",
+                   return_complex=True).numpy()
+    assert a.shape == b.shape == (201, 126)
+    assert np.abs(a - b).max() < 2e-5 * np.abs(b).max()
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_kaldi_restatement_matches_torchaudio(idx):
+    w = synth.clip(idx, 32000)
+    a, b = frontend.kaldi_fbank_numpy(w), frontend.kaldi_fbank_torchaudio(w)
+    assert a.shape == b.shape == (198, 80)
+    assert np.abs(a - b).mean() < 5e-4      # log domain; near-empty bins of a chirp differ by up to ~1e-2
+    assert np.abs(a - b).max() < 5e-2
+
+
+def test_trim_bounds_golden(golden_dir):
+    g = _load(golden_dir, "ref_W0.npz")
+    wavs = make_golden.golden_wavs()
+    got = np.array([frontend.trim_bounds(w, 20) for w in wavs])
+    assert (got == g["trim"]).all()
+    assert (got[2] != [0, 50000]).all()         # the silent-edged clip is really trimmed
+
+
+@pytest.mark.parametrize("kind", ["W0", "W1"])
+def test_oracle_vs_golden_embeddings(golden_dir, kind):
+    g = _load(golden_dir, f"ref_{kind}.npz")
+    wavs = make_golden.golden_wavs()
+    sdv, sdc = weights.ve_state_dict(kind), weights.campplus_state_dict(kind)
+    ve = nets.ve_embed_wavs(sdv, wavs)
+    assert np.abs(ve - g["ve_emb"]).max() < 2e-6
+    ve2 = nets.ve_embed_wavs(sdv, wavs, trim_top_db=None)
+    assert np.abs(ve2 - g["ve_emb_notrim"]).max() < 2e-6
+    sel = [0, 1, 4]
+    xv = nets.campplus_embed_wavs(sdc, [wavs[i] for i in sel])
+    assert np.abs(xv - g["xv_emb"][sel]).max() < 2e-5 * max(1.0, np.abs(g["xv_emb"]).max())
+
+
+@pytest.mark.parametrize("kind", ["W0", "W1"])
+def test_oracle_vs_golden_stages(golden_dir, kind):
+    g = _load(golden_dir, f"ref_{kind}.npz")
+    w = make_golden.golden_wavs()[1]
+    mel = frontend.ve_melspectrogram(w)
+    assert np.abs(mel - g["mel_1"]).max() <= 1e-6 * np.abs(g["mel_1"]).max()
+    sdv, sdc = weights.ve_state_dict(kind), weights.campplus_state_dict(kind)
+    with torch.inference_mode():
+        pe = nets.ve_forward(sdv, nets.ve_partials(mel)).numpy()
+    assert np.abs(pe - g["partial_emb_1"]).max() < 2e-6
+    feat = frontend.campplus_features(w)
+    assert np.abs(feat - g["fbank_cmn_1"]).max() < 1e-5
+    taps = {}
+    nets.campplus_embed_wavs(sdc, [w], taps)
+    for key, stride in (("fcm", 16), ("tdnn", 8), ("block1", 16)):
+        a = taps[key][0, :, ::stride].numpy()
+        b = g[f"{key}_1"]
+        assert np.abs(a - b).max() <= 1e-4 * max(1.0, np.abs(b).max()), key
+
+
+def test_npy_fixture_format_roundtrip(tmp_path):
+    """audio_test/reference_voice_clone.npy pins the FORMAT (NPY v1, <f4, (1,192), C order): np.save reproduces it."""
+    emb = np.arange(192, dtype=np.float32)[None] / 7
+    p = tmp_path / "clone.npy"
+    np.save(p, emb)
+    raw = p.read_bytes()
+    assert len(raw) == 896 and raw[:8] == b"\x93NUMPY\x01\x00"
+    assert b"'descr': '<f4'" in raw[:128] and b"'fortran_order': False" in raw[:128] and b"'shape': (1, 192)" in raw[:128]
+    ref_fixture = os.path.join(refload.REF_ROOT, "audio_test", "reference_voice_clone.npy")
+    if os.path.exists(ref_fixture):
+        rb = open(ref_fixture, "rb").read()
+        assert rb[:128] == raw[:128] and len(rb) == 896
+
+
+@pytest.mark.skipif(not refload.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("kind", ["W0", "W1"])
+def test_oracle_vs_live_reference(kind):
+    sdv, sdc = weights.ve_state_dict(kind), weights.campplus_state_dict(kind)
+    ve = refload.make_voice_encoder(sdv)
+    cp = refload.make_campplus(sdc)
+    wavs = [synth.clip(10, 20000), synth.with_silence(11, 30000, 4000, 3000)]
+    assert np.abs(ve.embeds_from_wavs(wavs, 16000) - nets.ve_embed_wavs(sdv, wavs)).max() < 2e-6
+    with torch.inference_mode():
+        r = np.concatenate([cp.inference(torch.from_numpy(w)[None]).numpy() for w in wavs])
+    assert np.abs(r - nets.campplus_embed_wavs(sdc, wavs)).max() < 2e-5 * max(1.0, np.abs(r).max())
+
+
+def test_w2_is_sensitive():
+    """The sensitised set must tell a correct front-end from a zeroed one (SURVEY.md 8d hazard 1)."""
+    sdv = weights.ve_state_dict("W2")
+    a = nets.ve_embed_wavs(sdv, [synth.clip(0, 32000)])[0]
+    b = nets.ve_embed_mels(sdv, [np.zeros((201, 40), np.float32)])[0]
+    assert float(a @ b) < 0.99
