@@ -1,5 +1,6 @@
 // Internal declarations shared by the translation units of libcbx.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -91,6 +92,7 @@ struct VeWeights {
   bool loaded = false;
   float* blob = nullptr;
   const float *wih0, *wih[3], *whhT[3], *bias[3], *wpT, *bp;   // whhT [256][1024], wpT [256][256]
+  CUtensorMap tm_wih[3];     // TMA maps of W_ih (B operand of the input-projection GEMMs)
 };
 struct XvWeights {
   bool loaded = false;
@@ -103,6 +105,8 @@ struct XvWeights {
   TransitW transit[3];
   const float *out_a, *out_b;                     // out_nonlinear BN
   const float *fin_w, *fin_b;                     // [192][1024] (BN folded), [192]
+  CUtensorMap tm_tdnn, tm_w1[52], tm_wl[52], tm_tr[3];   // TMA maps of the GEMM B operands
+  CUtensorMap tm_res[2][2][2], tm_head2;
 };
 struct FrontendTables {
   float* blob = nullptr;

@@ -1,0 +1,400 @@
+// sm_100a tensor-core GEMM engine: TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory -> tcgen05.mma
+// kind::tf32 with the fp32 accumulator in TMEM -> tcgen05.ld epilogue.
+//
+//   C[m][n] = epi( sum_k pro(A[m][k]) * W[n][k] )     A, W both K-major (row-major activations, PyTorch weights)
+//
+// One 128 x BN output tile per CTA.  Warp roles: warp 0 = TMA producer (one elected lane), warp 1 = TMEM
+// allocator + MMA issuer (one elected lane), warps 2..5 = epilogue (TMEM lane quadrant = warp % 4), and when the op
+// has an A-operand prologue (BatchNorm + ReLU before the conv, xvector.py:266-271) warps 6..9 transform each landed A
+// stage in place before it is handed to the MMA warp.  Pipelines: full/empty mbarriers per smem stage (TMA <-> MMA,
+// with an extra "ready" barrier when the prologue warps sit in between) and one accumulator barrier (MMA -> epilogue).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cbx_internal.h"
+
+namespace cbx {
+namespace tc {
+
+constexpr int BM = 128;       // UMMA M
+constexpr int BK = 32;        // fp32 elements per 128-byte swizzle row
+constexpr int UMMA_K = 8;     // tf32: 32 bytes of K per instruction
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier when all MMAs issued so far by this thread have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 columns: thread i of the warp gets columns [c, c+32) of TMEM lane (quadrant*32 + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float to_tf32(float x) {   // round-to-nearest (ties away) fp32 -> tf32, kept in an fp32 container
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (stride byte offset), version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                               // leading byte offset (unused for swizzled K-major), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                               // descriptor version, bits [46,48)
+  d |= (uint64_t)2 << 61;                               // layout type SWIZZLE_128B, bits [61,64)
+  return d;
+}
+// kind::tf32 instruction descriptor: D=f32, A=B=tf32, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- K-block -> A tile coordinates
+// The K loop runs over nkb blocks of 32 columns.  Block kb belongs to "tap" kb / cpb (cpb = column blocks per tap) and
+// reads A columns col0[tap] + (kb % cpb)*32 of rows m0 + shift[tap]: a time-shifted read is how the convolutions'
+// taps are expressed; rows outside the tensor come back as zeros from TMA, rows between clips are zero guard rows.
+struct TapMap {
+  int cpb;
+  int shift[5];
+  int col0[5];
+};
+__host__ inline TapMap plain_map(int K) { TapMap t{}; t.cpb = (K + BK - 1) / BK; return t; }
+
+// A-operand prologue: BatchNorm scale/shift + ReLU + tf32 rounding, applied in place on the landed smem stage
+struct NoPrologue { static constexpr bool kOn = false; };
+struct BnReluPrologue {
+  static constexpr bool kOn = true;
+  const float* a; const float* b;     // per input channel (column of A)
+};
+
+constexpr int smem_bytes(int BN, int stages) { return stages * (BM * BK * 4 + BN * BK * 4) + 1024 + 256; }
+
+template <int BN, int STAGES, class Pro, class Epi>
+__global__ void __launch_bounds__(Pro::kOn ? 320 : 192)
+tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int nkb, TapMap tap, Pro pro, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  uint64_t* empty = full + STAGES;
+  uint64_t* ready = empty + STAGES;          // only used with a prologue
+  uint64_t* accum = ready + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&ready[s], 128);
+    }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+        const int t = kb / tap.cpb, cb = kb - t * tap.cpb;
+        tma_load_2d(sA + s * A_BYTES, &tmA, &full[s], tap.col0[t] + cb * BK, m0 + tap.shift[t]);
+        tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        mbar_wait(Pro::kOn ? &ready[s] : &full[s], ph);
+        tc_fence_after();
+        const uint64_t ad = make_desc_sw128(smem_u32(sA + s * A_BYTES));
+        const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_tf32(tmem_base, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (kb | k) != 0);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accum);
+    }
+  } else if (warp < 6) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int q = warp & 3;                    // TMEM lane quadrant this warp may access
+    const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      epi(row, n0 + c, v);
+    }
+    tc_fence_before();
+  } else {
+    // ===== A-operand prologue warps (only instantiated for Pro::kOn) =====
+    if constexpr (Pro::kOn) {
+      const int t = threadIdx.x - 192;         // 0..127
+      const int chunk = t & 7, r0 = t >> 3;    // 16-byte chunk within the 128-byte row, first row
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        const int tp = kb / tap.cpb, cb = kb - tp * tap.cpb;
+        const int kcol = tap.col0[tp] + cb * BK;
+        float4* base = reinterpret_cast<float4*>(sA + s * A_BYTES);
+#pragma unroll
+        for (int i = 0; i < BM / 16; ++i) {
+          const int r = r0 + i * 16;
+          const int logical = chunk ^ (r & 7);                 // 128B swizzle: physical chunk = logical ^ (row % 8)
+          const int k = kcol + logical * 4;
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(pro.a + k));
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(pro.b + k));
+          float4 x = base[r * 8 + chunk];
+          x.x = to_tf32(fmaxf(fmaf(x.x, sc.x, sh.x), 0.f));
+          x.y = to_tf32(fmaxf(fmaf(x.y, sc.y, sh.y), 0.f));
+          x.z = to_tf32(fmaxf(fmaf(x.z, sc.z, sh.z), 0.f));
+          x.w = to_tf32(fmaxf(fmaf(x.w, sc.w, sh.w), 0.f));
+          base[r * 8 + chunk] = x;
+        }
+        fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core's async proxy
+        mbar_arrive(&ready[s]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn();
+
+// 2-D fp32 row-major [rows][cols] with leading dimension ld (floats); box = 32 columns x box_rows rows, 128B swizzle
+CUtensorMap make_map_2d(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool round_tf32);
+
+template <int BN, int STAGES, class Pro, class Epi>
+inline void tgemm(Launches& L, cudaStream_t st, const char* tag, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
+                  const TapMap& tap, int ntaps, Pro pro, Epi epi) {
+  if (M <= 0 || N <= 0) return;
+  auto kern = tgemm_kernel<BN, STAGES, Pro, Epi>;
+  constexpr int SMEM = smem_bytes(BN, STAGES);
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
+  const int nkb = tap.cpb * ntaps;
+  Scope sc(L, st, tag, 2.0 * M * N * K);
+  kern<<<grid, Pro::kOn ? 320 : 192, SMEM, st>>>(tmA, tmB, nkb, tap, pro, epi);
+}
+
+}  // namespace tc
+}  // namespace cbx
+
+// =====================================================================================================================
+// FCM head 3x3 convolutions (xvector.py:61-127) as implicit GEMMs on tcgen05.
+// Activations are [row][F][32] (time-major, then frequency, channels contiguous).  One CTA computes BR time rows x F_out
+// frequencies (= 120 of the 128 UMMA rows) x 32 output channels.  Each of the 9 taps is one K block of 32 input
+// channels, fetched by ONE 4-D TMA box {32 ch, 1 parity, F_out freqs, BR rows}: the tensor is viewed as
+// [row][F/2][parity][32] for the frequency-stride-2 convs, so the stride disappears into the coordinates, and
+// frequency / time zero padding is TMA out-of-bounds fill.  A 10th tap (other tensor map) carries the residual block's
+// 1x1 stride-2 shortcut conv.
+namespace cbx {
+namespace tc {
+
+struct FcmTap { int src, parity, f0, dr; };
+struct FcmParams {
+  int ntaps; FcmTap tap[10];
+  int F_out, BR, rows, row_base;          // rows of this sub-chunk; row_base = row coordinate of sub-chunk row 0 in the maps
+  const float* bias; const float* res; float* out; const int32_t* row_clip;
+};
+
+constexpr int FCM_STAGES = 4;
+constexpr int fcm_smem_bytes() { return FCM_STAGES * (BM * BK * 4 + 32 * BK * 4) + 1024 + 256; }
+
+static __global__ void __launch_bounds__(192)
+fcm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                   const __grid_constant__ CUtensorMap tmB, FcmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int STAGES = FCM_STAGES, BN = 32;
+  constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  uint64_t* empty = full + STAGES;
+  uint64_t* accum = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * p.BR;
+  const int m_valid = p.BR * p.F_out;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < p.ntaps; ++kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], m_valid * BK * 4 + B_BYTES);
+        const FcmTap t = p.tap[kb];
+        tma_load_4d(sA + s * A_BYTES, t.src ? &tmA2 : &tmA, &full[s], 0, t.parity, t.f0, p.row_base + r0 + t.dr);
+        tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * BK, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+      for (int kb = 0; kb < p.ntaps; ++kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint64_t ad = make_desc_sw128(smem_u32(sA + s * A_BYTES));
+        const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_tf32(tmem_base, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (kb | k) != 0);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accum);
+    }
+  } else {
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int ml = q * 32 + lane;
+    float v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), v);
+    const int lr = ml / p.F_out;
+    const int row = r0 + lr;
+    if (ml < m_valid && row < p.rows) {
+      const size_t o = ((size_t)row * p.F_out + (ml - lr * p.F_out)) * kFcmC;
+      const bool live = p.row_clip[row] >= 0;
+      if (p.res) {
+        const float4* rr = reinterpret_cast<const float4*>(p.res + o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float4 x = rr[i]; v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w; }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = live ? fmaxf(v[i] + __ldg(p.bias + i), 0.f) : 0.f;
+      float4* oo = reinterpret_cast<float4*>(p.out + o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) oo[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
+}
+
+// [rows][F][32] fp32 activation viewed as {32, P, F/P, rows}; box {32, 1, F_out, BR}
+CUtensorMap make_map_fcm(const float* base, int rows, int F, int P, int F_out, int BR);
+
+}  // namespace tc
+}  // namespace cbx

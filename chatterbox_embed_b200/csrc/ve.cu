@@ -4,6 +4,8 @@
 
 #include "cbx_internal.h"
 #include "sgemm.cuh"
+#include "tc.cuh"
+#include "epi.cuh"
 
 namespace cbx {
 
@@ -275,10 +277,23 @@ void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st) {
   const int rows = ch.slots * kVePartial;
   const int nb = (ch.slots + LSTM_MT - 1) / LSTM_MT;
   // layer 0: projection once per mel frame (partials overlap: hop 77 < 160), then the recurrence gathers rows
-  sgemm(L, st, "lstm_xw0_gemm", ch.mel_rows, kVeGates, kVeMels, PlainA{ch.mel, kVeMels}, W.wih0, kVeMels, StoreBias{ch.xw0, kVeGates, W.bias[0]});
+  const bool tcm = c->mode == 1;
+  if (tcm) {
+    CUtensorMap tmA = tc::make_map_2d(ch.mel, ch.mel_rows, kVeMels, kVeMels, tc::BM, true);
+    tc::tgemm<128, 3>(L, st, "lstm_xw0_gemm", tmA, W.tm_wih[0], ch.mel_rows, kVeGates, kVeMels, tc::plain_map(kVeMels), 1, tc::NoPrologue{},
+                      tc::EpiBias{ch.xw0, kVeGates, W.bias[0], ch.mel_rows});
+  } else {
+    sgemm(L, st, "lstm_xw0_gemm", ch.mel_rows, kVeGates, kVeMels, PlainA{ch.mel, kVeMels}, W.wih0, kVeMels, StoreBias{ch.xw0, kVeGates, W.bias[0]});
+  }
   { Scope sc(L, st, "lstm_rec_kernel", 2.0 * ch.slots * kVePartial * kVeHidden * kVeGates); lstm_rec_kernel<true><<<nb, 256, 0, st>>>(ch.xw0, ch.slot_row, W.whhT[0], ch.hseq, ch.slots); }
   for (int l = 1; l < 3; ++l) {
-    sgemm(L, st, "lstm_xw_gemm", rows, kVeGates, kVeHidden, PlainA{ch.hseq, kVeHidden}, W.wih[l], kVeHidden, StoreBias{ch.xw, kVeGates, W.bias[l]});
+    if (tcm) {
+      CUtensorMap tmA = tc::make_map_2d(ch.hseq, rows, kVeHidden, kVeHidden, tc::BM, true);
+      tc::tgemm<128, 3>(L, st, "lstm_xw_gemm", tmA, W.tm_wih[l], rows, kVeGates, kVeHidden, tc::plain_map(kVeHidden), 1, tc::NoPrologue{},
+                        tc::EpiBias{ch.xw, kVeGates, W.bias[l], rows});
+    } else {
+      sgemm(L, st, "lstm_xw_gemm", rows, kVeGates, kVeHidden, PlainA{ch.hseq, kVeHidden}, W.wih[l], kVeHidden, StoreBias{ch.xw, kVeGates, W.bias[l]});
+    }
     { Scope sc(L, st, "lstm_rec_kernel", 2.0 * ch.slots * kVePartial * kVeHidden * kVeGates); lstm_rec_kernel<false><<<nb, 256, 0, st>>>(ch.xw, ch.slot_row, W.whhT[l], ch.hseq, ch.slots); }
   }
   { Scope sc(L, st, "ve_proj_kernel"); ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hseq, W.wpT, W.bp, ch.pemb); }

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "cbx_internal.h"
+#include "tc.cuh"
 
 namespace cbx {
 namespace {
@@ -106,6 +107,11 @@ int load_ve(cbx_ctx* c, const TensorMap& t) {
   W.wih[0] = nullptr;
   int rc = pk.upload(c, &W.blob);
   if (rc) return rc;
+  W.wih[0] = W.wih0;
+  for (int l = 0; l < 3; ++l) {
+    const int in = l == 0 ? kVeMels : H;
+    W.tm_wih[l] = tc::make_map_2d(W.wih[l], G, in, in, 128, true);
+  }
   W.loaded = true;
   return CBX_OK;
 }
@@ -241,6 +247,16 @@ int load_xv(cbx_ctx* c, const TensorMap& t) {
   }
   int rc = pk.upload(c, &W.blob);
   if (rc) return rc;
+  W.tm_tdnn = tc::make_map_2d(W.tdnn.w, kTdnnC, W.tdnn.K, W.tdnn.K, 128, true);
+  for (int i = 0; i < 52; ++i) {
+    W.tm_w1[i] = tc::make_map_2d(W.dense[i].w1, kBnC, W.dense[i].cin, W.dense[i].cin, 128, true);
+    W.tm_wl[i] = tc::make_map_2d(W.dense[i].wl, kGrowth, 3 * kBnC, 3 * kBnC, 32, true);
+  }
+  for (int l = 0; l < 2; ++l)
+    for (int b = 0; b < 2; ++b)
+      for (int k = 0; k < 2; ++k) W.tm_res[l][b][k] = tc::make_map_2d(W.res[l][b][k].w, kFcmC, W.res[l][b][k].K, W.res[l][b][k].K, 32, true);
+  W.tm_head2 = tc::make_map_2d(W.head_conv2.w, kFcmC, 288, 288, 32, true);
+  for (int b = 0; b < 3; ++b) W.tm_tr[b] = tc::make_map_2d(W.transit[b].w, W.transit[b].cout, W.transit[b].cin, W.transit[b].cin, 128, true);
   W.loaded = true;
   return CBX_OK;
 }

@@ -8,6 +8,8 @@
 
 #include "cbx_internal.h"
 #include "sgemm.cuh"
+#include "tc.cuh"
+#include "epi.cuh"
 
 namespace cbx {
 
@@ -304,25 +306,63 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
       const long long npos = (long long)rows * kKMels;
       { Scope sc(L, st, "fcm_conv1_kernel"); fcm_conv1_kernel<<<(unsigned)((npos + 7) / 8), 256, 0, st>>>(ch.fbank, ch.cmn_sum, ch.fb_row_clip, W.conv1_w, W.conv1_b, b0, s.r0, rows, ch.fb_rows); }
     }
-    auto conv = [&](const ConvW& w, const float* in, int F_in, int F_out, int sf, const float* sc, int F_sc, const float* res, float* out) {
-      sgemm(L, st, "fcm_conv_gemm", rows * F_out, kFcmC, w.K, FcmConvA{in, F_in, F_out, sf, sc, F_sc}, w.w, w.K, FcmEpi{out, w.bias, res, rc, F_out});
+    // in: [row][F_in][32] (pad row in front), optional shortcut source sc [row][F_sc][32], residual res / out [row][F_out][32]
+    auto conv = [&](const ConvW& w, const CUtensorMap& tmw, const float* in, int F_in, int F_out, int sf, const float* sc, int F_sc,
+                    const float* res, float* out) {
+      if (c->mode == 1) {
+        const int BR = 120 / F_out;                 // 3 / 6 / 12 time rows per CTA -> 120 of the 128 UMMA rows
+        const int prows = ch.fcm_rows + 2;
+        tc::FcmParams p{};
+        // the maps start at the buffer's pad row, so sub-chunk row 0 has row coordinate 1
+        CUtensorMap tmA = tc::make_map_fcm(in - (size_t)F_in * kFcmC, prows, F_in, sf, F_out, BR);
+        CUtensorMap tmA2 = sc ? tc::make_map_fcm(sc - (size_t)F_sc * kFcmC, prows, F_sc, 2, F_out, BR) : tmA;
+        p.ntaps = sc ? 10 : 9;
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw) {
+            tc::FcmTap& t = p.tap[kh * 3 + kw];
+            t.src = 0; t.dr = kw - 1;
+            if (sf == 1) { t.parity = 0; t.f0 = kh - 1; }
+            else { t.parity = kh == 1 ? 0 : 1; t.f0 = kh == 0 ? -1 : 0; }      // f_in = 2 f_out + kh - 1
+          }
+        if (sc) p.tap[9] = tc::FcmTap{1, 0, 0, 0};
+        p.F_out = F_out; p.BR = BR; p.rows = rows; p.row_base = 1;
+        p.bias = w.bias; p.res = res; p.out = out; p.row_clip = rc;
+        static bool configured = false;
+        if (!configured) { cudaFuncSetAttribute(tc::fcm_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::fcm_smem_bytes()); configured = true; }
+        Scope scp(L, st, "fcm_conv_gemm", 2.0 * rows * F_out * kFcmC * w.K);
+        tc::fcm_conv_tc_kernel<<<(rows + BR - 1) / BR, 192, tc::fcm_smem_bytes(), st>>>(tmA, tmA2, tmw, p);
+      } else {
+        sgemm(L, st, "fcm_conv_gemm", rows * F_out, kFcmC, w.K, FcmConvA{in, F_in, F_out, sf, sc, F_sc}, w.w, w.K, FcmEpi{out, w.bias, res, rc, F_out});
+      }
     };
     // layer1: 80 -> 40
-    conv(W.res[0][0][0], b0, 80, 40, 2, nullptr, 0, nullptr, b1);
-    conv(W.res[0][0][1], b1, 40, 40, 1, b0, 80, nullptr, b2);
-    conv(W.res[0][1][0], b2, 40, 40, 1, nullptr, 0, nullptr, b1);
-    conv(W.res[0][1][1], b1, 40, 40, 1, nullptr, 0, b2, b2);
+    conv(W.res[0][0][0], W.tm_res[0][0][0], b0, 80, 40, 2, nullptr, 0, nullptr, b1);
+    conv(W.res[0][0][1], W.tm_res[0][0][1], b1, 40, 40, 1, b0, 80, nullptr, b2);
+    conv(W.res[0][1][0], W.tm_res[0][1][0], b2, 40, 40, 1, nullptr, 0, nullptr, b1);
+    conv(W.res[0][1][1], W.tm_res[0][1][1], b1, 40, 40, 1, nullptr, 0, b2, b2);
     // layer2: 40 -> 20
-    conv(W.res[1][0][0], b2, 40, 20, 2, nullptr, 0, nullptr, b4);
-    conv(W.res[1][0][1], b4, 20, 20, 1, b2, 40, nullptr, b5);
-    conv(W.res[1][1][0], b5, 20, 20, 1, nullptr, 0, nullptr, b4);
-    conv(W.res[1][1][1], b4, 20, 20, 1, nullptr, 0, b5, b5);
+    conv(W.res[1][0][0], W.tm_res[1][0][0], b2, 40, 20, 2, nullptr, 0, nullptr, b4);
+    conv(W.res[1][0][1], W.tm_res[1][0][1], b4, 20, 20, 1, b2, 40, nullptr, b5);
+    conv(W.res[1][1][0], W.tm_res[1][1][0], b5, 20, 20, 1, nullptr, 0, nullptr, b4);
+    conv(W.res[1][1][1], W.tm_res[1][1][1], b4, 20, 20, 1, nullptr, 0, b5, b5);
     // head.conv2: 20 -> 10, written straight into the chunk-level [row][f*32+c] buffer
-    conv(W.head_conv2, b5, 20, 10, 2, nullptr, 0, nullptr, ch.fcm_out + (size_t)s.r0 * kFcmOut);
+    conv(W.head_conv2, W.tm_head2, b5, 20, 10, 2, nullptr, 0, nullptr, ch.fcm_out + (size_t)s.r0 * kFcmOut);
   }
 
   const int M = ch.td_rows;
-  sgemm(L, st, "tdnn_gemm", M, kTdnnC, W.tdnn.K, TdnnA{ch.fcm_out, ch.fb_rows}, W.tdnn.w, W.tdnn.K, BiasReluMaskEpi{ch.cat1, 512, W.tdnn.bias, ch.td_row_clip});
+  const bool tcm = c->mode == 1;
+  if (tcm) {
+    // stride-2 conv: view the FCM output as [fb_rows/2][640] so that output row m reads the row pairs m-1, m, m+1
+    CUtensorMap tmA = tc::make_map_2d(ch.fcm_out, ch.fb_rows / 2, 2 * kFcmOut, 2 * kFcmOut, tc::BM, true);
+    tc::TapMap tap{};
+    tap.cpb = kFcmOut / tc::BK;
+    const int sh[5] = {-1, -1, 0, 0, 1}, c0[5] = {0, kFcmOut, 0, kFcmOut, 0};
+    for (int i = 0; i < 5; ++i) { tap.shift[i] = sh[i]; tap.col0[i] = c0[i]; }
+    tc::tgemm<128, 3>(L, st, "tdnn_gemm", tmA, W.tm_tdnn, M, kTdnnC, W.tdnn.K, tap, 5, tc::NoPrologue{},
+                      tc::EpiBiasReluMask{ch.cat1, 512, W.tdnn.bias, ch.td_row_clip, M});
+  } else {
+    sgemm(L, st, "tdnn_gemm", M, kTdnnC, W.tdnn.K, TdnnA{ch.fcm_out, ch.fb_rows}, W.tdnn.w, W.tdnn.K, BiasReluMaskEpi{ch.cat1, 512, W.tdnn.bias, ch.td_row_clip});
+  }
 
   static const int kLayers[3] = {12, 24, 16};
   static const int kDil[3] = {1, 2, 2};
@@ -332,19 +372,39 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
   for (int b = 0; b < 3; ++b) {
     float* cat = cats[b];
     const int ld = lds[b];
+    CUtensorMap tm_cat, tm_u;
+    tc::TapMap tap_local{};
+    if (tcm) {
+      tm_cat = tc::make_map_2d(cat, M, ld, ld, tc::BM, false);        // fp32: the prologue warps round after BN+ReLU
+      tm_u = tc::make_map_2d(ch.u, M, kBnC, kBnC, tc::BM, true);
+      tap_local.cpb = kBnC / tc::BK;
+      for (int t = 0; t < 3; ++t) tap_local.shift[t] = (t - 1) * kDil[b];
+    }
     for (int i = 0; i < kLayers[b]; ++i, ++li) {
       const DenseLayerW& D = W.dense[li];
-      sgemm(L, st, "dense_bottleneck_gemm", M, kBnC, D.cin, BnReluA{cat, ld, D.a1, D.b1}, D.w1, D.cin, BiasReluMaskEpi{ch.u, kBnC, D.t2, ch.td_row_clip});
+      if (tcm)
+        tc::tgemm<128, 3>(L, st, "dense_bottleneck_gemm", tm_cat, W.tm_w1[li], M, kBnC, D.cin, tc::plain_map(D.cin), 1,
+                          tc::BnReluPrologue{D.a1, D.b1}, tc::EpiBiasReluMask{ch.u, kBnC, D.t2, ch.td_row_clip, M});
+      else
+        sgemm(L, st, "dense_bottleneck_gemm", M, kBnC, D.cin, BnReluA{cat, ld, D.a1, D.b1}, D.w1, D.cin, BiasReluMaskEpi{ch.u, kBnC, D.t2, ch.td_row_clip});
       if (ch.segs > 0) {
         { Scope sc(L, st, "seg_sum_kernel"); seg_sum_kernel<<<ch.segs, 128, 0, st>>>(ch.u, ch.plan, ch.seg_clip, ch.seg_sum); }
         { Scope sc(L, st, "cam_gate_kernel"); cam_gate_kernel<<<ch.segs, 128, 0, st>>>(ch.seg_sum, ch.plan, ch.seg_clip, D, ch.gate); }
       }
-      sgemm(L, st, "dense_local_gemm", M, kGrowth, 3 * kBnC, LocalConvA{ch.u, kDil[b], M}, D.wl, 3 * kBnC, GateEpi{cat, ld, D.cin, ch.gate, ch.td_row_seg});
+      if (tcm)
+        tc::tgemm<32, 4>(L, st, "dense_local_gemm", tm_u, W.tm_wl[li], M, kGrowth, 3 * kBnC, tap_local, 3, tc::NoPrologue{},
+                         tc::EpiGate{cat, ld, D.cin, ch.gate, ch.td_row_seg, M});
+      else
+        sgemm(L, st, "dense_local_gemm", M, kGrowth, 3 * kBnC, LocalConvA{ch.u, kDil[b], M}, D.wl, 3 * kBnC, GateEpi{cat, ld, D.cin, ch.gate, ch.td_row_seg});
     }
     const TransitW& T = W.transit[b];
     float* out = b == 0 ? ch.cat2 : (b == 1 ? ch.cat3 : ch.tr3);
     const int ldo = b == 2 ? kStatsC : 1024;
-    sgemm(L, st, "transit_gemm", M, T.cout, T.cin, BnReluA{cat, ld, T.a, T.b}, T.w, T.cin, MaskEpi{out, ldo, ch.td_row_clip});
+    if (tcm)
+      tc::tgemm<128, 3>(L, st, "transit_gemm", tm_cat, W.tm_tr[b], M, T.cout, T.cin, tc::plain_map(T.cin), 1,
+                        tc::BnReluPrologue{T.a, T.b}, tc::EpiMask{out, ldo, ch.td_row_clip, M});
+    else
+      sgemm(L, st, "transit_gemm", M, T.cout, T.cin, BnReluA{cat, ld, T.a, T.b}, T.w, T.cin, MaskEpi{out, ldo, ch.td_row_clip});
   }
   { Scope sc(L, st, "stats_pool_kernel"); stats_pool_kernel<<<ch.n_clips, 512, 0, st>>>(ch.tr3, ch.plan, W.out_a, W.out_b, ch.stats); }
   { Scope sc(L, st, "xv_final_kernel"); xv_final_kernel<<<ch.n_clips, 256, 0, st>>>(ch.stats, ch.plan, W.fin_w, W.fin_b, xv_out, status); }
