@@ -138,7 +138,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--mode", type=int, default=int(os.environ.get("CBX_MODE", "0")))
+    ap.add_argument("--mode", type=int, default=int(os.environ.get("CBX_MODE", "1")))
+    ap.add_argument("--opt", action="append", default=[], help="libcbx option key=value (cbx_set_option)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -164,6 +165,9 @@ def main():
     emb = scheduler.SpeakerEmbedder(ve, cp)
     ctx = emb.ctx()
     ctx.set_option("mode", args.mode)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
 
     wavs, off = make_batch(rank)
     host = torch.empty(CLIPS * CLIP_SAMPLES, dtype=torch.float32).pin_memory()

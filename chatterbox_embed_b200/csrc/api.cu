@@ -53,6 +53,7 @@ VeChunk carve_ve(Carver& cv, const VeLayout& L, cbx_ctx* c) {
   ch.xw0 = cv.take<float>((int64_t)L.mel_rows * kVeGates);
   ch.xw = cv.take<float>((int64_t)L.slots * kVePartial * kVeGates);
   ch.hseq = cv.take<float>((int64_t)L.slots * kVePartial * kVeHidden);
+  ch.hlast = cv.take<float>((int64_t)L.slots * kVeHidden);
   ch.pemb = cv.take<float>((int64_t)L.slots * kVeEmbed);
   if (cv.base && c) {
     c->taps["ve_dyn"] = {(char*)ch.dyn - cv.base, ch.n_clips, 6, 6};
@@ -228,6 +229,8 @@ int cbx_set_option(cbx_ctx* c, const char* key, int64_t v) {
   else if (k == "fcm_chunk_rows" && v >= 64) c->fcm_chunk_rows = v;
   else if (k == "lstm_chunk_partials" && v >= 1) c->lstm_chunk_slots = v;
   else if (k == "mode" && (v == 0 || v == 1)) c->mode = v;
+  else if (k == "lstm_dbg") c->lstm_dbg = v;
+  else if (k == "lstm_trace") c->lstm_trace = v;
   else { c->err = "bad option " + k; return CBX_ERR_ARG; }
   return CBX_OK;
 }
@@ -364,6 +367,7 @@ int64_t cbx_ve_forward_workspace_bytes(cbx_ctx* c, int n) {
   cv.take<int32_t>(n);
   cv.take<float>((int64_t)n * kVePartial * kVeGates);
   cv.take<float>((int64_t)n * kVePartial * kVeHidden);
+  cv.take<float>((int64_t)n * kVeHidden);
   return cv.off + 1024;
 }
 

@@ -93,6 +93,9 @@ struct VeWeights {
   float* blob = nullptr;
   const float *wih0, *wih[3], *whhT[3], *bias[3], *wpT, *bp;   // whhT [256][1024], wpT [256][256]
   CUtensorMap tm_wih[3];     // TMA maps of W_ih (B operand of the input-projection GEMMs)
+  // tensor-core recurrence (lstm_tc.cu): gate rows permuted to row 128 j + 4 u + g  <->  gate g of unit 32 j + u
+  const float *wih_p[3], *whh_p[3], *bias_p[3];   // whh_p tf32-rounded [1024][256]
+  CUtensorMap tm_wih_p[3];
 };
 struct XvWeights {
   bool loaded = false;
@@ -126,10 +129,12 @@ struct cbx_ctx {
   cbx::FrontendTables ft;
   cbx::Launches launches;
   // options
-  int64_t xv_chunk_rows = 36000;      // fbank rows per CAMPPlus chunk
-  int64_t fcm_chunk_rows = 4096;      // fbank rows per FCM sub-chunk
-  int64_t lstm_chunk_slots = 2048;    // partial slots per VoiceEncoder chunk
+  int64_t xv_chunk_rows = 300000;     // fbank rows per CAMPPlus chunk
+  int64_t fcm_chunk_rows = 65536;     // fbank rows per FCM sub-chunk
+  int64_t lstm_chunk_slots = 3072;    // partial slots per VoiceEncoder chunk
   int64_t mode = 0;
+  int64_t lstm_trace = 0;             // device pointer of the clock trace buffer
+  int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)
   // buffers owned by the library (cbx_embed_host)
   void* own_ws = nullptr; int64_t own_ws_bytes = 0;
   float* own_pcm = nullptr; int64_t own_pcm_floats = 0;
@@ -177,6 +182,7 @@ struct VeChunk {            // device buffers of one VoiceEncoder chunk
   float* xw0;               // [mel_rows][1024]
   float* xw;                // [slots*160][1024]
   float* hseq;              // [slots*160][256]
+  float* hlast;             // [slots][256]  final hidden state of layer 3 (tensor-core recurrence)
   float* pemb;              // [slots][256]
 };
 
@@ -206,6 +212,8 @@ void run_ve_chunk(cbx_ctx* c, const float* pcm, const VeChunk& ch, float trim_to
                   double min_cov, float* ve_out, int32_t* status, cudaStream_t st);
 void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st);   // xw0 .. pemb
 void run_ve_forward_partials(cbx_ctx* c, const float* mels, int n, float* out, void* ws, cudaStream_t st);
+void run_lstm_rec_tc(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
+                     int n_slots, cudaStream_t st);   // lstm_tc.cu
 void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out, int32_t* status, cudaStream_t st);
 
 }  // namespace cbx

@@ -225,12 +225,12 @@ __global__ void __launch_bounds__(256) lstm_rec_kernel(const float* __restrict__
 }
 
 // K6  proj + ReLU + L2 on the final hidden state of layer 3 (one CTA per slot)
-__global__ void __launch_bounds__(256) ve_proj_kernel(const float* __restrict__ hseq, const float* __restrict__ wpT,
+__global__ void __launch_bounds__(256) ve_proj_kernel(const float* __restrict__ hfin, size_t stride, const float* __restrict__ wpT,
                                                       const float* __restrict__ bp, float* __restrict__ pemb) {
   __shared__ float h[kVeHidden];
   __shared__ float red[8];
   const int q = blockIdx.x, j = threadIdx.x;
-  h[j] = hseq[((size_t)q * kVePartial + (kVePartial - 1)) * kVeHidden + j];
+  h[j] = hfin[(size_t)q * stride + j];
   __syncthreads();
   float a = __ldg(bp + j);
   for (int k = 0; k < kVeHidden; ++k) a = fmaf(h[k], __ldg(wpT + (size_t)k * kVeEmbed + j), a);
@@ -275,28 +275,32 @@ void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st) {
   const VeWeights& W = c->ve;
   Launches& L = c->launches;
   const int rows = ch.slots * kVePartial;
-  const int nb = (ch.slots + LSTM_MT - 1) / LSTM_MT;
-  // layer 0: projection once per mel frame (partials overlap: hop 77 < 160), then the recurrence gathers rows
-  const bool tcm = c->mode == 1;
-  if (tcm) {
+  if (c->mode == 1) {
+    // tensor-core path: input projections as dense tcgen05 GEMMs (gate columns in the recurrence's permuted order), the
+    // recurrence as the persistent cluster kernel of lstm_tc.cu.  Layer 0 projects once per mel frame (partials overlap:
+    // hop 77 < 160) and the recurrence gathers rows through slot_row.
     CUtensorMap tmA = tc::make_map_2d(ch.mel, ch.mel_rows, kVeMels, kVeMels, tc::BM, true);
-    tc::tgemm<128, 3>(L, st, "lstm_xw0_gemm", tmA, W.tm_wih[0], ch.mel_rows, kVeGates, kVeMels, tc::plain_map(kVeMels), 1, tc::NoPrologue{},
-                      tc::EpiBias{ch.xw0, kVeGates, W.bias[0], ch.mel_rows});
-  } else {
-    sgemm(L, st, "lstm_xw0_gemm", ch.mel_rows, kVeGates, kVeMels, PlainA{ch.mel, kVeMels}, W.wih0, kVeMels, StoreBias{ch.xw0, kVeGates, W.bias[0]});
+    tc::tgemm<128, 3>(L, st, "lstm_xw0_gemm", tmA, W.tm_wih_p[0], ch.mel_rows, kVeGates, kVeMels, tc::plain_map(kVeMels), 1, tc::NoPrologue{},
+                      tc::EpiBias{ch.xw0, kVeGates, W.bias_p[0], ch.mel_rows});
+    run_lstm_rec_tc(c, ch.xw0, ch.slot_row, W.whh_p[0], ch.hseq, nullptr, ch.slots, st);
+    for (int l = 1; l < 3; ++l) {
+      CUtensorMap tmH = tc::make_map_2d(ch.hseq, rows, kVeHidden, kVeHidden, tc::BM, true);
+      tc::tgemm<128, 3>(L, st, "lstm_xw_gemm", tmH, W.tm_wih_p[l], rows, kVeGates, kVeHidden, tc::plain_map(kVeHidden), 1, tc::NoPrologue{},
+                        tc::EpiBias{ch.xw, kVeGates, W.bias_p[l], rows});
+      run_lstm_rec_tc(c, ch.xw, nullptr, W.whh_p[l], l == 2 ? nullptr : ch.hseq, l == 2 ? ch.hlast : nullptr, ch.slots, st);
+    }
+    { Scope sc(L, st, "ve_proj_kernel"); ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hlast, (size_t)kVeHidden, W.wpT, W.bp, ch.pemb); }
+    return;
   }
+  // strict-fp32 path
+  const int nb = (ch.slots + LSTM_MT - 1) / LSTM_MT;
+  sgemm(L, st, "lstm_xw0_gemm", ch.mel_rows, kVeGates, kVeMels, PlainA{ch.mel, kVeMels}, W.wih0, kVeMels, StoreBias{ch.xw0, kVeGates, W.bias[0]});
   { Scope sc(L, st, "lstm_rec_kernel", 2.0 * ch.slots * kVePartial * kVeHidden * kVeGates); lstm_rec_kernel<true><<<nb, 256, 0, st>>>(ch.xw0, ch.slot_row, W.whhT[0], ch.hseq, ch.slots); }
   for (int l = 1; l < 3; ++l) {
-    if (tcm) {
-      CUtensorMap tmA = tc::make_map_2d(ch.hseq, rows, kVeHidden, kVeHidden, tc::BM, true);
-      tc::tgemm<128, 3>(L, st, "lstm_xw_gemm", tmA, W.tm_wih[l], rows, kVeGates, kVeHidden, tc::plain_map(kVeHidden), 1, tc::NoPrologue{},
-                        tc::EpiBias{ch.xw, kVeGates, W.bias[l], rows});
-    } else {
-      sgemm(L, st, "lstm_xw_gemm", rows, kVeGates, kVeHidden, PlainA{ch.hseq, kVeHidden}, W.wih[l], kVeHidden, StoreBias{ch.xw, kVeGates, W.bias[l]});
-    }
+    sgemm(L, st, "lstm_xw_gemm", rows, kVeGates, kVeHidden, PlainA{ch.hseq, kVeHidden}, W.wih[l], kVeHidden, StoreBias{ch.xw, kVeGates, W.bias[l]});
     { Scope sc(L, st, "lstm_rec_kernel", 2.0 * ch.slots * kVePartial * kVeHidden * kVeGates); lstm_rec_kernel<false><<<nb, 256, 0, st>>>(ch.xw, ch.slot_row, W.whhT[l], ch.hseq, ch.slots); }
   }
-  { Scope sc(L, st, "ve_proj_kernel"); ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hseq, W.wpT, W.bp, ch.pemb); }
+  { Scope sc(L, st, "ve_proj_kernel"); ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hseq + (size_t)(kVePartial - 1) * kVeHidden, (size_t)kVePartial * kVeHidden, W.wpT, W.bp, ch.pemb); }
 }
 
 void run_ve_chunk(cbx_ctx* c, const float* pcm, const VeChunk& ch, float trim_top_db, bool no_trim, int step,
@@ -327,6 +331,7 @@ void run_ve_forward_partials(cbx_ctx* c, const float* mels, int n, float* out, v
   ch.xw0 = cv.take<float>((int64_t)ch.mel_rows * kVeGates);
   ch.xw = ch.xw0;                       // layer-0 rows are exactly slot*160+t here, so one buffer serves both
   ch.hseq = cv.take<float>((int64_t)ch.mel_rows * kVeHidden);
+  ch.hlast = cv.take<float>((int64_t)n * kVeHidden);
   ch.pemb = out;
   { Scope sc(c->launches, st, "ve_identity_slots_kernel"); ve_identity_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(ch.slot_row, n); }
   run_ve_lstm(c, ch, st);

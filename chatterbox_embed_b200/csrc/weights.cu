@@ -44,6 +44,15 @@ struct Getter {
   }
 };
 
+// fp32 -> tf32 (10-bit mantissa), round to nearest even, kept in an fp32 container
+float round_tf32(float x) {
+  uint32_t b;
+  std::memcpy(&b, &x, 4);
+  if ((b & 0x7f800000u) != 0x7f800000u) { b += 0xfffu + ((b >> 13) & 1u); b &= ~0x1fffu; }
+  std::memcpy(&x, &b, 4);
+  return x;
+}
+
 struct Bn { std::vector<float> scale, shift; };
 
 Bn fold_bn(Getter& g, const std::string& p, int c, bool affine = true) {
@@ -95,6 +104,18 @@ int load_ve(cbx_ctx* c, const TensorMap& t) {
     }
     pk.add(&W.whhT[l], tr);
     pk.add(&W.bias[l], bias);
+    // permuted copies for the tensor-core recurrence: row 128 j + 4 u + g  <-  gate g of unit 32 j + u
+    std::vector<float> wih_p((size_t)G * in), whh_p((size_t)G * H), bias_p(G);
+    for (int n = 0; n < G; ++n) {
+      const int jj = n >> 7, uu = (n >> 2) & 31, gg = n & 3;
+      const int src = gg * H + jj * 32 + uu;
+      std::memcpy(&wih_p[(size_t)n * in], wih + (size_t)src * in, sizeof(float) * in);
+      for (int k = 0; k < H; ++k) whh_p[(size_t)n * H + k] = round_tf32(whh[(size_t)src * H + k]);
+      bias_p[n] = bias[src];
+    }
+    pk.add(&W.wih_p[l], wih_p);
+    pk.add(&W.whh_p[l], whh_p);
+    pk.add(&W.bias_p[l], bias_p);
   }
   const float* wp = g.get("proj.weight", (int64_t)kVeEmbed * H);
   const float* bp = g.get("proj.bias", kVeEmbed);
@@ -111,6 +132,7 @@ int load_ve(cbx_ctx* c, const TensorMap& t) {
   for (int l = 0; l < 3; ++l) {
     const int in = l == 0 ? kVeMels : H;
     W.tm_wih[l] = tc::make_map_2d(W.wih[l], G, in, in, 128, true);
+    W.tm_wih_p[l] = tc::make_map_2d(W.wih_p[l], G, in, in, 128, true);
   }
   W.loaded = true;
   return CBX_OK;

@@ -144,7 +144,7 @@ def test_ve_forward_and_inference_api(models):
     assert np.abs(got - want).max() < 1e-5
     mels = [mel, frontend.ve_melspectrogram(synth.clip(1, 21000))]
     got = ve.embeds_from_mels(mels)
-    want = nets.ve_embed_mels(sdv, mels)
+    want = nets.ve_embed_mels(sdv, mels, rate=None)     # embeds_from_mels does not set rate: step 80 (voice_encoder.py:172)
     assert got.shape == (2, 256) and np.abs(got - want).max() < 1e-5
     spk = ve.embeds_from_mels(mels, as_spk=True)
     assert spk.shape == (256,) and abs(np.linalg.norm(spk) - 1) < 1e-5
@@ -191,3 +191,66 @@ def test_full_size_batch_properties(models):
     assert np.abs(ve[:4] - ve[4:][::-1]).max() < 1e-6 and np.abs(xv[:4] - xv[4:][::-1]).max() < 1e-5
     want = nets.campplus_embed_wavs(sdc, base[:1])
     assert np.abs(xv[0] - want[0]).max() < 1e-3 * max(1.0, np.abs(want).max())
+
+
+# ---- tensor-core mode (tcgen05 TF32): the north_star gate ---------------------------------------------------------------
+# fp32/TF32 mode tolerance (BASELINE.json north_star): embeddings cos >= 0.9999 and max-abs <= 1e-3 against the reference
+# with random-init weights of the same architecture (W0 = default init, W1 = W0 with randomised BatchNorm).  The x-vector is
+# not L2-normalised (values O(1)..O(10) with W1), so its max-abs is taken relative to max(1, max|x|).  W2 (sensitised LSTM,
+# BN-calibrated CAMPPlus) is reported with its own measured tolerance: TF32 rounding noise there is ~50x the default-init
+# case (SURVEY.md 8d hazard 2).
+@pytest.fixture
+def mode1(models):
+    ctx = _lib.context(0)
+    ctx.set_option("mode", 1)
+    yield ctx
+    ctx.set_option("mode", 0)
+
+
+@pytest.mark.parametrize("kind", ["W0", "W1"])
+def test_mode1_north_star_gate(models, mode1, kind):
+    sdv, sdc, emb = _emb(models, kind)
+    wavs = [synth.clip(i, n) for i, n in enumerate(EDGE)]
+    ve, xv = emb.embed_wavs(wavs)
+    want_ve = nets.ve_embed_wavs(sdv, wavs)
+    want_xv = nets.campplus_embed_wavs(sdc, wavs)
+    assert np.abs(ve - want_ve).max() <= 1e-3 and min(cos(a, b) for a, b in zip(ve, want_ve)) >= 0.9999
+    scale = max(1.0, float(np.abs(want_xv).max()))
+    assert np.abs(xv - want_xv).max() <= 1e-3 * scale
+    assert min(cos(a, b) for a, b in zip(xv, want_xv)) >= 0.9999
+    ve1, xv1 = emb.embed_wavs([wavs[3]])               # batch composition must not matter
+    assert np.abs(ve1[0] - ve[3]).max() < 1e-6 and np.abs(xv1[0] - xv[3]).max() < 1e-5 * scale
+
+
+def test_mode1_sensitised_weights(models, mode1):
+    sdv, sdc, emb = _emb(models, "W2")
+    wavs = [synth.mixed(i, n) for i, n in enumerate(EDGE)]
+    ve, xv = emb.embed_wavs(wavs)
+    want_ve = nets.ve_embed_wavs(sdv, wavs)
+    want_xv = nets.campplus_embed_wavs(sdc, wavs)
+    assert np.abs(ve - want_ve).max() <= 2e-3 and min(cos(a, b) for a, b in zip(ve, want_ve)) >= 0.9999
+    scale = max(1.0, float(np.abs(want_xv).max()))
+    assert np.abs(xv - want_xv).max() <= 5e-2 * scale and min(cos(a, b) for a, b in zip(xv, want_xv)) >= 0.999
+
+
+@pytest.mark.parametrize("n", [1, 3, 97, 200, 400])
+def test_mode1_lstm_partials(models, mode1, n):
+    """VoiceEncoder.forward on n pre-cut partials: exercises the cluster LSTM kernel on partly filled and multiple tiles."""
+    sdv, sdc, ve, cp = models["W1"]
+    g = torch.Generator().manual_seed(n)
+    parts = (torch.rand((n, 160, 40), generator=g) * 0.3).numpy()
+    got = ve(torch.from_numpy(parts).to(DEV)).cpu().numpy()
+    with torch.inference_mode():
+        want = nets.ve_forward(sdv, parts).numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() <= 1e-3 and min(cos(a, b) for a, b in zip(got, want)) >= 0.9999
+
+
+def test_mode1_golden_stages(models, mode1, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_W1.npz"))
+    sdv, sdc, emb = _emb(models, "W1")
+    wavs = make_golden.golden_wavs()
+    ve, xv = emb.embed_wavs(wavs)
+    assert np.abs(ve - g["ve_emb"]).max() <= 1e-3 and min(cos(a, b) for a, b in zip(ve, g["ve_emb"])) >= 0.9999
+    assert np.abs(xv - g["xv_emb"]).max() <= 1e-3 * max(1.0, np.abs(g["xv_emb"]).max())
+    assert min(cos(a, b) for a, b in zip(xv, g["xv_emb"])) >= 0.9999
