@@ -18,6 +18,7 @@ constexpr int kSR = 16000;
 constexpr int kVeNfft = 400, kVeHop = 160, kVeBins = 201, kVeMels = 40;
 constexpr int kVePartial = 160, kVeHidden = 256, kVeEmbed = 256, kVeGates = 1024;
 constexpr int kVeSpecN = 2 * kVeBins;      // interleaved re/im columns of the DFT GEMM
+constexpr int kVeTcBins = 200, kKTcBins = 256;   // bins (incl. one zero pad) of the tensor-core front-end GEMMs
 // Kaldi fbank as called by xvector.py:50 (torchaudio kaldi.py defaults, 80 bins)
 constexpr int kKWin = 400, kKHop = 160, kKPad = 512, kKBins = 257, kKMels = 80;
 constexpr int kKSpecN = 2 * kKBins;
@@ -117,6 +118,12 @@ struct FrontendTables {
   const float *ve_mel;     // [40][201]
   const float *k_dft;      // [514][400]  dc-removal, pre-emphasis, povey window folded
   const float *k_mel;      // [80][257]
+  // tensor-core front end (frontend_tc.cu): DFT rows of bins 1.. only (bin 0 and the Nyquist bin carry zero mel weight in
+  // both banks), split hi/lo for 3xTF32, and the 2-sparse bin -> mel tables
+  const float *ve_dft_hi, *ve_dft_lo;   // [400][400]  bins 1..199 + one zero pair
+  const float *k_dft_hi, *k_dft_lo;     // [512][400]  bins 1..255 + one zero pair
+  const float *ve_bins, *k_bins;        // [200][4], [256][4]
+  CUtensorMap tm_ve_hi[2], tm_ve_lo[2], tm_k_hi, tm_k_lo;
 };
 
 }  // namespace cbx
@@ -212,6 +219,9 @@ void run_ve_chunk(cbx_ctx* c, const float* pcm, const VeChunk& ch, float trim_to
                   double min_cov, float* ve_out, int32_t* status, cudaStream_t st);
 void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st);   // xw0 .. pemb
 void run_ve_forward_partials(cbx_ctx* c, const float* mels, int n, float* out, void* ws, cudaStream_t st);
+// frontend_tc.cu: frames -> 3xTF32 DFT GEMM -> power -> sparse mel (-> log) in one kernel
+void run_ve_mel_tc(cbx_ctx* c, const float* pcm, const VeChunk& ch, cudaStream_t st);
+void run_kaldi_fbank_tc(cbx_ctx* c, const float* pcm, const XvChunk& ch, cudaStream_t st);
 void run_lstm_rec_tc(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
                      int n_slots, cudaStream_t st);   // lstm_tc.cu
 void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out, int32_t* status, cudaStream_t st);

@@ -1,0 +1,258 @@
+// Audio front-ends on the sm_100a tensor cores: framing + window + DFT as ONE GEMM per 128-frame tile, then |X|^2, the
+// mel filterbank and (Kaldi) the log, fused in the epilogue.  Nothing but the mel/fbank rows is written to HBM.
+//
+//   VoiceEncoder mel  (melspec.py:26-64):   reflect-padded frames [T x 400] . (Hann-folded DFT)^T [400 x 2*199]  -> 40 Slaney mels
+//   Kaldi fbank       (xvector.py:50, torchaudio kaldi.py:514-645):
+//                                           raw frames [T x 400] . (DC-removal/pre-emphasis/Povey-folded 512-pt DFT)^T [400 x 2*255]
+//                                           -> 80 HTK mels -> log(max(., eps))
+//
+// Precision: plain TF32 is not acceptable here (the log exposes near-empty bins: errors of 4.5 in the log domain on chirps,
+// SURVEY.md 8d hazard 3), so both operands are split hi + lo and the product is 3 MMAs: A_hi.B_hi + A_lo.B_hi + A_hi.B_lo.
+//
+// Warp roles (192 threads): warp 0 = TMA producer of the DFT-matrix tiles (B operand, hi and lo maps), warp 1 = MMA issuer,
+// warps 2..5 = frame producers (gather PCM -> split hi/lo -> 128B-swizzled K-major A stages in shared memory) and, after the
+// last K block, the epilogue (TMEM -> power -> 2-sparse mel accumulation in shared memory -> log -> coalesced store).
+// The accumulator is the whole TMEM: [128 frames x up to 512 columns] fp32 (re, im interleaved).
+#include <math.h>
+
+#include "cbx_internal.h"
+#include "tc.cuh"
+
+namespace cbx {
+namespace fe {
+
+using namespace tc;
+
+constexpr int KTOT = 400;                       // both front-ends: 400-sample frames
+constexpr int NKB = (KTOT + BK - 1) / BK;       // 13 K blocks of 32 (the last holds 16)
+constexpr int SA = 2;                           // A stages: hi + lo, 16 KB each
+constexpr int SB = 4;                           // B slots of 32 KB: [256 x 32] of either the hi or the lo matrix
+constexpr int A_BYTES = BM * BK * 4;            // 16 KB
+constexpr int B_BYTES = 256 * BK * 4;           // 32 KB
+constexpr int SMEM_BYTES = SA * 2 * A_BYTES + SB * B_BYTES + 1024 + 128 * 16 + 256;
+
+struct RowDesc { long long base; int start; int n; };   // element k of the frame = pcm[base + reflect(start + k, n)]; n == 0: zero row
+
+// Kaldi frames: snip_edges, no padding (kaldi.py:63-67): frame t of clip c = pcm[off_c + 160 t ...]
+struct KaldiRows {
+  const ClipPlan* plan; const int32_t* row_clip;
+  __device__ RowDesc operator()(int row) const {
+    const int c = row_clip[row];
+    if (c < 0) return RowDesc{0, 0, 0};
+    const ClipPlan cp = plan[c];
+    return RowDesc{cp.pcm_off, (row - cp.fb_row) * kKHop, 0x7fffffff};
+  }
+  __device__ bool live(int row) const { return row_clip[row] >= 0; }
+};
+// VoiceEncoder frames: centred, reflect-padded by 200 on the trimmed clip (melspec.py:57-64, voice_encoder.py:267)
+struct VeRows {
+  const ClipPlan* plan; const ClipDyn* dyn; const int32_t* row_clip;
+  __device__ RowDesc operator()(int row) const {
+    const int c = row_clip[row];
+    if (c < 0) return RowDesc{0, 0, 0};
+    const ClipPlan cp = plan[c];
+    const ClipDyn d = dyn[c];
+    const int t = row - cp.mel_row;
+    if (t >= d.ve_frames_eff) return RowDesc{0, 0, 0};
+    return RowDesc{cp.pcm_off + d.trim_s, t * kVeHop - kVeNfft / 2, d.trim_e - d.trim_s};
+  }
+  __device__ bool live(int) const { return true; }      // rows past the clip are zero frames -> zero mels (voice_encoder.py:176-179)
+};
+
+template <class Rows, int NB1, int NMEL, bool LOG>
+__global__ void __launch_bounds__(192, 1)
+dftmel_kernel(const __grid_constant__ CUtensorMap tmHi0, const __grid_constant__ CUtensorMap tmLo0,
+              const __grid_constant__ CUtensorMap tmHi1, const __grid_constant__ CUtensorMap tmLo1,
+              const float* __restrict__ pcm, Rows rows_fn, const float4* __restrict__ bintab, float* __restrict__ out, int rows) {
+  constexpr int NB0 = 256;
+  constexpr int NTOT = NB0 + NB1;
+  constexpr int MELLD = NMEL + 1;
+  static_assert(BM * MELLD * 4 <= SA * 2 * A_BYTES, "mel accumulators overlay the A stages");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                   // [SA][hi | lo][128 x 128 B]
+  uint8_t* sB = smem + SA * 2 * A_BYTES;                // [SB][256 x 128 B]
+  RowDesc* rdesc = reinterpret_cast<RowDesc*>(sB + SB * B_BYTES);     // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rdesc + BM);
+  uint64_t* a_full = bars;                 // [SA] 128 producer arrivals
+  uint64_t* a_empty = bars + SA;           // [SA] MMA commit
+  uint64_t* b_full = bars + 2 * SA;        // [SB] TMA bytes
+  uint64_t* b_empty = b_full + SB;         // [SB] MMA commit
+  uint64_t* accum = b_empty + SB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  float* melacc = reinterpret_cast<float*>(sA);         // [128][MELLD], after the K loop
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmHi0); tma_prefetch_desc(&tmLo0); tma_prefetch_desc(&tmHi1); tma_prefetch_desc(&tmLo1);
+    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp >= 2) {
+    const int r = threadIdx.x - 64;
+    rdesc[r] = (m0 + r < rows) ? rows_fn(m0 + r) : RowDesc{0, 0, 0};
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: per K block the slots are  hi(cols 0..255), lo(0..255), hi(256..), lo(256..)
+    if (lane == 0) {
+      int it = 0;
+      for (int kb = 0; kb < NKB; ++kb)
+        for (int q = 0; q < 4; ++q, ++it) {
+          const int s = it % SB, ph = (it / SB) & 1;
+          mbar_wait(&b_empty[s], ph ^ 1);
+          const int nb = q >> 1;
+          mbar_expect_tx(&b_full[s], (nb ? NB1 : NB0) * BK * 4);
+          const CUtensorMap* tm = nb ? ((q & 1) ? &tmLo1 : &tmHi1) : ((q & 1) ? &tmLo0 : &tmHi0);
+          tma_load_2d(sB + s * B_BYTES, tm, &b_full[s], kb * BK, nb * NB0);
+        }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc0 = make_idesc_tf32(BM, NB0), idesc1 = make_idesc_tf32(BM, NB1);
+      int it = 0;
+      for (int kb = 0; kb < NKB; ++kb) {
+        const int sa = kb % SA, pa = (kb / SA) & 1;
+        mbar_wait(&a_full[sa], pa);
+        tc_fence_after();
+        const uint64_t ahi = make_desc_sw128(smem_u32(sA + sa * 2 * A_BYTES));
+        const uint64_t alo = make_desc_sw128(smem_u32(sA + sa * 2 * A_BYTES + A_BYTES));
+        const int ksteps = (kb == NKB - 1) ? (KTOT - (NKB - 1) * BK) / UMMA_K : BK / UMMA_K;
+        for (int q = 0; q < 4; ++q, ++it) {
+          const int s = it % SB, ph = (it / SB) & 1;
+          mbar_wait(&b_full[s], ph);
+          tc_fence_after();
+          const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+          const int nb = q >> 1;
+          const uint32_t d = tmem_base + nb * NB0;
+          const uint32_t idesc = nb ? idesc1 : idesc0;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ko = (uint64_t)(k * UMMA_K * 4 >> 4);
+            if ((q & 1) == 0) {       // B_hi: A_hi.B_hi + A_lo.B_hi
+              umma_tf32(d, ahi + ko, bd + ko, idesc, (kb | k) != 0);
+              umma_tf32(d, alo + ko, bd + ko, idesc, 1);
+            } else {                  // B_lo: A_hi.B_lo
+              umma_tf32(d, ahi + ko, bd + ko, idesc, 1);
+            }
+          }
+          umma_commit(&b_empty[s]);
+        }
+        umma_commit(&a_empty[sa]);
+      }
+      umma_commit(accum);
+    }
+  } else {
+    // ===== frame producers: warp w fills rows [32 w', 32 w' + 32) of every A stage, lanes along K (coalesced PCM reads)
+    const int wq = warp - 2;
+    for (int kb = 0; kb < NKB; ++kb) {
+      const int sa = kb % SA, pa = (kb / SA) & 1;
+      const int k = kb * BK + lane;
+      // all 32 rows' loads in flight before the stage is even free (memory-level parallelism: the PCM comes from L2 / HBM)
+      float v[32];
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) {
+        const RowDesc d = rdesc[wq * 32 + rr];
+        int i = d.start + k;
+        if (i < 0) i = -i; else if (i >= d.n) i = 2 * (d.n - 1) - i;
+        v[rr] = (d.n > 0 && k < KTOT) ? __ldg(pcm + d.base + i) : 0.f;
+      }
+      mbar_wait(&a_empty[sa], pa ^ 1);
+      uint8_t* hi = sA + sa * 2 * A_BYTES;
+      uint8_t* lo = hi + A_BYTES;
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) {
+        const int r = wq * 32 + rr;
+        const float vh = to_tf32(v[rr]);
+        const float vl = to_tf32(v[rr] - vh);
+        const uint32_t o = r * 128 + ((((uint32_t)lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4;
+        *reinterpret_cast<float*>(hi + o) = vh;
+        *reinterpret_cast<float*>(lo + o) = vl;
+      }
+      fence_proxy_async();
+      mbar_arrive(&a_full[sa]);
+    }
+    // ===== epilogue: thread = frame row; D columns 2b, 2b+1 = re, im of bin b
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    float* acc = melacc + row * MELLD;
+#pragma unroll 1
+    for (int m = 0; m < NMEL; ++m) acc[m] = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < NTOT / 16; ++c) {
+      float v[16];
+      {
+        uint32_t* rv = reinterpret_cast<uint32_t*>(v);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(rv[0]), "=r"(rv[1]), "=r"(rv[2]), "=r"(rv[3]), "=r"(rv[4]), "=r"(rv[5]), "=r"(rv[6]), "=r"(rv[7]), "=r"(rv[8]),
+              "=r"(rv[9]), "=r"(rv[10]), "=r"(rv[11]), "=r"(rv[12]), "=r"(rv[13]), "=r"(rv[14]), "=r"(rv[15])
+            : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16))
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float pw = fmaf(v[2 * i], v[2 * i], v[2 * i + 1] * v[2 * i + 1]);
+        const float4 tb = __ldg(bintab + c * 8 + i);              // warp-uniform: {w0, w1, m0, m1}
+        const int ma = __float_as_int(tb.z), mb = __float_as_int(tb.w);
+        acc[ma] = fmaf(tb.x, pw, acc[ma]);
+        acc[mb] = fmaf(tb.y, pw, acc[mb]);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    // each warp owns the 32 rows it accumulated: write them out row by row, lanes along the mel axis
+    for (int rr = 0; rr < 32; ++rr) {
+      const int r = q * 32 + rr;
+      const int gr = m0 + r;
+      if (gr >= rows) break;
+      const bool live = rows_fn.live(gr);
+      for (int m = lane; m < NMEL; m += 32) {
+        float val = melacc[r * MELLD + m];
+        if (LOG) val = logf(fmaxf(val, 1.1920928955078125e-07f));
+        out[(size_t)gr * NMEL + m] = live ? val : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+template <class Rows, int NB1, int NMEL, bool LOG>
+void launch(cbx_ctx* c, cudaStream_t st, const char* tag, const CUtensorMap& hi0, const CUtensorMap& lo0, const CUtensorMap& hi1,
+            const CUtensorMap& lo1, const float* pcm, Rows rf, const float* bintab, float* out, int rows) {
+  if (rows <= 0) return;
+  auto kern = dftmel_kernel<Rows, NB1, NMEL, LOG>;
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); configured = true; }
+  Scope sc(c->launches, st, tag, 3.0 * 2.0 * rows * (256 + NB1) * KTOT);
+  kern<<<(rows + BM - 1) / BM, 192, SMEM_BYTES, st>>>(hi0, lo0, hi1, lo1, pcm, rf, reinterpret_cast<const float4*>(bintab), out, rows);
+}
+
+}  // namespace fe
+
+void run_ve_mel_tc(cbx_ctx* c, const float* pcm, const VeChunk& ch, cudaStream_t st) {
+  const FrontendTables& F = c->ft;
+  fe::launch<fe::VeRows, 2 * kVeTcBins - 256, kVeMels, false>(c, st, "ve_dftmel_tc_kernel", F.tm_ve_hi[0], F.tm_ve_lo[0], F.tm_ve_hi[1], F.tm_ve_lo[1],
+                                                            pcm, fe::VeRows{ch.plan, ch.dyn, ch.mel_row_clip}, F.ve_bins, ch.mel, ch.mel_rows);
+}
+
+void run_kaldi_fbank_tc(cbx_ctx* c, const float* pcm, const XvChunk& ch, cudaStream_t st) {
+  const FrontendTables& F = c->ft;
+  fe::launch<fe::KaldiRows, 2 * kKTcBins - 256, kKMels, true>(c, st, "kaldi_dftmel_tc_kernel", F.tm_k_hi, F.tm_k_lo, F.tm_k_hi, F.tm_k_lo,
+                                                             pcm, fe::KaldiRows{ch.plan, ch.fb_row_clip}, F.k_bins, ch.fbank, ch.fb_rows);
+}
+
+}  // namespace cbx

@@ -309,9 +309,13 @@ void run_ve_chunk(cbx_ctx* c, const float* pcm, const VeChunk& ch, float trim_to
   { Scope sc(L, st, "trim_plan_kernel"); trim_plan_kernel<<<ch.n_clips, 256, 0, st>>>(pcm, ch.plan, ch.dyn, ch.trim_scratch, trim_top_db, no_trim ? 1 : 0, step, min_cov); }
   cudaMemsetAsync(ch.mel_row_clip, 0xff, sizeof(int32_t) * ch.mel_rows, st);
   { Scope sc(L, st, "ve_maps_kernel"); ve_maps_kernel<<<ch.n_clips, 256, 0, st>>>(ch.plan, ch.dyn, step, ch.mel_row_clip, ch.slot_clip, ch.slot_row); }
-  sgemm(L, st, "ve_dft_gemm", ch.mel_rows, kVeSpecN, kVeNfft, VeFrameGather{pcm, ch.plan, ch.dyn, ch.mel_row_clip}, c->ft.ve_dft, kVeNfft,
-        StoreRowMajor{ch.spec, kVeSpecN});
-  { Scope sc(L, st, "ve_mel_kernel"); ve_mel_kernel<<<(ch.mel_rows + 7) / 8, 256, 0, st>>>(ch.spec, c->ft.ve_mel, ch.plan, ch.dyn, ch.mel_row_clip, ch.mel, ch.mel_rows); }
+  if (c->mode == 1) {
+    run_ve_mel_tc(c, pcm, ch, st);
+  } else {
+    sgemm(L, st, "ve_dft_gemm", ch.mel_rows, kVeSpecN, kVeNfft, VeFrameGather{pcm, ch.plan, ch.dyn, ch.mel_row_clip}, c->ft.ve_dft, kVeNfft,
+          StoreRowMajor{ch.spec, kVeSpecN});
+    { Scope sc(L, st, "ve_mel_kernel"); ve_mel_kernel<<<(ch.mel_rows + 7) / 8, 256, 0, st>>>(ch.spec, c->ft.ve_mel, ch.plan, ch.dyn, ch.mel_row_clip, ch.mel, ch.mel_rows); }
+  }
   run_ve_lstm(c, ch, st);
   { Scope sc(L, st, "ve_clip_mean_kernel"); ve_clip_mean_kernel<<<ch.n_clips, 256, 0, st>>>(ch.pemb, ch.plan, ch.dyn, ve_out, status); }
 }

@@ -296,6 +296,38 @@ double slaney_hz_to_mel(double f) {
   return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
 }
 
+// Tensor-core front-end tables.  Rows 2b, 2b+1 = re, im of DFT bin (first_bin + b), b < nbins - 1 (the last bin pair is
+// zero padding); each value v is stored as hi = tf32(v), lo = tf32(v - hi) for the 3xTF32 product (SURVEY.md 8d hazard 3).
+void split_dft(Packer& pk, const std::vector<double>& dd, int K, int first_bin, int nbins, const float** hi_slot, const float** lo_slot) {
+  std::vector<float> hi((size_t)2 * nbins * K, 0.f), lo((size_t)2 * nbins * K, 0.f);
+  for (int b = 0; b < nbins - 1; ++b)
+    for (int part = 0; part < 2; ++part)
+      for (int n = 0; n < K; ++n) {
+        const double v = dd[(size_t)(2 * (first_bin + b) + part) * K + n];
+        const float h = round_tf32((float)v);
+        hi[(size_t)(2 * b + part) * K + n] = h;
+        lo[(size_t)(2 * b + part) * K + n] = round_tf32((float)(v - (double)h));
+      }
+  pk.add(hi_slot, hi);
+  pk.add(lo_slot, lo);
+}
+// Per DFT bin: the (at most two) mel filters it feeds, {w0, w1, bits(m0), bits(m1)} -- triangular banks are 2-sparse per bin.
+void bin_table(Packer& pk, const std::vector<float>& bank, int nmel, int nbank_bins, int first_bin, int nbins, const float** slot) {
+  std::vector<float> t((size_t)4 * nbins, 0.f);
+  for (int b = 0; b < nbins; ++b) {
+    int m[2] = {0, 0}; float w[2] = {0.f, 0.f}; int cnt = 0;
+    const int k = first_bin + b;
+    if (b < nbins - 1 && k < nbank_bins)
+      for (int mm = 0; mm < nmel; ++mm) {
+        const float v = bank[(size_t)mm * nbank_bins + k];
+        if (v != 0.f && cnt < 2) { m[cnt] = mm; w[cnt] = v; ++cnt; }
+      }
+    t[4 * b] = w[0]; t[4 * b + 1] = w[1];
+    std::memcpy(&t[4 * b + 2], &m[0], 4); std::memcpy(&t[4 * b + 3], &m[1], 4);
+  }
+  pk.add(slot, t);
+}
+
 }  // namespace
 
 int build_frontend_tables(cbx_ctx* c) {
@@ -304,14 +336,17 @@ int build_frontend_tables(cbx_ctx* c) {
   const double PI = 3.14159265358979323846;
   {  // VoiceEncoder: periodic Hann folded into the 400-point DFT (melspec.py:57-64); rows 2k = re, 2k+1 = im
     std::vector<float> d((size_t)kVeSpecN * kVeNfft);
+    std::vector<double> dd((size_t)kVeSpecN * kVeNfft);
     for (int k = 0; k < kVeBins; ++k)
       for (int n = 0; n < kVeNfft; ++n) {
         double w = 0.5 - 0.5 * std::cos(2.0 * PI * n / kVeNfft);
         double ang = 2.0 * PI * (double)((k * n) % kVeNfft) / kVeNfft;
-        d[(size_t)(2 * k) * kVeNfft + n] = (float)(w * std::cos(ang));
-        d[(size_t)(2 * k + 1) * kVeNfft + n] = (float)(-w * std::sin(ang));
+        dd[(size_t)(2 * k) * kVeNfft + n] = w * std::cos(ang);
+        dd[(size_t)(2 * k + 1) * kVeNfft + n] = -w * std::sin(ang);
       }
+    for (size_t i = 0; i < d.size(); ++i) d[i] = (float)dd[i];
     pk.add(&F.ve_dft, d);
+    split_dft(pk, dd, kVeNfft, 1, kVeTcBins, &F.ve_dft_hi, &F.ve_dft_lo);
     // librosa.filters.mel(sr=16000,n_fft=400,n_mels=40,fmin=0,fmax=8000): Slaney scale + area norm (melspec.py:11-16)
     std::vector<double> edges(kVeMels + 2);
     const double m_lo = slaney_hz_to_mel(0.0), m_hi = slaney_hz_to_mel(8000.0);
@@ -326,12 +361,14 @@ int build_frontend_tables(cbx_ctx* c) {
         mel[(size_t)m * kVeBins + k] = (float)((double)tri * (2.0 / (edges[m + 2] - edges[m])));
       }
     pk.add(&F.ve_mel, mel);
+    bin_table(pk, mel, kVeMels, kVeBins, 1, kVeTcBins, &F.ve_bins);
   }
   {  // Kaldi: DC removal, pre-emphasis 0.97 (replicate-left), Povey window and zero-pad to 512 folded into
      // one [514][400] matrix (torchaudio kaldi.py:183-211).
     std::vector<double> pov(kKWin);
     for (int n = 0; n < kKWin; ++n) pov[n] = std::pow(0.5 - 0.5 * std::cos(2.0 * PI * n / (kKWin - 1)), 0.85);
     std::vector<float> d((size_t)kKSpecN * kKWin);
+    std::vector<double> dd((size_t)kKSpecN * kKWin);
     std::vector<double> y(kKWin + 1), z(kKWin);
     for (int col = 0; col < kKSpecN; ++col) {
       const int k = col >> 1;
@@ -347,9 +384,10 @@ int build_frontend_tables(cbx_ctx* c) {
         zbar += z[j];
       }
       zbar /= kKWin;
-      for (int j = 0; j < kKWin; ++j) d[(size_t)col * kKWin + j] = (float)(z[j] - zbar);
+      for (int j = 0; j < kKWin; ++j) { dd[(size_t)col * kKWin + j] = z[j] - zbar; d[(size_t)col * kKWin + j] = (float)(z[j] - zbar); }
     }
     pk.add(&F.k_dft, d);
+    split_dft(pk, dd, kKWin, 1, kKTcBins, &F.k_dft_hi, &F.k_dft_lo);
     // 80 HTK-mel triangles 20 Hz..8 kHz on the 512-point grid, slopes in mel, Nyquist bin weight 0 (kaldi.py:436-511)
     auto mel = [](double f) { return 1127.0 * std::log(1.0 + f / 700.0); };
     const double lo = mel(20.0), hi = mel(8000.0), delta = (hi - lo) / (kKMels + 1);
@@ -364,8 +402,18 @@ int build_frontend_tables(cbx_ctx* c) {
       }
     }
     pk.add(&F.k_mel, bank);
+    bin_table(pk, bank, kKMels, kKBins, 1, kKTcBins, &F.k_bins);
   }
-  return pk.upload(c, &F.blob);
+  int rc = pk.upload(c, &F.blob);
+  if (rc) return rc;
+  // TMA maps of the split DFT matrices (B operands of the front-end GEMM): boxes of 32 k x (256 | rest) rows
+  F.tm_ve_hi[0] = tc::make_map_2d(F.ve_dft_hi, 2 * kVeTcBins, kVeNfft, kVeNfft, 256, false);
+  F.tm_ve_lo[0] = tc::make_map_2d(F.ve_dft_lo, 2 * kVeTcBins, kVeNfft, kVeNfft, 256, false);
+  F.tm_ve_hi[1] = tc::make_map_2d(F.ve_dft_hi, 2 * kVeTcBins, kVeNfft, kVeNfft, 2 * kVeTcBins - 256, false);
+  F.tm_ve_lo[1] = tc::make_map_2d(F.ve_dft_lo, 2 * kVeTcBins, kVeNfft, kVeNfft, 2 * kVeTcBins - 256, false);
+  F.tm_k_hi = tc::make_map_2d(F.k_dft_hi, 2 * kKTcBins, kKWin, kKWin, 256, false);
+  F.tm_k_lo = tc::make_map_2d(F.k_dft_lo, 2 * kKTcBins, kKWin, kKWin, 256, false);
+  return CBX_OK;
 }
 
 }  // namespace cbx

@@ -289,7 +289,8 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
       i = j;
     }
   }
-  for (const Sub& s : subs) {
+  if (c->mode == 1) run_kaldi_fbank_tc(c, pcm, ch, st);
+  else for (const Sub& s : subs) {
     const int rows = s.r1 - s.r0;
     sgemm(L, st, "kaldi_dft_gemm", rows, kKSpecN, kKWin, KaldiFrameGather{pcm, ch.plan, ch.fb_row_clip, s.r0}, c->ft.k_dft, kKWin, StoreRM{ch.spec, kKSpecN});
     { Scope sc(L, st, "fbank_from_spec_kernel"); fbank_from_spec_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ch.spec, c->ft.k_mel, ch.fb_row_clip, ch.fbank, s.r0, rows); }
