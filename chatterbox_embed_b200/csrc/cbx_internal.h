@@ -222,6 +222,8 @@ void run_ve_forward_partials(cbx_ctx* c, const float* mels, int n, float* out, v
 // frontend_tc.cu: frames -> 3xTF32 DFT GEMM -> power -> sparse mel (-> log) in one kernel
 void run_ve_mel_tc(cbx_ctx* c, const float* pcm, const VeChunk& ch, cudaStream_t st);
 void run_kaldi_fbank_tc(cbx_ctx* c, const float* pcm, const XvChunk& ch, cudaStream_t st);
+void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const float* bias, const float* in, int F_in, int F_out, int sf,
+                     const float* sc, int F_sc, const float* res, float* out, const int32_t* row_clip, int rows, int prows, double flops);   // fcm_tc.cu
 void run_lstm_rec_tc(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
                      int n_slots, cudaStream_t st);   // lstm_tc.cu
 void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out, int32_t* status, cudaStream_t st);

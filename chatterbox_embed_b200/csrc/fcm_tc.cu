@@ -1,0 +1,221 @@
+// FCM head of CAMPPlus (xvector.py:61-127): the 3x3 convolutions as implicit GEMMs on tcgen05, one persistent kernel per
+// convolution.
+//
+// Activations are [time row][F][32 channels] fp32.  A CTA works on tiles of BR time rows.  For every tile ONE halo block of
+// the input -- (BR+2) rows x (F+2) frequencies x 32 channels, zero padding supplied by TMA out-of-bounds fill -- is brought
+// into shared memory (128B-swizzled rows of 32 channels); the nine taps are then nine tcgen05.mma groups whose A
+// descriptors are ROW-SHIFTED VIEWS of that one block (a shift of kw*(F+2)+kh rows), so the input crosses L2->SM once instead
+// of nine times.  The GEMM's M index therefore runs over (t, f') with f' in [0, F+2): the two extra positions per time row
+// are computed and dropped.  Frequency-stride-2 convs read two parity planes ({32, parity, F/2, rows} view of the tensor) so
+// the stride disappears into the TMA coordinates; a residual block's 1x1 stride-2 shortcut conv is a tenth tap on its own
+// plane.  Weights ([32][taps*32], BN folded) stay resident in shared memory for the CTA's lifetime; the fp32 accumulator
+// [128 x 32] is double-buffered in TMEM so the epilogue (bias, residual, ReLU, guard-row mask, 128-byte stores) of one tile
+// overlaps the MMAs of the next.
+#include "cbx_internal.h"
+#include "tc.cuh"
+
+namespace cbx {
+namespace fcm {
+
+using namespace tc;
+
+constexpr int STAGES = 3;
+constexpr int MAX_TAPS = 10;
+constexpr int W_BYTES = MAX_TAPS * 32 * 128;       // 40 KB: [tap][32 out channels][32 in channels]
+
+struct Plane { int par, f0, dr, nrows; uint32_t bytes, offset; };   // TMA box {32, 1, pitch, nrows} at (0, par, f0, row + dr)
+struct Tap { int plane, start; };                  // A rows start at row `start` of the plane
+struct Params {
+  int nplanes, ntaps;
+  Plane plane[3];
+  Tap tap[MAX_TAPS];
+  int pitch, BR, F_out, rows, row_base, ntiles;
+  uint32_t stage_bytes;
+  const float* bias; const float* res; float* out; const int32_t* row_clip;
+};
+
+__global__ void __launch_bounds__(192, 1)
+fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
+                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sW = smem;
+  uint8_t* sIn = smem + W_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + STAGES * p.stage_bytes + 2048);
+  uint64_t* full = bars;              // [STAGES]
+  uint64_t* empty = bars + STAGES;    // [STAGES]
+  uint64_t* tfull = empty + STAGES;   // [2] accumulator ready
+  uint64_t* tempty = tfull + 2;       // [2] accumulator drained (4 warp arrivals)
+  uint64_t* wfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm0); tma_prefetch_desc(&tmW);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    mbar_init(wfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wfull, p.ntaps * 32 * 128);
+      for (int t = 0; t < p.ntaps; ++t) tma_load_2d(sW + t * 4096, &tmW, wfull, t * 32, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint32_t bytes = 0;
+        for (int q = 0; q < p.nplanes; ++q) bytes += p.plane[q].bytes;
+        mbar_expect_tx(&full[s], bytes);
+        const int r0 = p.row_base + tile * p.BR;
+        for (int q = 0; q < p.nplanes; ++q) {
+          const Plane& pl = p.plane[q];
+          const CUtensorMap* tm = q == 0 ? &tm0 : (q == 1 ? &tm1 : &tm2);
+          tma_load_4d(sIn + s * p.stage_bytes + pl.offset, tm, &full[s], 0, pl.par, pl.f0, r0 + pl.dr);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, 32);
+      mbar_wait(wfull, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
+        const int a = it & 1, pa = (it >> 1) & 1;
+        mbar_wait(&tempty[a], pa ^ 1);
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t d = tmem_base + a * 32;
+        const uint32_t in = smem_u32(sIn + s * p.stage_bytes);
+        for (int t = 0; t < p.ntaps; ++t) {
+          const uint64_t ad = make_desc_sw128(in + p.plane[p.tap[t].plane].offset + p.tap[t].start * 128);
+          const uint64_t bd = make_desc_sw128(smem_u32(sW + t * 4096));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32(d, ad + (uint64_t)(k * 32 >> 4), bd + (uint64_t)(k * 32 >> 4), idesc, (t | k) != 0);
+        }
+        umma_commit(&empty[s]);
+        umma_commit(&tfull[a]);
+      }
+    }
+  } else {
+    // ===== epilogue: thread = output position (t, f') of the tile; f' >= F_out are the padding positions
+    const int q = warp & 3;
+    const int i = q * 32 + lane;
+    const int t = i / p.pitch, f = i - t * p.pitch;
+    const bool pos_ok = t < p.BR && f < p.F_out;
+    float bias[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) bias[c] = __ldg(p.bias + c);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int a = it & 1, pa = (it >> 1) & 1;
+      mbar_wait(&tfull[a], pa);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 32, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[a]);
+      const int row = tile * p.BR + t;
+      if (pos_ok && row < p.rows) {
+        const size_t o = ((size_t)row * p.F_out + f) * kFcmC;
+        const bool live = p.row_clip[row] >= 0;
+        if (p.res) {
+          const float4* rr = reinterpret_cast<const float4*>(p.res + o);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { const float4 x = rr[c]; v[4 * c] += x.x; v[4 * c + 1] += x.y; v[4 * c + 2] += x.z; v[4 * c + 3] += x.w; }
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = live ? fmaxf(v[c] + bias[c], 0.f) : 0.f;
+        float4* oo = reinterpret_cast<float4*>(p.out + o);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) oo[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+}
+
+// [prows][F][32] fp32 viewed as {32, P, F/P, prows}; box {32, 1, pitch, nrows}
+static CUtensorMap make_map(const float* base, int prows, int F, int P, int pitch, int nrows) {
+  CUtensorMap m;
+  memset(&m, 0, sizeof m);
+  cuuint64_t dims[4] = {32, (cuuint64_t)P, (cuuint64_t)(F / P), (cuuint64_t)prows};
+  cuuint64_t strides[3] = {128, (cuuint64_t)128 * P, (cuuint64_t)128 * F};
+  cuuint32_t box[4] = {32, 1, (cuuint32_t)pitch, (cuuint32_t)nrows};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  EncodeTiledFn fn = encode_fn();
+  CUresult r = fn ? fn(&m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+                  : CUDA_ERROR_NOT_FOUND;
+  if (r != CUDA_SUCCESS) fprintf(stderr, "libcbx: cuTensorMapEncodeTiled(fcm2) failed (%d) prows=%d F=%d P=%d pitch=%d nrows=%d\n", (int)r, prows, F, P, pitch, nrows);
+  return m;
+}
+
+}  // namespace fcm
+
+// in: [rows][F_in][32] with one pad row in front (in points at row 0, the map starts one row earlier); prows = rows of the
+// buffer including both pad rows; sf = frequency stride; sc: optional 1x1 stride-2 shortcut source [rows][2*F_out][32].
+void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const float* bias, const float* in, int F_in, int F_out, int sf,
+                     const float* sc, int F_sc, const float* res, float* out, const int32_t* row_clip, int rows, int prows, double flops) {
+  using namespace fcm;
+  Params p{};
+  const int pitch = sf == 1 ? F_out + 2 : F_out + 1;
+  const int BR = 128 / pitch;
+  p.pitch = pitch; p.BR = BR; p.F_out = F_out; p.rows = rows; p.row_base = 1; p.ntiles = (rows + BR - 1) / BR;
+  p.bias = bias; p.res = res; p.out = out; p.row_clip = row_clip;
+  auto plane_bytes = [&](int nrows) { return (uint32_t)(nrows * pitch * 128); };
+  auto align1k = [](uint32_t x) { return (x + 1023u) & ~1023u; };
+  CUtensorMap tm[3];
+  uint32_t off = 0;
+  int np = 0;
+  if (sf == 1) {
+    p.plane[np] = Plane{0, -1, -1, BR + 2, plane_bytes(BR + 2), off};
+    tm[np] = make_map(in - (size_t)F_in * kFcmC, prows, F_in, 1, pitch, BR + 2);
+    off += align1k(p.plane[np].bytes); ++np;
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) p.tap[kh * 3 + kw] = Tap{0, kw * pitch + kh};
+  } else {
+    p.plane[np] = Plane{0, 0, -1, BR + 2, plane_bytes(BR + 2), off};          // even input frequencies 2f
+    tm[np] = make_map(in - (size_t)F_in * kFcmC, prows, F_in, 2, pitch, BR + 2);
+    off += align1k(p.plane[np].bytes); ++np;
+    p.plane[np] = Plane{1, -1, -1, BR + 2, plane_bytes(BR + 2), off};         // odd input frequencies 2f-1 (index f-1)
+    tm[np] = tm[0];
+    off += align1k(p.plane[np].bytes); ++np;
+    for (int kw = 0; kw < 3; ++kw) {
+      p.tap[0 * 3 + kw] = Tap{1, kw * pitch};          // kh = 0: f_in = 2f - 1
+      p.tap[1 * 3 + kw] = Tap{0, kw * pitch};          // kh = 1: f_in = 2f
+      p.tap[2 * 3 + kw] = Tap{1, kw * pitch + 1};      // kh = 2: f_in = 2f + 1
+    }
+  }
+  p.ntaps = 9;
+  if (sc) {
+    p.plane[np] = Plane{0, 0, 0, BR, plane_bytes(BR), off};
+    tm[np] = make_map(sc - (size_t)F_sc * kFcmC, prows, F_sc, 2, pitch, BR);
+    off += align1k(p.plane[np].bytes);
+    p.tap[9] = Tap{np, 0};
+    p.ntaps = 10; ++np;
+  }
+  for (int q = np; q < 3; ++q) tm[q] = tm[0];
+  p.nplanes = np;
+  p.stage_bytes = off;
+  const int smem = W_BYTES + STAGES * (int)off + 2048 + 1024 + 256;
+  static int configured = 0;
+  if (configured < smem) { cudaFuncSetAttribute(fcm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); configured = 220 * 1024; }
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+  const int grid = p.ntiles < nsm ? p.ntiles : nsm;
+  Scope scp(c->launches, st, "fcm_conv_gemm", flops);
+  fcm_conv_kernel<<<grid, 192, smem, st>>>(tm[0], tm[1], tm[2], tmW, p);
+}
+
+}  // namespace cbx

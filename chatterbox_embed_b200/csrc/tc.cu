@@ -90,3 +90,59 @@ extern "C" int cbx_test_tgemm(cbx_ctx* c, const float* A, int64_t lda, const flo
   CBX_CUDA_OK(c, cudaGetLastError());
   return CBX_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Unit test: A operand descriptors that start at an arbitrary 128-byte row of a swizzled tile (the implicit-GEMM convs
+// read their taps as row-shifted views of ONE halo tile in shared memory).  C[128][32] = A[shift .. shift+128) . W^T
+namespace cbx { namespace tc {
+__global__ void __launch_bounds__(128) shift_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                                                         float* C, int shift, int use_base_offset) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                  // [256 rows][128 B]
+  uint8_t* sW = smem + 256 * 128;      // [32 rows][128 B]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sW + 32 * 128);
+  uint64_t* accum = full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(full, 1); mbar_init(accum, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(tmem_slot, 32);
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(full, 256 * 128 + 32 * 128);
+    tma_load_2d(sA, &tmA, full, 0, 0);
+    tma_load_2d(sA + 128 * 128, &tmA, full, 0, 128);
+    tma_load_2d(sW, &tmW, full, 0, 0);
+    mbar_wait(full, 0);
+    tc_fence_after();
+    const uint32_t a_addr = smem_u32(sA) + shift * 128;
+    uint64_t ad = make_desc_sw128(a_addr);
+    if (use_base_offset) ad |= (uint64_t)((a_addr >> 7) & 7) << 49;
+    const uint64_t bd = make_desc_sw128(smem_u32(sW));
+    constexpr uint32_t idesc = make_idesc_tf32(128, 32);
+    for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, ad + (uint64_t)(k * 32 >> 4), bd + (uint64_t)(k * 32 >> 4), idesc, k != 0);
+    umma_commit(accum);
+  }
+  mbar_wait(accum, 0);
+  tc_fence_after();
+  float v[32];
+  tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), v);
+  for (int i = 0; i < 32; ++i) C[(size_t)(warp * 32 + lane) * 32 + i] = v[i];
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
+}
+}}  // namespace cbx::tc
+
+extern "C" int cbx_test_shift_gemm(cbx_ctx* c, const float* A /*[256][32]*/, const float* W /*[32][32]*/, float* C /*[128][32]*/,
+                                   int shift, int use_base_offset) {
+  if (!c) return CBX_ERR_ARG;
+  cudaSetDevice(c->device);
+  CUtensorMap tmA = tc::make_map_2d(A, 256, 32, 32, 128, true);
+  CUtensorMap tmW = tc::make_map_2d(W, 32, 32, 32, 32, true);
+  const int smem = 256 * 128 + 32 * 128 + 1024 + 64;
+  tc::shift_gemm_kernel<<<1, 128, smem>>>(tmA, tmW, C, shift, use_base_offset);
+  CBX_CUDA_OK(c, cudaDeviceSynchronize());
+  return CBX_OK;
+}

@@ -115,6 +115,46 @@ __global__ void __launch_bounds__(256) fcm_conv1_kernel(const float* __restrict_
   out[((size_t)lr * kKMels + f) * kFcmC + co] = v;
 }
 
+// conv1, one warp per fbank row: the three CMN'd input rows go to shared memory once, lane = output channel (weights in
+// registers), 128-byte coalesced stores.
+__global__ void __launch_bounds__(256) fcm_conv1_rows_kernel(const float* __restrict__ fbank, const float* __restrict__ cmn_mean,
+                                                             const int32_t* __restrict__ row_clip, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ out,
+                                                             int row0, int rows, int fb_rows) {
+  __shared__ float xin[8][3][kKMels + 2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lr = blockIdx.x * 8 + warp;
+  if (lr >= rows) return;
+  const int r = row0 + lr;
+  const int c = row_clip[r];
+  float* o = out + (size_t)lr * kKMels * kFcmC + lane;
+  if (c < 0) {
+    for (int f = 0; f < kKMels; ++f) o[(size_t)f * kFcmC] = 0.f;
+    return;
+  }
+  for (int kw = 0; kw < 3; ++kw) {
+    const int rr = r + kw - 1;
+    const bool ok = rr >= 0 && rr < fb_rows && row_clip[rr] == c;
+    for (int ff = lane; ff < kKMels; ff += 32)
+      xin[warp][kw][ff + 1] = ok ? fbank[(size_t)rr * kKMels + ff] - cmn_mean[c * kKMels + ff] : 0.f;
+    if (lane == 0) { xin[warp][kw][0] = 0.f; xin[warp][kw][kKMels + 1] = 0.f; }
+  }
+  float wr[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) wr[i] = __ldg(w + lane * 9 + i);
+  const float b = __ldg(bias + lane);
+  __syncwarp();
+#pragma unroll 4
+  for (int f = 0; f < kKMels; ++f) {
+    float acc = b;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) acc = fmaf(xin[warp][kw][f + kh], wr[kh * 3 + kw], acc);
+    o[(size_t)f * kFcmC] = fmaxf(acc, 0.f);
+  }
+}
+
 // 3x3 conv over [row][F_in][32] as an implicit GEMM (k = (kh*3+kw)*32 + ci), optionally with the block's
 // 1x1 stride-2 shortcut conv appended as 32 extra K columns (k >= 288).
 struct FcmConvA {
@@ -305,33 +345,14 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     float* b4 = ch.b4 + 20 * kFcmC; float* b5 = ch.b5 + 20 * kFcmC;
     {
       const long long npos = (long long)rows * kKMels;
-      { Scope sc(L, st, "fcm_conv1_kernel"); fcm_conv1_kernel<<<(unsigned)((npos + 7) / 8), 256, 0, st>>>(ch.fbank, ch.cmn_sum, ch.fb_row_clip, W.conv1_w, W.conv1_b, b0, s.r0, rows, ch.fb_rows); }
+      if (c->mode == 1) { Scope sc(L, st, "fcm_conv1_kernel"); fcm_conv1_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ch.fbank, ch.cmn_sum, ch.fb_row_clip, W.conv1_w, W.conv1_b, b0, s.r0, rows, ch.fb_rows); }
+      else { Scope sc(L, st, "fcm_conv1_kernel"); fcm_conv1_kernel<<<(unsigned)((npos + 7) / 8), 256, 0, st>>>(ch.fbank, ch.cmn_sum, ch.fb_row_clip, W.conv1_w, W.conv1_b, b0, s.r0, rows, ch.fb_rows); }
     }
     // in: [row][F_in][32] (pad row in front), optional shortcut source sc [row][F_sc][32], residual res / out [row][F_out][32]
     auto conv = [&](const ConvW& w, const CUtensorMap& tmw, const float* in, int F_in, int F_out, int sf, const float* sc, int F_sc,
                     const float* res, float* out) {
       if (c->mode == 1) {
-        const int BR = 120 / F_out;                 // 3 / 6 / 12 time rows per CTA -> 120 of the 128 UMMA rows
-        const int prows = ch.fcm_rows + 2;
-        tc::FcmParams p{};
-        // the maps start at the buffer's pad row, so sub-chunk row 0 has row coordinate 1
-        CUtensorMap tmA = tc::make_map_fcm(in - (size_t)F_in * kFcmC, prows, F_in, sf, F_out, BR);
-        CUtensorMap tmA2 = sc ? tc::make_map_fcm(sc - (size_t)F_sc * kFcmC, prows, F_sc, 2, F_out, BR) : tmA;
-        p.ntaps = sc ? 10 : 9;
-        for (int kh = 0; kh < 3; ++kh)
-          for (int kw = 0; kw < 3; ++kw) {
-            tc::FcmTap& t = p.tap[kh * 3 + kw];
-            t.src = 0; t.dr = kw - 1;
-            if (sf == 1) { t.parity = 0; t.f0 = kh - 1; }
-            else { t.parity = kh == 1 ? 0 : 1; t.f0 = kh == 0 ? -1 : 0; }      // f_in = 2 f_out + kh - 1
-          }
-        if (sc) p.tap[9] = tc::FcmTap{1, 0, 0, 0};
-        p.F_out = F_out; p.BR = BR; p.rows = rows; p.row_base = 1;
-        p.bias = w.bias; p.res = res; p.out = out; p.row_clip = rc;
-        static bool configured = false;
-        if (!configured) { cudaFuncSetAttribute(tc::fcm_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::fcm_smem_bytes()); configured = true; }
-        Scope scp(L, st, "fcm_conv_gemm", 2.0 * rows * F_out * kFcmC * w.K);
-        tc::fcm_conv_tc_kernel<<<(rows + BR - 1) / BR, 192, tc::fcm_smem_bytes(), st>>>(tmA, tmA2, tmw, p);
+        run_fcm_conv_tc(c, st, tmw, w.bias, in, F_in, F_out, sf, sc, F_sc, res, out, rc, rows, ch.fcm_rows + 2, 2.0 * rows * F_out * kFcmC * w.K);
       } else {
         sgemm(L, st, "fcm_conv_gemm", rows * F_out, kFcmC, w.K, FcmConvA{in, F_in, F_out, sf, sc, F_sc}, w.w, w.K, FcmEpi{out, w.bias, res, rc, F_out});
       }
