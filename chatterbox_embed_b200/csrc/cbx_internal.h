@@ -86,6 +86,7 @@ struct DenseLayerW {
   const float *wl;           // [32][3*128] local conv, k = tap*128 + c
   const float *wc1, *bc1;    // [64][128], [64]
   const float *wc2, *bc2;    // [32][64], [32]
+  const float *wc1T, *wc2T;  // [128][64], [64][32] transposed copies
 };
 struct TransitW { int cin, cout; const float *a, *b, *w; };
 

@@ -33,6 +33,55 @@ struct EpiBiasReluMask {         // out = row is a real frame ? relu(acc + bias)
   }
 };
 
+// Bottleneck of a CAM dense layer: u = row is a real frame ? relu(acc + bias) : 0, stored, AND the per-segment column sums of
+// u that the CAM context needs (seg_pooling / mean over T, xvector.py:214-231) accumulated on the fly: the 32 rows a warp
+// holds are summed with a transposed butterfly (31 shuffles per 32 columns) and one 128-byte red.add per segment present.
+// Warp-collective: every lane of the warp must call it (rows >= M take part as "no segment").
+struct EpiBiasReluMaskSegsum {
+  float* out; int ld; const float* bias; const int32_t* row_seg; float* seg_sum; int M;
+  __device__ void operator()(int m, int n0, float* v) const {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int seg = m < M ? row_seg[m] : -1;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = seg >= 0 ? fmaxf(v[i] + __ldg(bias + n0 + i), 0.f) : 0.f;
+    if (m < M) store32(out + (size_t)m * ld + n0, v);
+    unsigned rem = __ballot_sync(full, seg >= 0);
+    while (rem) {
+      const int s = __shfl_sync(full, seg, __ffs(rem) - 1);
+      rem &= ~__ballot_sync(full, seg == s);
+      const bool mine = seg == s;
+      float a[16], b[8], c[4], d[2];
+      {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float lo = mine ? v[i] : 0.f, hi = mine ? v[16 + i] : 0.f;
+          a[i] = (up ? hi : lo) + __shfl_xor_sync(full, up ? lo : hi, 16);
+        }
+      }
+      {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = (up ? a[8 + i] : a[i]) + __shfl_xor_sync(full, up ? a[i] : a[8 + i], 8);
+      }
+      {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[i] = (up ? b[4 + i] : b[i]) + __shfl_xor_sync(full, up ? b[i] : b[4 + i], 4);
+      }
+      {
+        const bool up = lane & 2;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) d[i] = (up ? c[2 + i] : c[i]) + __shfl_xor_sync(full, up ? c[i] : c[2 + i], 2);
+      }
+      const bool up = lane & 1;
+      const float e = (up ? d[1] : d[0]) + __shfl_xor_sync(full, up ? d[0] : d[1], 1);
+      atomicAdd(seg_sum + (size_t)s * kBnC + n0 + lane, e);      // lane l holds the sum of column n0 + l
+    }
+  }
+};
+
 struct EpiMask {                 // out = row is a real frame ? acc : 0                (transit layers)
   float* out; int ld; const int32_t* row_clip; int M;
   __device__ void operator()(int m, int n0, float* v) const {

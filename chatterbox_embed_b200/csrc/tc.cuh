@@ -261,6 +261,123 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
+// ---------------------------------------------------------------- pre-activation GEMM (BN + ReLU on the A operand)
+//   C[m][n] = epi( sum_k relu(a[k] * X[m][k] + b[k]) * W[n][k] )
+// The D-TDNN layers are pre-activation (BN -> ReLU -> conv, xvector.py:266-271), every layer with its OWN BatchNorm over the
+// shared concat buffer, so the normalisation cannot be folded into weights and must happen while the A operand is staged.
+// Here producer warps do the staging themselves: coalesced 16-byte global loads of X (many in flight), BN + ReLU + tf32
+// rounding in registers, one store into the 128B-swizzled K-major stage.  Two producer groups of 4 warps alternate K blocks,
+// so one group's load latency hides behind the other's arithmetic.  W tiles come by TMA; MMA / epilogue as in tgemm_kernel.
+// Warps: 0 = TMA (W), 1 = MMA issuer, 2..5 = epilogue, 6..9 = producer group 0, 10..13 = producer group 1.
+constexpr int PG = 2;     // producer groups
+
+template <int BN, int STAGES, class Epi>
+__global__ void __launch_bounds__(448, 2)
+tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __restrict__ bn_a, const float* __restrict__ bn_b,
+                    const __grid_constant__ CUtensorMap tmB, int nkb, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* bfull = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  uint64_t* afull = bfull + STAGES;          // 128 producer arrivals
+  uint64_t* empty = afull + STAGES;          // MMA commit: both the A and the B half of the stage are free
+  uint64_t* accum = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&afull[s], 128); mbar_init(&empty[s], 1); }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&bfull[s], B_BYTES);
+        tma_load_2d(sB + s * B_BYTES, &tmB, &bfull[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        mbar_wait(&afull[s], ph);
+        mbar_wait(&bfull[s], ph);
+        tc_fence_after();
+        const uint64_t ad = make_desc_sw128(smem_u32(sA + s * A_BYTES));
+        const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_tf32(tmem_base, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (kb | k) != 0);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accum);
+    }
+  } else if (warp < 6) {
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      epi(row, n0 + c, v);
+    }
+    tc_fence_before();
+  } else {
+    // ===== producers: thread = (16-byte chunk of the 128-byte row, row r0 + 16 i)
+    const int g = (warp - 6) >> 2;
+    const int t = (threadIdx.x - 192) & 127;
+    const int chunk = t & 7, r0 = t >> 3;
+    const float* xp = X + (size_t)(m0 + r0) * lda + chunk * 4;
+    for (int kb = g; kb < nkb; kb += PG) {
+      const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+      const int kcol = kb * BK;
+      float4 x[BM / 16];
+#pragma unroll
+      for (int i = 0; i < BM / 16; ++i)
+        x[i] = (m0 + r0 + i * 16 < M) ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)i * 16 * lda + kcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(bn_a + kcol + chunk * 4));
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(bn_b + kcol + chunk * 4));
+      mbar_wait(&empty[s], ph ^ 1);
+      float4* base = reinterpret_cast<float4*>(sA + s * A_BYTES);
+#pragma unroll
+      for (int i = 0; i < BM / 16; ++i) {
+        const int r = r0 + i * 16;
+        float4 y;
+        y.x = to_tf32(fmaxf(fmaf(x[i].x, sc.x, sh.x), 0.f));
+        y.y = to_tf32(fmaxf(fmaf(x[i].y, sc.y, sh.y), 0.f));
+        y.z = to_tf32(fmaxf(fmaf(x[i].z, sc.z, sh.z), 0.f));
+        y.w = to_tf32(fmaxf(fmaf(x[i].w, sc.w, sh.w), 0.f));
+        base[r * 8 + (chunk ^ (r & 7))] = y;
+      }
+      fence_proxy_async();
+      mbar_arrive(&afull[s]);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -282,6 +399,19 @@ inline void tgemm(Launches& L, cudaStream_t st, const char* tag, const CUtensorM
   const int nkb = tap.cpb * ntaps;
   Scope sc(L, st, tag, 2.0 * M * N * K);
   kern<<<grid, Pro::kOn ? 320 : 192, SMEM, st>>>(tmA, tmB, nkb, tap, pro, epi);
+}
+
+template <int BN, int STAGES, class Epi>
+inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const float* X, int lda, const float* bn_a, const float* bn_b,
+                         const CUtensorMap& tmB, int M, int N, int K, Epi epi) {
+  if (M <= 0 || N <= 0) return;
+  auto kern = tgemm_bnrelu_kernel<BN, STAGES, Epi>;
+  constexpr int SMEM = smem_bytes(BN, STAGES);
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
+  Scope sc(L, st, tag, 2.0 * M * N * K);
+  kern<<<grid, 448, SMEM, st>>>(X, lda, M, bn_a, bn_b, tmB, (K + BK - 1) / BK, epi);
 }
 
 }  // namespace tc

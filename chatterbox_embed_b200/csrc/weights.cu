@@ -238,6 +238,13 @@ int load_xv(cbx_ctx* c, const TensorMap& t) {
           for (int tap = 0; tap < 3; ++tap) ol[(size_t)n * 384 + tap * kBnC + cc] = wl[((size_t)n * kBnC + cc) * 3 + tap];
       pk.add(&L.wl, ol);
       pk.add(&L.wc1, std::vector<float>(wc1, wc1 + kCamHid * kBnC));
+      {   // transposed copies: lanes along the output index read consecutive addresses in the gate kernel
+        std::vector<float> t1((size_t)kBnC * kCamHid), t2((size_t)kCamHid * kGrowth);
+        for (int o = 0; o < kCamHid; ++o) for (int k = 0; k < kBnC; ++k) t1[(size_t)k * kCamHid + o] = wc1[(size_t)o * kBnC + k];
+        for (int o = 0; o < kGrowth; ++o) for (int k = 0; k < kCamHid; ++k) t2[(size_t)k * kGrowth + o] = wc2[(size_t)o * kCamHid + k];
+        pk.add(&L.wc1T, t1);
+        pk.add(&L.wc2T, t2);
+      }
       pk.add(&L.bc1, std::vector<float>(bc1, bc1 + kCamHid));
       pk.add(&L.wc2, std::vector<float>(wc2, wc2 + kGrowth * kCamHid));
       pk.add(&L.bc2, std::vector<float>(bc2, bc2 + kGrowth));

@@ -247,6 +247,57 @@ __global__ void __launch_bounds__(128) cam_gate_kernel(const float* __restrict__
   }
 }
 
+constexpr int kMaxSegsSm = 8;      // segments per pass of the gate kernel
+// Gate from the segment sums the bottleneck epilogue accumulated (tensor-core mode), one CTA per clip; the sums are zeroed
+// after use so the next layer's epilogue can accumulate into the same buffer.
+__global__ void __launch_bounds__(256) cam_gate_clip_kernel(float* __restrict__ seg_sum, const ClipPlan* __restrict__ plan, DenseLayerW L,
+                                                            float* __restrict__ gate) {
+  __shared__ float w1[kBnC * kCamHid];        // [128][64] transposed
+  __shared__ float w2[kCamHid * kGrowth];     // [64][32] transposed
+  __shared__ float ctx[kMaxSegsSm][kBnC];
+  __shared__ float hid[kMaxSegsSm][kCamHid];
+  __shared__ float tot[kBnC];
+  const ClipPlan cp = plan[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int T = cp.xv_tdnn, S = cp.xv_segs;
+  // weights -> shared memory (coalesced 16-byte loads, all in flight at once)
+  for (int i = tid; i < kBnC * kCamHid / 4; i += 256) reinterpret_cast<float4*>(w1)[i] = __ldg(reinterpret_cast<const float4*>(L.wc1T) + i);
+  for (int i = tid; i < kCamHid * kGrowth / 4; i += 256) reinterpret_cast<float4*>(w2)[i] = __ldg(reinterpret_cast<const float4*>(L.wc2T) + i);
+  float* ss = seg_sum + (size_t)cp.seg0 * kBnC;
+  if (tid < kBnC) {
+    float t = 0.f;
+    for (int s = 0; s < S; ++s) t += ss[(size_t)s * kBnC + tid];
+    tot[tid] = t / (float)T;
+  }
+  __syncthreads();
+  for (int s0 = 0; s0 < S; s0 += kMaxSegsSm) {
+    const int ns = min(kMaxSegsSm, S - s0);
+    for (int o = tid; o < ns * kBnC; o += 256) {
+      const int s = o >> 7, ch = o & 127;
+      const int len = min(kSegLen, T - (s0 + s) * kSegLen);
+      ctx[s][ch] = tot[ch] + ss[(size_t)(s0 + s) * kBnC + ch] / (float)len;
+    }
+    __syncthreads();
+    for (int o = tid; o < ns * kCamHid; o += 256) {
+      const int s = o / kCamHid, hch = o - s * kCamHid;
+      float a = __ldg(L.bc1 + hch);
+#pragma unroll 8
+      for (int k = 0; k < kBnC; ++k) a = fmaf(w1[k * kCamHid + hch], ctx[s][k], a);
+      hid[s][hch] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    for (int o = tid; o < ns * kGrowth; o += 256) {
+      const int s = o / kGrowth, g = o - s * kGrowth;
+      float a = __ldg(L.bc2 + g);
+#pragma unroll 8
+      for (int k = 0; k < kCamHid; ++k) a = fmaf(w2[k * kGrowth + g], hid[s][k], a);
+      gate[(size_t)(cp.seg0 + s0 + s) * kGrowth + g] = 1.f / (1.f + expf(-a));
+    }
+    __syncthreads();
+  }
+  for (int o = tid; o < S * kBnC; o += 256) ss[o] = 0.f;
+}
+
 struct LocalConvA {   // Conv1d(128->32, k3, dilation d, zero pad d): k = tap*128 + c
   const float* u; int dil; int td_rows;
   __device__ float operator()(int m, int k) const {
@@ -386,6 +437,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     sgemm(L, st, "tdnn_gemm", M, kTdnnC, W.tdnn.K, TdnnA{ch.fcm_out, ch.fb_rows}, W.tdnn.w, W.tdnn.K, BiasReluMaskEpi{ch.cat1, 512, W.tdnn.bias, ch.td_row_clip});
   }
 
+  if (tcm && ch.segs > 0) cudaMemsetAsync(ch.seg_sum, 0, sizeof(float) * (size_t)ch.segs * kBnC, st);
   static const int kLayers[3] = {12, 24, 16};
   static const int kDil[3] = {1, 2, 2};
   float* cats[3] = {ch.cat1, ch.cat2, ch.cat3};
@@ -405,11 +457,14 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     for (int i = 0; i < kLayers[b]; ++i, ++li) {
       const DenseLayerW& D = W.dense[li];
       if (tcm)
-        tc::tgemm<128, 3>(L, st, "dense_bottleneck_gemm", tm_cat, W.tm_w1[li], M, kBnC, D.cin, tc::plain_map(D.cin), 1,
-                          tc::BnReluPrologue{D.a1, D.b1}, tc::EpiBiasReluMask{ch.u, kBnC, D.t2, ch.td_row_clip, M});
+        tc::tgemm_bnrelu<128, 3>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], M, kBnC, D.cin,
+                                 tc::EpiBiasReluMaskSegsum{ch.u, kBnC, D.t2, ch.td_row_seg, ch.seg_sum, M});
       else
         sgemm(L, st, "dense_bottleneck_gemm", M, kBnC, D.cin, BnReluA{cat, ld, D.a1, D.b1}, D.w1, D.cin, BiasReluMaskEpi{ch.u, kBnC, D.t2, ch.td_row_clip});
-      if (ch.segs > 0) {
+      if (ch.segs > 0 && tcm) {
+        Scope sc(L, st, "cam_gate_kernel");
+        cam_gate_clip_kernel<<<ch.n_clips, 256, 0, st>>>(ch.seg_sum, ch.plan, D, ch.gate);
+      } else if (ch.segs > 0) {
         { Scope sc(L, st, "seg_sum_kernel"); seg_sum_kernel<<<ch.segs, 128, 0, st>>>(ch.u, ch.plan, ch.seg_clip, ch.seg_sum); }
         { Scope sc(L, st, "cam_gate_kernel"); cam_gate_kernel<<<ch.segs, 128, 0, st>>>(ch.seg_sum, ch.plan, ch.seg_clip, D, ch.gate); }
       }
@@ -423,8 +478,8 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     float* out = b == 0 ? ch.cat2 : (b == 1 ? ch.cat3 : ch.tr3);
     const int ldo = b == 2 ? kStatsC : 1024;
     if (tcm)
-      tc::tgemm<128, 3>(L, st, "transit_gemm", tm_cat, W.tm_tr[b], M, T.cout, T.cin, tc::plain_map(T.cin), 1,
-                        tc::BnReluPrologue{T.a, T.b}, tc::EpiMask{out, ldo, ch.td_row_clip, M});
+      tc::tgemm_bnrelu<128, 3>(L, st, "transit_gemm", cat, ld, T.a, T.b, W.tm_tr[b], M, T.cout, T.cin,
+                               tc::EpiMask{out, ldo, ch.td_row_clip, M});
     else
       sgemm(L, st, "transit_gemm", M, T.cout, T.cin, BnReluA{cat, ld, T.a, T.b}, T.w, T.cin, MaskEpi{out, ldo, ch.td_row_clip});
   }

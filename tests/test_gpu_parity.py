@@ -218,8 +218,11 @@ def test_mode1_north_star_gate(models, mode1, kind):
     scale = max(1.0, float(np.abs(want_xv).max()))
     assert np.abs(xv - want_xv).max() <= 1e-3 * scale
     assert min(cos(a, b) for a, b in zip(xv, want_xv)) >= 0.9999
-    ve1, xv1 = emb.embed_wavs([wavs[3]])               # batch composition must not matter
-    assert np.abs(ve1[0] - ve[3]).max() < 1e-6 and np.abs(xv1[0] - xv[3]).max() < 1e-5 * scale
+    # batch composition must not matter beyond TF32 rounding noise: the CAM segment sums are accumulated with atomics in
+    # the GEMM epilogue, so their summation order depends on where the clip's rows fall in the 128-row tiles (the strict
+    # fp32 mode is order-independent and holds this to 1e-5 in test_ragged_batch_equals_per_clip_oracle)
+    ve1, xv1 = emb.embed_wavs([wavs[3]])
+    assert np.abs(ve1[0] - ve[3]).max() < 1e-6 and np.abs(xv1[0] - xv[3]).max() < 5e-4 * scale
 
 
 def test_mode1_sensitised_weights(models, mode1):
