@@ -51,8 +51,9 @@ VeChunk carve_ve(Carver& cv, const VeLayout& L, cbx_ctx* c) {
   ch.spec = cv.take<float>((int64_t)L.mel_rows * kVeSpecN);
   ch.mel = cv.take<float>((int64_t)L.mel_rows * kVeMels);
   ch.xw0 = cv.take<float>((int64_t)L.mel_rows * kVeGates);
-  ch.xw = cv.take<float>((int64_t)L.slots * kVePartial * kVeGates);
-  ch.hseq = cv.take<float>((int64_t)L.slots * kVePartial * kVeHidden);
+  const int64_t pslots = lstm_padded_slots(L.slots);       // the tensor-core recurrence works on whole 224-partial tiles
+  ch.xw = cv.take<float>(pslots * kVePartial * kVeGates);
+  ch.hseq = cv.take<float>(pslots * kVePartial * kVeHidden);
   ch.hlast = cv.take<float>((int64_t)L.slots * kVeHidden);
   ch.pemb = cv.take<float>((int64_t)L.slots * kVeEmbed);
   if (cv.base && c) {
@@ -230,6 +231,7 @@ int cbx_set_option(cbx_ctx* c, const char* key, int64_t v) {
   else if (k == "lstm_chunk_partials" && v >= 1) c->lstm_chunk_slots = v;
   else if (k == "mode" && (v == 0 || v == 1)) c->mode = v;
   else if (k == "lstm_dbg") c->lstm_dbg = v;
+  else if (k == "lstm_impl" && (v == 1 || v == 2)) c->lstm_impl = v;
   else if (k == "lstm_trace") c->lstm_trace = v;
   else { c->err = "bad option " + k; return CBX_ERR_ARG; }
   return CBX_OK;
@@ -365,8 +367,8 @@ int64_t cbx_ve_forward_workspace_bytes(cbx_ctx* c, int n) {
   if (!c || n <= 0) return CBX_ERR_ARG;
   Carver cv(nullptr, 0);
   cv.take<int32_t>(n);
-  cv.take<float>((int64_t)n * kVePartial * kVeGates);
-  cv.take<float>((int64_t)n * kVePartial * kVeHidden);
+  cv.take<float>((int64_t)lstm_padded_slots(n) * kVePartial * kVeGates);
+  cv.take<float>((int64_t)lstm_padded_slots(n) * kVePartial * kVeHidden);
   cv.take<float>((int64_t)n * kVeHidden);
   return cv.off + 1024;
 }

@@ -142,6 +142,7 @@ struct cbx_ctx {
   int64_t lstm_chunk_slots = 3072;    // partial slots per VoiceEncoder chunk
   int64_t mode = 0;
   int64_t lstm_trace = 0;             // device pointer of the clock trace buffer
+  int64_t lstm_impl = 2;              // 1: DSMEM-push recurrence, 2: L2 multicast-TMA recurrence
   int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)
   // buffers owned by the library (cbx_embed_host)
   void* own_ws = nullptr; int64_t own_ws_bytes = 0;
@@ -223,6 +224,9 @@ void run_ve_forward_partials(cbx_ctx* c, const float* mels, int n, float* out, v
 // frontend_tc.cu: frames -> 3xTF32 DFT GEMM -> power -> sparse mel (-> log) in one kernel
 void run_ve_mel_tc(cbx_ctx* c, const float* pcm, const VeChunk& ch, cudaStream_t st);
 void run_kaldi_fbank_tc(cbx_ctx* c, const float* pcm, const XvChunk& ch, cudaStream_t st);
+int lstm_padded_slots(int n_slots);     // slots rounded up to whole 224-partial cluster tiles (lstm_tc.cu)
+void run_lstm_rec_tc2(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
+                      int n_slots, cudaStream_t st);
 void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const float* bias, const float* in, int F_in, int F_out, int sf,
                      const float* sc, int F_sc, const float* res, float* out, const int32_t* row_clip, int rows, int prows, double flops);   // fcm_tc.cu
 void run_lstm_rec_tc(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,

@@ -306,6 +306,232 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) lstm_re
   }
 }
 
+
+// =====================================================================================================================
+// v2 of the recurrence.  Same decomposition (8-CTA cluster, W_hh slice in TMEM as the A operand, two ping-pong sub-tiles
+// of 112 partials), but
+//   * the exchange of h_t goes through L2: every CTA stores its [112 x 32] slice into the layer's hseq buffer (which the
+//     next layer's input-projection GEMM needs anyway), then ONE thread issues a multicast TMA load of that slice into the
+//     B tiles of all 8 CTAs.  (The DSMEM pushes of v1 ran at the ~20 B/clk/SM DSMEM port rate and cost 4-6 k cycles a step.)
+//   * xw (layers 1, 2) and hseq use a tiled time-major row order, row(q, t) = ((tile*160 + t)*2 + x)*112 + n for partial
+//     slot q = tile*224 + x*112 + n, so that everything a (tile, t, x) half-step touches is one contiguous block and all
+//     the addressing in the loop is immediate offsets from two running pointers;
+//   * the gate math of a half-step is spread over all 8 gate warps (two per TMEM lane quadrant, 56 partials each) and the
+//     xw loads of the NEXT half-step are issued chunk by chunk while the current one is being computed.
+constexpr int HALF = NSUB / 2;             // partials per gate warp and half-step
+constexpr int CH2 = 8;                     // partials per tcgen05.ld in v2
+static_assert(HALF % CH2 == 0, "chunking");
+
+struct Params2 {
+  const float* xw;            // layer 0: [mel rows][1024] gathered through slot_row; else tiled time-major [tiles*160*224][1024]
+  const int32_t* slot_row;    // layer 0 only
+  const float* whh;
+  float* hseq;                // tiled time-major [tiles*160*224][256] (tf32-rounded h), also the exchange medium
+  float* hlast;               // [n_slots][256] or nullptr
+  int n_slots;
+  long long* trace;           // [160][2][8] clock64 stamps of CTA 0 when non-null (tools/lstm_trace.py)
+};
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+
+template <bool kLayer0>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* hbuf = smem;                                                   // [2][8 K blocks][NSUB rows x 128 B]
+  int32_t* rowbase = reinterpret_cast<int32_t*>(smem + 2 * H_BYTES);      // [2][NSUB] (layer 0)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rowbase + 2 * NSUB);
+  uint64_t* full = bars;          // [2] 1 local arrive (expect 8 slices) + 8 multicast TMA loads
+  uint64_t* freeb = bars + 2;     // [2] all 8 CTAs' MMAs have finished reading h_{t-1}
+  uint64_t* accum = bars + 4;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t j = cluster_rank();
+  const int tile = blockIdx.x / CL;
+  const int q_tile = tile * TILE;
+  const bool tr = p.trace != nullptr && blockIdx.x == 0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmH);
+    for (int x = 0; x < 2; ++x) { mbar_init(&full[x], 1); mbar_init(&freeb[x], CL); mbar_init(&accum[x], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < 2 * H_BYTES / 16; i += THREADS) reinterpret_cast<float4*>(hbuf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (kLayer0)
+    for (int i = threadIdx.x; i < TILE; i += THREADS) rowbase[i] = p.slot_row[min(q_tile + i, p.n_slots - 1)];
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 1) {
+    const int wg = (warp - 1) >> 2, qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const float* wrow = p.whh + ((size_t)j * 128 + r) * kVeHidden + wg * 128;
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(wrow + c) + i);
+        v[4 * i] = w.x; v[4 * i + 1] = w.y; v[4 * i + 2] = w.z; v[4 * i + 3] = w.w;
+      }
+      tmem_st32(tmem_base + ((uint32_t)(qd * 32) << 16) + COL_W + wg * 128 + c, v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  __syncwarp();
+  cluster_sync_all();
+  tc_fence_after();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, NSUB);
+      for (int t = 0; t < kVePartial; ++t) {
+#pragma unroll 1
+        for (int x = 0; x < 2; ++x) {
+          if (t > 0) mbar_wait(&full[x], (t - 1) & 1);
+          tc_fence_after();
+          if (tr) p.trace[(t * 2 + x) * 8 + 0] = clock64();
+          const uint32_t hb = smem_u32(hbuf + x * H_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < CL; ++kb) {
+            const uint64_t bd = make_desc_sw128(hb + kb * KB_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32_ts(tmem_base + COL_D + x * NSUB, tmem_base + COL_W + kb * 32 + k * 8, bd + (uint64_t)(k * 32 >> 4), idesc, (kb | k) != 0);
+          }
+          umma_commit(&accum[x]);
+          if (tr) p.trace[(t * 2 + x) * 8 + 1] = clock64();
+        }
+      }
+    }
+  } else {
+    // ===================== gate warps: quadrant qd, column half hf; all 8 warps work on sub-tile A, then on sub-tile B
+    const int qd = warp & 3, hf = (warp - 1) >> 2;
+    const int r = qd * 32 + lane;
+    const int u = r >> 2, g = r & 3;
+    const bool P0 = g & 1, P1 = g & 2;
+    const float m = g == 2 ? 2.f : 1.f;
+    const float neg_m_log2e = -m * 1.4426950408889634f, one_minus_m = 1.f - m;
+    const int gt = threadIdx.x - 32;               // 0..255
+    const int n0 = hf * HALF;                      // first partial (within a sub-tile) of this warp
+    // running pointers; a half-step advances by one (t, x) block of 112 rows
+    const size_t blk0 = (size_t)tile * kVePartial * 2 * NSUB;                      // first tiled row of the tile
+    const float* xq = p.xw + (kLayer0 ? (size_t)0 : (blk0 + n0) * kVeGates) + j * 128 + r;
+    float* hq = p.hseq + (blk0 + n0 + g) * kVeHidden + j * UNITS + u;
+    const uint32_t dcol = tmem_base + ((uint32_t)(qd * 32) << 16) + COL_D + n0;
+    float cst[2][HALF / 4];
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+      for (int i = 0; i < HALF / 4; ++i) cst[x][i] = 0.f;
+    uint32_t peer_free[2] = {0, 0};
+    if (gt < CL) { peer_free[0] = mapa(smem_u32(&freeb[0]), gt); peer_free[1] = mapa(smem_u32(&freeb[1]), gt); }
+
+    auto xw_load = [&](int hs, int n) -> float {     // input projection of partial n0 + n for half-step hs = 2 t + x
+      if (kLayer0) {
+        const int x = hs & 1, t = hs >> 1;
+        return __ldg(xq + (size_t)(rowbase[x * NSUB + n0 + n] + t) * kVeGates);
+      }
+      return __ldg(xq + ((size_t)hs * NSUB + n) * kVeGates);
+    };
+    float xv[HALF];
+#pragma unroll
+    for (int n = 0; n < HALF; ++n) xv[n] = xw_load(0, n);
+
+    for (int t = 0; t < kVePartial; ++t) {
+      const bool last = t == kVePartial - 1;
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const int hs = 2 * t + x;
+        const bool trt = tr && gt == 0;
+        if (trt) p.trace[(t * 2 + x) * 8 + 2] = clock64();
+        mbar_wait(&accum[x], t & 1);
+        tc_fence_after();
+        if (trt) p.trace[(t * 2 + x) * 8 + 3] = clock64();
+        if (gt < CL) remote_arrive(peer_free[x]);
+        float* hrow = hq + (size_t)hs * NSUB * kVeHidden;
+#pragma unroll
+        for (int c = 0; c < HALF / CH2; ++c) {
+          float v[CH2];
+          tmem_ld8(dcol + x * NSUB + c * CH2, v);
+#pragma unroll
+          for (int i = 0; i < CH2; ++i) v[i] = gate_act(v[i] + xv[c * CH2 + i], m, neg_m_log2e, one_minus_m);
+          // the registers just consumed take the loads of the next half-step
+          if (hs + 1 < 2 * kVePartial) {
+#pragma unroll
+            for (int i = 0; i < CH2; ++i) xv[c * CH2 + i] = xw_load(hs + 1, c * CH2 + i);
+          }
+#pragma unroll
+          for (int grp = 0; grp < CH2 / 4; ++grp) {
+            const float a0 = v[4 * grp], a1 = v[4 * grp + 1], a2 = v[4 * grp + 2], a3 = v[4 * grp + 3];
+            const float k0 = P0 ? a1 : a0, s0 = P0 ? a0 : a1;
+            const float k1 = P0 ? a3 : a2, s1 = P0 ? a2 : a3;
+            const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+            const float own = P1 ? k1 : k0, sown = P1 ? k0 : k1;
+            const float par = P1 ? r1 : r0, spar = P1 ? r0 : r1;
+            const float own2 = __shfl_xor_sync(0xffffffffu, sown, 2), par2 = __shfl_xor_sync(0xffffffffu, spar, 2);
+            const float e0 = P0 ? par : own, o0 = P0 ? own : par;
+            const float e1 = P0 ? par2 : own2, o1 = P0 ? own2 : par2;
+            const float gi = P1 ? e1 : e0, gg = P1 ? e0 : e1, gf = P1 ? o1 : o0, go = P1 ? o0 : o1;
+            const int ci = c * (CH2 / 4) + grp;
+            const float cn = fmaf(gf, cst[x][ci], gi * gg);
+            cst[x][ci] = cn;
+            const float h = go * tanh_acc(cn);
+            hrow[(size_t)(c * CH2 + grp * 4) * kVeHidden] = to_tf32(h);       // partial n0 + c*8 + grp*4 + g
+            if (last && p.hlast) {
+              const int q = q_tile + x * NSUB + n0 + c * CH2 + grp * 4 + g;
+              if (q < p.n_slots) p.hlast[(size_t)q * kVeHidden + j * UNITS + u] = h;
+            }
+          }
+        }
+        if (trt) p.trace[(t * 2 + x) * 8 + 4] = clock64();
+        if (!last) {
+          __threadfence();                            // the slice is in L2 ...
+          fence_proxy_async();                        // ... and ordered before the async-proxy (TMA) read below
+          tc_fence_before();
+          if (trt) p.trace[(t * 2 + x) * 8 + 5] = clock64();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (trt) p.trace[(t * 2 + x) * 8 + 6] = clock64();
+          if (gt == 0) {
+            mbar_wait_cluster(&freeb[x], t & 1);      // every peer's MMA has finished reading h_{t-1} of this sub-tile
+            mbar_expect_tx(&full[x], CL * KB_BYTES);  // local arrival; 8 slices of 14 KB will land
+            tma_load_2d_mc(hbuf + x * H_BYTES + j * KB_BYTES, &tmH, &full[x], j * UNITS, (int)(blk0 + (size_t)hs * NSUB), (uint16_t)0xff);
+            if (trt) p.trace[(t * 2 + x) * 8 + 7] = clock64();
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  __syncwarp();
+  cluster_sync_all();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace lstm
 
 void run_lstm_rec_tc(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
@@ -340,3 +566,27 @@ extern "C" int cbx_lstm_max_clusters(cbx_ctx* c) {
   if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return -2; }
   return n;
 }
+
+namespace cbx {
+// v2 entry point.  hseq / xw rows are in the tiled time-major order (see lstm_rec_tc2_kernel); both must hold
+// lstm_padded_slots(n_slots) * 160 rows.
+int lstm_padded_slots(int n_slots) { return (n_slots + lstm::TILE - 1) / lstm::TILE * lstm::TILE; }
+
+void run_lstm_rec_tc2(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
+                      int n_slots, cudaStream_t st) {
+  if (n_slots <= 0) return;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(lstm::lstm_rec_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::SMEM_BYTES);
+    cudaFuncSetAttribute(lstm::lstm_rec_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::SMEM_BYTES);
+    configured = true;
+  }
+  const int tiles = (n_slots + lstm::TILE - 1) / lstm::TILE;
+  const int64_t rows = (int64_t)tiles * lstm::TILE * kVePartial;
+  CUtensorMap tmH = tc::make_map_2d(hseq, rows, kVeHidden, kVeHidden, lstm::NSUB, false);
+  lstm::Params2 p{xw, slot_row, whh_perm, hseq, hlast, n_slots, (long long*)c->lstm_trace};
+  Scope sc(c->launches, st, "lstm_rec_tc_kernel", 2.0 * n_slots * kVePartial * kVeHidden * kVeGates);
+  if (slot_row) lstm::lstm_rec_tc2_kernel<true><<<tiles * lstm::CL, lstm::THREADS, lstm::SMEM_BYTES, st>>>(tmH, p);
+  else lstm::lstm_rec_tc2_kernel<false><<<tiles * lstm::CL, lstm::THREADS, lstm::SMEM_BYTES, st>>>(tmH, p);
+}
+}  // namespace cbx
