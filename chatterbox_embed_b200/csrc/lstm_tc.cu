@@ -346,8 +346,18 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, 
       : "memory");
 }
 
+constexpr int THREADS2 = 320;              // warp 0: MMA issuer, warps 1-8: gate warps, warp 9: exchange
+
+// 4 reciprocals for one MUFU: r = 1/(d0 d1 d2 d3); the d's are 1 + 2^x with x clamped to 30, so the product stays finite
+__device__ __forceinline__ void rcp4(float d0, float d1, float d2, float d3, float& i0, float& i1, float& i2, float& i3) {
+  const float p01 = d0 * d1, p23 = d2 * d3;
+  const float r = rcp_approx(p01 * p23);
+  const float r01 = r * p23, r23 = r * p01;
+  i0 = r01 * d1; i1 = r01 * d0; i2 = r23 * d3; i3 = r23 * d2;
+}
+
 template <bool kLayer0>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS2, 1)
 lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -357,7 +367,8 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
   uint64_t* full = bars;          // [2] 1 local arrive (expect 8 slices) + 8 multicast TMA loads
   uint64_t* freeb = bars + 2;     // [2] all 8 CTAs' MMAs have finished reading h_{t-1}
   uint64_t* accum = bars + 4;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* ready = bars + 6;     // [2] this CTA's slice of h_t is stored and fenced (256 gate-thread arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t j = cluster_rank();
@@ -367,20 +378,20 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmH);
-    for (int x = 0; x < 2; ++x) { mbar_init(&full[x], 1); mbar_init(&freeb[x], CL); mbar_init(&accum[x], 1); }
+    for (int x = 0; x < 2; ++x) { mbar_init(&full[x], 1); mbar_init(&freeb[x], CL); mbar_init(&accum[x], 1); mbar_init(&ready[x], 256); }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
-  for (int i = threadIdx.x; i < 2 * H_BYTES / 16; i += THREADS) reinterpret_cast<float4*>(hbuf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < 2 * H_BYTES / 16; i += THREADS2) reinterpret_cast<float4*>(hbuf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (kLayer0)
-    for (int i = threadIdx.x; i < TILE; i += THREADS) rowbase[i] = p.slot_row[min(q_tile + i, p.n_slots - 1)];
+    for (int i = threadIdx.x; i < TILE; i += THREADS2) rowbase[i] = p.slot_row[min(q_tile + i, p.n_slots - 1)];
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 1) {
+  if (warp >= 1 && warp <= 8) {
     const int wg = (warp - 1) >> 2, qd = warp & 3;
     const int r = qd * 32 + lane;
     const float* wrow = p.whh + ((size_t)j * 128 + r) * kVeHidden + wg * 128;
@@ -402,7 +413,9 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
   cluster_sync_all();
   tc_fence_after();
 
+  const size_t blk0 = (size_t)tile * kVePartial * 2 * NSUB;                      // first tiled row of the tile
   if (warp == 0) {
+    // ===================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(128, NSUB);
       for (int t = 0; t < kVePartial; ++t) {
@@ -424,6 +437,24 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
         }
       }
     }
+  } else if (warp == 9) {
+    // ===================== exchange: slice stored -> peers' MMAs done with h_{t-1} -> multicast TMA load into all 8 B tiles
+    if (lane == 0) {
+      for (int t = 0; t < kVePartial - 1; ++t) {
+#pragma unroll 1
+        for (int x = 0; x < 2; ++x) {
+          const int hs = 2 * t + x;
+          mbar_wait(&ready[x], t & 1);
+          fence_proxy_async();
+          if (tr) p.trace[(t * 2 + x) * 8 + 5] = clock64();
+          mbar_wait_cluster(&freeb[x], t & 1);
+          if (tr) p.trace[(t * 2 + x) * 8 + 6] = clock64();
+          mbar_expect_tx(&full[x], CL * KB_BYTES);
+          tma_load_2d_mc(hbuf + x * H_BYTES + j * KB_BYTES, &tmH, &full[x], j * UNITS, (int)(blk0 + (size_t)hs * NSUB), (uint16_t)0xff);
+          if (tr) p.trace[(t * 2 + x) * 8 + 7] = clock64();
+        }
+      }
+    }
   } else {
     // ===================== gate warps: quadrant qd, column half hf; all 8 warps work on sub-tile A, then on sub-tile B
     const int qd = warp & 3, hf = (warp - 1) >> 2;
@@ -434,8 +465,6 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
     const float neg_m_log2e = -m * 1.4426950408889634f, one_minus_m = 1.f - m;
     const int gt = threadIdx.x - 32;               // 0..255
     const int n0 = hf * HALF;                      // first partial (within a sub-tile) of this warp
-    // running pointers; a half-step advances by one (t, x) block of 112 rows
-    const size_t blk0 = (size_t)tile * kVePartial * 2 * NSUB;                      // first tiled row of the tile
     const float* xq = p.xw + (kLayer0 ? (size_t)0 : (blk0 + n0) * kVeGates) + j * 128 + r;
     float* hq = p.hseq + (blk0 + n0 + g) * kVeHidden + j * UNITS + u;
     const uint32_t dcol = tmem_base + ((uint32_t)(qd * 32) << 16) + COL_D + n0;
@@ -454,6 +483,19 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
       }
       return __ldg(xq + ((size_t)hs * NSUB + n) * kVeGates);
     };
+    // activations of one 8-column chunk: own gate of 8 partials; two shared reciprocals
+    auto activate = [&](int x, int c, const float* xin, float* a) {
+      float v[CH2];
+      tmem_ld8(dcol + x * NSUB + c * CH2, v);
+      float d[CH2];
+#pragma unroll
+      for (int i = 0; i < CH2; ++i) d[i] = 1.f + ex2_approx(fminf((v[i] + xin[c * CH2 + i]) * neg_m_log2e, 30.f));
+      float inv[CH2];
+      rcp4(d[0], d[1], d[2], d[3], inv[0], inv[1], inv[2], inv[3]);
+      rcp4(d[4], d[5], d[6], d[7], inv[4], inv[5], inv[6], inv[7]);
+#pragma unroll
+      for (int i = 0; i < CH2; ++i) a[i] = fmaf(m, inv[i], one_minus_m);
+    };
     float xv[HALF];
 #pragma unroll
     for (int n = 0; n < HALF; ++n) xv[n] = xw_load(0, n);
@@ -469,20 +511,30 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
         tc_fence_after();
         if (trt) p.trace[(t * 2 + x) * 8 + 3] = clock64();
         if (gt < CL) remote_arrive(peer_free[x]);
+        if (hs > 0) {
+          // publish the PREVIOUS half-step's slice now: its stores have had the whole accumulator wait to reach L2, so the
+          // fence is cheap, and the exchange it triggers is not needed before this half-step's math is over anyway
+          __threadfence();
+          fence_proxy_async();                        // generic-proxy stores ordered before the exchange warp's TMA read
+          mbar_arrive(&ready[x ^ 1]);
+        }
         float* hrow = hq + (size_t)hs * NSUB * kVeHidden;
+        // software pipeline over the 7 chunks: the activations (MUFU) of chunk c+1 are issued alongside the transpose and
+        // cell update (ALU / shuffle) of chunk c
+        float act[2][CH2];
+        activate(x, 0, xv, act[0]);
 #pragma unroll
         for (int c = 0; c < HALF / CH2; ++c) {
-          float v[CH2];
-          tmem_ld8(dcol + x * NSUB + c * CH2, v);
-#pragma unroll
-          for (int i = 0; i < CH2; ++i) v[i] = gate_act(v[i] + xv[c * CH2 + i], m, neg_m_log2e, one_minus_m);
-          // the registers just consumed take the loads of the next half-step
+          if (c + 1 < HALF / CH2) activate(x, c + 1, xv, act[(c + 1) & 1]);
+          // the xw registers of chunk c have been consumed: they take the loads of the next half-step
           if (hs + 1 < 2 * kVePartial) {
 #pragma unroll
             for (int i = 0; i < CH2; ++i) xv[c * CH2 + i] = xw_load(hs + 1, c * CH2 + i);
           }
+          const float* v = act[c & 1];
+          float cn[2], gout[2];
 #pragma unroll
-          for (int grp = 0; grp < CH2 / 4; ++grp) {
+          for (int grp = 0; grp < 2; ++grp) {
             const float a0 = v[4 * grp], a1 = v[4 * grp + 1], a2 = v[4 * grp + 2], a3 = v[4 * grp + 3];
             const float k0 = P0 ? a1 : a0, s0 = P0 ? a0 : a1;
             const float k1 = P0 ? a3 : a2, s1 = P0 ? a2 : a3;
@@ -492,33 +544,27 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
             const float own2 = __shfl_xor_sync(0xffffffffu, sown, 2), par2 = __shfl_xor_sync(0xffffffffu, spar, 2);
             const float e0 = P0 ? par : own, o0 = P0 ? own : par;
             const float e1 = P0 ? par2 : own2, o1 = P0 ? own2 : par2;
-            const float gi = P1 ? e1 : e0, gg = P1 ? e0 : e1, gf = P1 ? o1 : o0, go = P1 ? o0 : o1;
-            const int ci = c * (CH2 / 4) + grp;
-            const float cn = fmaf(gf, cst[x][ci], gi * gg);
-            cst[x][ci] = cn;
-            const float h = go * tanh_acc(cn);
-            hrow[(size_t)(c * CH2 + grp * 4) * kVeHidden] = to_tf32(h);       // partial n0 + c*8 + grp*4 + g
-            if (last && p.hlast) {
-              const int q = q_tile + x * NSUB + n0 + c * CH2 + grp * 4 + g;
-              if (q < p.n_slots) p.hlast[(size_t)q * kVeHidden + j * UNITS + u] = h;
-            }
+            const float gi = P1 ? e1 : e0, gg = P1 ? e0 : e1, gf = P1 ? o1 : o0;
+            gout[grp] = P1 ? o0 : o1;
+            const int ci = c * 2 + grp;
+            cn[grp] = fmaf(gf, cst[x][ci], gi * gg);
+            cst[x][ci] = cn[grp];
+          }
+          // tanh(c) of the two cells with one reciprocal
+          const float d0 = 1.f + ex2_approx(fminf(cn[0] * (-2.f * 1.4426950408889634f), 60.f));
+          const float d1 = 1.f + ex2_approx(fminf(cn[1] * (-2.f * 1.4426950408889634f), 60.f));
+          const float rr = rcp_approx(d0 * d1);
+          const float h0 = gout[0] * fmaf(2.f, rr * d1, -1.f), h1 = gout[1] * fmaf(2.f, rr * d0, -1.f);
+          hrow[(size_t)(c * CH2) * kVeHidden] = to_tf32(h0);           // partial n0 + c*8 + g
+          hrow[(size_t)(c * CH2 + 4) * kVeHidden] = to_tf32(h1);       // partial n0 + c*8 + 4 + g
+          if (last && p.hlast) {
+            const int q = q_tile + x * NSUB + n0 + c * CH2 + g;
+            if (q < p.n_slots) p.hlast[(size_t)q * kVeHidden + j * UNITS + u] = h0;
+            if (q + 4 < p.n_slots) p.hlast[(size_t)(q + 4) * kVeHidden + j * UNITS + u] = h1;
           }
         }
         if (trt) p.trace[(t * 2 + x) * 8 + 4] = clock64();
-        if (!last) {
-          __threadfence();                            // the slice is in L2 ...
-          fence_proxy_async();                        // ... and ordered before the async-proxy (TMA) read below
-          tc_fence_before();
-          if (trt) p.trace[(t * 2 + x) * 8 + 5] = clock64();
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (trt) p.trace[(t * 2 + x) * 8 + 6] = clock64();
-          if (gt == 0) {
-            mbar_wait_cluster(&freeb[x], t & 1);      // every peer's MMA has finished reading h_{t-1} of this sub-tile
-            mbar_expect_tx(&full[x], CL * KB_BYTES);  // local arrival; 8 slices of 14 KB will land
-            tma_load_2d_mc(hbuf + x * H_BYTES + j * KB_BYTES, &tmH, &full[x], j * UNITS, (int)(blk0 + (size_t)hs * NSUB), (uint16_t)0xff);
-            if (trt) p.trace[(t * 2 + x) * 8 + 7] = clock64();
-          }
-        }
+        tc_fence_before();
       }
     }
   }
@@ -586,7 +632,7 @@ void run_lstm_rec_tc2(cbx_ctx* c, const float* xw, const int32_t* slot_row, cons
   CUtensorMap tmH = tc::make_map_2d(hseq, rows, kVeHidden, kVeHidden, lstm::NSUB, false);
   lstm::Params2 p{xw, slot_row, whh_perm, hseq, hlast, n_slots, (long long*)c->lstm_trace};
   Scope sc(c->launches, st, "lstm_rec_tc_kernel", 2.0 * n_slots * kVePartial * kVeHidden * kVeGates);
-  if (slot_row) lstm::lstm_rec_tc2_kernel<true><<<tiles * lstm::CL, lstm::THREADS, lstm::SMEM_BYTES, st>>>(tmH, p);
-  else lstm::lstm_rec_tc2_kernel<false><<<tiles * lstm::CL, lstm::THREADS, lstm::SMEM_BYTES, st>>>(tmH, p);
+  if (slot_row) lstm::lstm_rec_tc2_kernel<true><<<tiles * lstm::CL, lstm::THREADS2, lstm::SMEM_BYTES, st>>>(tmH, p);
+  else lstm::lstm_rec_tc2_kernel<false><<<tiles * lstm::CL, lstm::THREADS2, lstm::SMEM_BYTES, st>>>(tmH, p);
 }
 }  // namespace cbx

@@ -14,7 +14,7 @@ trace = torch.zeros(160 * 2 * 8, dtype=torch.int64, device=dev)
 ctx.set_option("lstm_trace", trace.data_ptr())
 ve(parts); torch.cuda.synchronize()
 tr = trace.cpu().numpy().reshape(160, 2, 8).astype(np.float64)
-names = ["mma:full_ok", "mma:committed", "g0:top", "g0:accum_ok", "g0:math_done", "g0:fenced", "g0:bar_done", "g0:tma_issued"]
+names = ["mma:full_ok", "mma:committed", "g0:top", "g0:accum_ok", "g0:math_done", "ex:ready_ok", "ex:free_ok", "ex:tma_issued"]
 print("cycles relative to mma:full_ok of sub-tile A of the same step (last layer traced)")
 for t in (1, 2, 50, 100, 158):
     base = tr[t, 0, 0]
@@ -24,6 +24,6 @@ print(f"cycles per step (t=50..150): {(tr[150, 0, 0] - tr[50, 0, 0]) / 100:.0f}"
 d = tr[50:150]
 for x in (0, 1):
     print(f"  x={x} mean: mma issue {np.mean(d[:, x, 1] - d[:, x, 0]):.0f}  commit->accum_ok {np.mean(d[:, x, 3] - d[:, x, 1]):.0f}  wait accum {np.mean(d[:, x, 3] - d[:, x, 2]):.0f}"
-          f"  math {np.mean(d[:, x, 4] - d[:, x, 3]):.0f}  fence {np.mean(d[:, x, 5] - d[:, x, 4]):.0f}  bar {np.mean(d[:, x, 6] - d[:, x, 5]):.0f}"
-          f"  free+issue {np.mean(d[:, x, 7] - d[:, x, 6]):.0f}  issued->next full_ok {np.mean(tr[51:151, x, 0] - d[:, x, 7]):.0f}")
+          f"  math {np.mean(d[:, x, 4] - d[:, x, 3]):.0f}  math_done->ready_ok {np.mean(d[:, x, 5] - d[:, x, 4]):.0f}  free wait {np.mean(d[:, x, 6] - d[:, x, 5]):.0f}"
+          f"  issue {np.mean(d[:, x, 7] - d[:, x, 6]):.0f}  issued->next full_ok {np.mean(tr[51:151, x, 0] - d[:, x, 7]):.0f}")
 ctx.set_option("lstm_trace", 0)
