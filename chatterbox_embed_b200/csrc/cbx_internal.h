@@ -97,7 +97,7 @@ struct VeWeights {
   CUtensorMap tm_wih[3];     // TMA maps of W_ih (B operand of the input-projection GEMMs)
   // tensor-core recurrence (lstm_tc.cu): gate rows permuted to row 128 j + 4 u + g  <->  gate g of unit 32 j + u
   const float *wih_p[3], *whh_p[3], *bias_p[3];   // whh_p tf32-rounded [1024][256]
-  CUtensorMap tm_wih_p[3];
+  CUtensorMap tm_wih_p[3], tm_wih_p256[3];     // boxes of 128 / 256 gate rows
 };
 struct XvWeights {
   bool loaded = false;

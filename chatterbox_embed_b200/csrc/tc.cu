@@ -23,6 +23,12 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+int sm_count() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
+
 CUtensorMap make_map_2d(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool round_tf32) {
   CUtensorMap m;
   std::memset(&m, 0, sizeof m);

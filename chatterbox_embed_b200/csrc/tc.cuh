@@ -378,6 +378,147 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
   }
 }
 
+// ---------------------------------------------------------------- persistent GEMM
+//   C[m][n] = epi( sum_k pro(A[m][k]) * W[n][k] ),   one CTA per SM looping over 128 x BN output tiles (n fastest).
+// The shared-memory stage ring and the barriers' phases run on across tiles, and the fp32 accumulator is double-buffered
+// in TMEM (2 x BN columns), so the epilogue of tile i (TMEM -> registers -> global) overlaps the K loop of tile i+1 and
+// the per-CTA set-up (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM instead of once per tile.
+// kPro = false: A tiles come by TMA (tf32 rounding in the tensor map); warps 0 = TMA, 1 = MMA, 2..5 = epilogue.
+// kPro = true:  A is produced by warps 6..13 (two groups alternating K blocks): coalesced 16-byte loads of X, BatchNorm +
+//               ReLU + tf32 rounding in registers, one store into the swizzled stage (pre-activation D-TDNN layers).
+template <int BN, int STAGES, bool kPro, class Epi>
+__global__ void __launch_bounds__(kPro ? 448 : 192, 1)
+pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float* __restrict__ X, int lda,
+             const float* __restrict__ bn_a, const float* __restrict__ bn_b, int M, int n_tiles_n, int n_tiles, int nkb, Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+  static_assert(2 * BN <= 512, "two accumulators must fit TMEM");
+  constexpr int TMEM_COLS = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* bfull = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));   // TMA bytes (B, and A when !kPro)
+  uint64_t* afull = bfull + STAGES;          // 128 producer arrivals (kPro)
+  uint64_t* empty = afull + STAGES;          // MMA commit
+  uint64_t* tfull = empty + STAGES;          // [2] accumulator ready
+  uint64_t* tempty = tfull + 2;              // [2] accumulator drained (4 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    if (!kPro) tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&afull[s], 128); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&bfull[s], kPro ? B_BYTES : A_BYTES + B_BYTES);
+          if (!kPro) tma_load_2d(sA + s * A_BYTES, &tmA, &bfull[s], kb * BK, m0);
+          tma_load_2d(sB + s * B_BYTES, &tmB, &bfull[s], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+      int it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+        const int a = ti & 1, pa = (ti >> 1) & 1;
+        mbar_wait(&tempty[a], pa ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + a * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES, ph = (it / STAGES) & 1;
+          if (kPro) mbar_wait(&afull[s], ph);
+          mbar_wait(&bfull[s], ph);
+          tc_fence_after();
+          const uint64_t ad = make_desc_sw128(smem_u32(sA + s * A_BYTES));
+          const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_tf32(d, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (kb | k) != 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tfull[a]);
+      }
+    }
+  } else if (warp < 6) {
+    const int q = warp & 3;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+      const int a = ti & 1, pa = (ti >> 1) & 1;
+      mbar_wait(&tfull[a], pa);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c), v);
+        if (c + 32 >= BN) {                    // all of this warp's accumulator columns are in registers: release the buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[a]);
+        }
+        epi(row, n0 + c, v);
+      }
+    }
+  } else if (kPro) {
+    const int g = (warp - 6) >> 2;
+    const int t = (threadIdx.x - 192) & 127;
+    const int chunk = t & 7, r0 = t >> 3;
+    int it0 = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it0 += nkb) {
+      const int m0 = (tile / n_tiles_n) * BM;
+      const float* xp = X + (size_t)(m0 + r0) * lda + chunk * 4;
+      for (int kb = g; kb < nkb; kb += PG) {
+        const int it = it0 + kb;
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
+        const int kcol = kb * BK;
+        float4 x[BM / 16];
+#pragma unroll
+        for (int i = 0; i < BM / 16; ++i)
+          x[i] = (m0 + r0 + i * 16 < M) ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)i * 16 * lda + kcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(bn_a + kcol + chunk * 4));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(bn_b + kcol + chunk * 4));
+        mbar_wait(&empty[s], ph ^ 1);
+        float4* base = reinterpret_cast<float4*>(sA + s * A_BYTES);
+#pragma unroll
+        for (int i = 0; i < BM / 16; ++i) {
+          const int r = r0 + i * 16;
+          float4 y;
+          y.x = to_tf32(fmaxf(fmaf(x[i].x, sc.x, sh.x), 0.f));
+          y.y = to_tf32(fmaxf(fmaf(x[i].y, sc.y, sh.y), 0.f));
+          y.z = to_tf32(fmaxf(fmaf(x[i].z, sc.z, sh.z), 0.f));
+          y.w = to_tf32(fmaxf(fmaf(x[i].w, sc.w, sh.w), 0.f));
+          base[r * 8 + (chunk ^ (r & 7))] = y;
+        }
+        fence_proxy_async();
+        mbar_arrive(&afull[s]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -399,6 +540,32 @@ inline void tgemm(Launches& L, cudaStream_t st, const char* tag, const CUtensorM
   const int nkb = tap.cpb * ntaps;
   Scope sc(L, st, tag, 2.0 * M * N * K);
   kern<<<grid, Pro::kOn ? 320 : 192, SMEM, st>>>(tmA, tmB, nkb, tap, pro, epi);
+}
+
+// persistent GEMM launchers: plain (A by TMA) and pre-activation (A = relu(bn(X)) produced by warps)
+int sm_count();
+template <int BN, int STAGES, class Epi>
+inline void pgemm(Launches& L, cudaStream_t st, const char* tag, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, Epi epi) {
+  if (M <= 0 || N <= 0) return;
+  auto kern = pgemm_kernel<BN, STAGES, false, Epi>;
+  constexpr int SMEM = smem_bytes(BN, STAGES);
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
+  const int tn = (N + BN - 1) / BN, tiles = ((M + BM - 1) / BM) * tn;
+  Scope sc(L, st, tag, 2.0 * M * N * K);
+  kern<<<tiles < sm_count() ? tiles : sm_count(), 192, SMEM, st>>>(tmA, tmB, nullptr, 0, nullptr, nullptr, M, tn, tiles, (K + BK - 1) / BK, epi);
+}
+template <int BN, int STAGES, class Epi>
+inline void pgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const float* X, int lda, const float* bn_a, const float* bn_b,
+                         const CUtensorMap& tmB, int M, int N, int K, Epi epi) {
+  if (M <= 0 || N <= 0) return;
+  auto kern = pgemm_kernel<BN, STAGES, true, Epi>;
+  constexpr int SMEM = smem_bytes(BN, STAGES);
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
+  const int tn = (N + BN - 1) / BN, tiles = ((M + BM - 1) / BM) * tn;
+  Scope sc(L, st, tag, 2.0 * M * N * K);
+  kern<<<tiles < sm_count() ? tiles : sm_count(), 448, SMEM, st>>>(tmB, tmB, X, lda, bn_a, bn_b, M, tn, tiles, (K + BK - 1) / BK, epi);
 }
 
 template <int BN, int STAGES, class Epi>

@@ -133,6 +133,7 @@ int load_ve(cbx_ctx* c, const TensorMap& t) {
     const int in = l == 0 ? kVeMels : H;
     W.tm_wih[l] = tc::make_map_2d(W.wih[l], G, in, in, 128, true);
     W.tm_wih_p[l] = tc::make_map_2d(W.wih_p[l], G, in, in, 128, true);
+    W.tm_wih_p256[l] = tc::make_map_2d(W.wih_p[l], G, in, in, 256, true);
   }
   W.loaded = true;
   return CBX_OK;
