@@ -22,6 +22,7 @@ using namespace tc;
 constexpr int STAGES = 3;
 constexpr int MAX_TAPS = 10;
 constexpr int W_BYTES = MAX_TAPS * 32 * 128;       // 40 KB: [tap][32 out channels][32 in channels]
+constexpr int OUT_BYTES = 128 * 128;               // 16 KB
 
 struct Plane { int par, f0, dr, nrows; uint32_t bytes, offset; };   // TMA box {32, 1, pitch, nrows} at (0, par, f0, row + dr)
 struct Tap { int plane, start; };                  // A rows start at row `start` of the plane
@@ -29,18 +30,20 @@ struct Params {
   int nplanes, ntaps;
   Plane plane[3];
   Tap tap[MAX_TAPS];
-  int pitch, BR, F_out, rows, row_base, ntiles;
+  int pitch, BR, F_out, rows, row_base, ntiles, res_plane;
   uint32_t stage_bytes;
   const float* bias; const float* res; float* out; const int32_t* row_clip;
 };
 
 __global__ void __launch_bounds__(192, 1)
 fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
-                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ Params p) {
+                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+                const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = smem;
-  uint8_t* sIn = smem + W_BYTES;
+  uint8_t* sOut = smem + W_BYTES;                       // [128 positions][128 B] output staging (swizzled), one tile
+  uint8_t* sIn = sOut + OUT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + STAGES * p.stage_bytes + 2048);
   uint64_t* full = bars;              // [STAGES]
   uint64_t* empty = bars + STAGES;    // [STAGES]
@@ -51,8 +54,9 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm0); tma_prefetch_desc(&tmW);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    tma_prefetch_desc(&tm0); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmOut);
+    // a stage is free when its MMAs have completed and, if it carries a residual plane, the 4 epilogue warps have read it
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], p.res_plane >= 0 ? 5 : 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     mbar_init(wfull, 1);
     fence_barrier_init();
@@ -78,45 +82,62 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
         for (int q = 0; q < p.nplanes; ++q) {
           const Plane& pl = p.plane[q];
           const CUtensorMap* tm = q == 0 ? &tm0 : (q == 1 ? &tm1 : &tm2);
-          tma_load_4d(sIn + s * p.stage_bytes + pl.offset, tm, &full[s], 0, pl.par, pl.f0, r0 + pl.dr);
+          if (q == p.res_plane) tma_load_3d(sIn + s * p.stage_bytes + pl.offset, &tmRes, &full[s], 0, 0, tile * p.BR);
+          else tma_load_4d(sIn + s * p.stage_bytes + pl.offset, tm, &full[s], 0, pl.par, pl.f0, r0 + pl.dr);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(128, 32);
-      mbar_wait(wfull, 0);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int s = it % STAGES, ph = (it / STAGES) & 1;
-        const int a = it & 1, pa = (it >> 1) & 1;
-        mbar_wait(&tempty[a], pa ^ 1);
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t d = tmem_base + a * 32;
-        const uint32_t in = smem_u32(sIn + s * p.stage_bytes);
-        for (int t = 0; t < p.ntaps; ++t) {
-          const uint64_t ad = make_desc_sw128(in + p.plane[p.tap[t].plane].offset + p.tap[t].start * 128);
-          const uint64_t bd = make_desc_sw128(smem_u32(sW + t * 4096));
+    // ===== MMA issuer: the whole warp runs the loop (waits included), one elected lane issues
+    constexpr uint32_t idesc = make_idesc_tf32(128, 32);
+    // per-tap A offsets (16-byte units) once, in registers: the issue loop below is then adds and MMAs only -- with N = 32
+    // an MMA occupies the tensor pipe for ~16 cycles, so descriptor arithmetic on the issuing thread is what would bound it
+    uint32_t aoff[MAX_TAPS];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_tf32(d, ad + (uint64_t)(k * 32 >> 4), bd + (uint64_t)(k * 32 >> 4), idesc, (t | k) != 0);
+    for (int t = 0; t < MAX_TAPS; ++t) aoff[t] = t < p.ntaps ? (p.plane[p.tap[t].plane].offset + (uint32_t)p.tap[t].start * 128u) >> 4 : 0u;
+    const uint64_t dhi = make_desc_sw128(0);                      // descriptor bits other than the start address
+    const uint32_t w16 = smem_u32(sW) >> 4;
+    const int ntaps = p.ntaps;
+    mbar_wait(wfull, 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % STAGES, ph = (it / STAGES) & 1;
+      const int a = it & 1, pa = (it >> 1) & 1;
+      mbar_wait(&tempty[a], pa ^ 1);
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint32_t d = tmem_base + a * 32;
+      const uint32_t in16 = smem_u32(sIn + s * p.stage_bytes) >> 4;
+      if (elect_one()) {
+#pragma unroll
+        for (int t = 0; t < MAX_TAPS; ++t) {
+          if (t < ntaps) {
+            const uint64_t ad = dhi | (uint64_t)((in16 + aoff[t]) & 0x3FFFu);
+            const uint64_t bd = dhi | (uint64_t)((w16 + t * 256) & 0x3FFFu);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (t | k) != 0);
+          }
         }
         umma_commit(&empty[s]);
         umma_commit(&tfull[a]);
       }
+      __syncwarp();
     }
   } else {
-    // ===== epilogue: thread = output position (t, f') of the tile; f' >= F_out are the padding positions
+    // ===== epilogue: thread = output position i = (t, f') of the tile (f' >= F_out are the padding positions).  All global
+    // traffic is TMA: the residual tile arrives as one more plane of the stage, the output tile leaves through a staging
+    // buffer and ONE tensor store whose box is clipped by the tensor's bounds (padding positions / rows past the end).
     const int q = warp & 3;
     const int i = q * 32 + lane;
-    const int t = i / p.pitch, f = i - t * p.pitch;
-    const bool pos_ok = t < p.BR && f < p.F_out;
+    const int t = i / p.pitch;
     float bias[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) bias[c] = __ldg(p.bias + c);
+    float4* so = reinterpret_cast<float4*>(sOut) + i * 8;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int a = it & 1, pa = (it >> 1) & 1;
+      const int s = it % STAGES;
       mbar_wait(&tfull[a], pa);
       tc_fence_after();
       float v[32];
@@ -124,22 +145,29 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[a]);
-      const int row = tile * p.BR + t;
-      if (pos_ok && row < p.rows) {
-        const size_t o = ((size_t)row * p.F_out + f) * kFcmC;
-        const bool live = p.row_clip[row] >= 0;
-        if (p.res) {
-          const float4* rr = reinterpret_cast<const float4*>(p.res + o);
+      if (p.res_plane >= 0) {
+        const float4* rr = reinterpret_cast<const float4*>(sIn + s * p.stage_bytes + p.plane[p.res_plane].offset) + i * 8;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) { const float4 x = rr[c]; v[4 * c] += x.x; v[4 * c + 1] += x.y; v[4 * c + 2] += x.z; v[4 * c + 3] += x.w; }
-        }
+        for (int c = 0; c < 8; ++c) { const float4 x = rr[c ^ (i & 7)]; v[4 * c] += x.x; v[4 * c + 1] += x.y; v[4 * c + 2] += x.z; v[4 * c + 3] += x.w; }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+      const int row = min(tile * p.BR + t, p.rows - 1);
+      const bool live = p.row_clip[row] >= 0;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = live ? fmaxf(v[c] + bias[c], 0.f) : 0.f;
-        float4* oo = reinterpret_cast<float4*>(p.out + o);
+      for (int c = 0; c < 32; ++c) v[c] = live ? fmaxf(v[c] + bias[c], 0.f) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");                      // the previous tile's store has read the staging buffer
 #pragma unroll
-        for (int c = 0; c < 8; ++c) oo[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      for (int c = 0; c < 8; ++c) so[c ^ (i & 7)] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      fence_proxy_async();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        tma_store_3d(&tmOut, sOut, 0, 0, tile * p.BR);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
     }
+    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
@@ -161,12 +189,28 @@ static CUtensorMap make_map(const float* base, int prows, int F, int P, int pitc
   return m;
 }
 
+// [rows][F][32] fp32 output / residual tensor as {32, F, rows}; box {32, pitch, BR}: a store clips f >= F and rows past the end
+static CUtensorMap make_map_out(const float* base, int rows, int F, int pitch, int BR) {
+  CUtensorMap m;
+  memset(&m, 0, sizeof m);
+  cuuint64_t dims[3] = {32, (cuuint64_t)F, (cuuint64_t)rows};
+  cuuint64_t strides[2] = {128, (cuuint64_t)128 * F};
+  cuuint32_t box[3] = {32, (cuuint32_t)pitch, (cuuint32_t)BR};
+  cuuint32_t estr[3] = {1, 1, 1};
+  EncodeTiledFn fn = encode_fn();
+  CUresult r = fn ? fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+                  : CUDA_ERROR_NOT_FOUND;
+  if (r != CUDA_SUCCESS) fprintf(stderr, "libcbx: cuTensorMapEncodeTiled(fcm out) failed (%d) rows=%d F=%d pitch=%d BR=%d\n", (int)r, rows, F, pitch, BR);
+  return m;
+}
+
 }  // namespace fcm
 
 // in: [rows][F_in][32] with one pad row in front (in points at row 0, the map starts one row earlier); prows = rows of the
 // buffer including both pad rows; sf = frequency stride; sc: optional 1x1 stride-2 shortcut source [rows][2*F_out][32].
 void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const float* bias, const float* in, int F_in, int F_out, int sf,
-                     const float* sc, int F_sc, const float* res, float* out, const int32_t* row_clip, int rows, int prows, double flops) {
+                     const float* sc, int F_sc, const float* res, float* out, const int32_t* row_clip, int rows, int prows, double flops, const char* tag) {
   using namespace fcm;
   Params p{};
   const int pitch = sf == 1 ? F_out + 2 : F_out + 1;
@@ -205,17 +249,25 @@ void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const 
     p.tap[9] = Tap{np, 0};
     p.ntaps = 10; ++np;
   }
+  p.res_plane = -1;
+  CUtensorMap tmOut = make_map_out(out, rows, F_out, pitch, BR), tmRes = tmOut;
+  if (res) {
+    p.plane[np] = Plane{0, 0, 0, BR, plane_bytes(BR), off};
+    tmRes = make_map_out(res, rows, F_out, pitch, BR);
+    off += align1k(p.plane[np].bytes);
+    p.res_plane = np; ++np;
+  }
   for (int q = np; q < 3; ++q) tm[q] = tm[0];
   p.nplanes = np;
   p.stage_bytes = off;
-  const int smem = W_BYTES + STAGES * (int)off + 2048 + 1024 + 256;
+  const int smem = W_BYTES + OUT_BYTES + STAGES * (int)off + 2048 + 1024 + 256;
   static int configured = 0;
   if (configured < smem) { cudaFuncSetAttribute(fcm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); configured = 220 * 1024; }
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
   const int grid = p.ntiles < nsm ? p.ntiles : nsm;
-  Scope scp(c->launches, st, "fcm_conv_gemm", flops);
-  fcm_conv_kernel<<<grid, 192, smem, st>>>(tm[0], tm[1], tm[2], tmW, p);
+  Scope scp(c->launches, st, tag, flops);
+  fcm_conv_kernel<<<grid, 192, smem, st>>>(tm[0], tm[1], tm[2], tmW, tmOut, tmRes, p);
 }
 
 }  // namespace cbx

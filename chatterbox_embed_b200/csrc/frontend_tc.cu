@@ -117,25 +117,25 @@ dftmel_kernel(const __grid_constant__ CUtensorMap tmHi0, const __grid_constant__
         }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc0 = make_idesc_tf32(BM, NB0), idesc1 = make_idesc_tf32(BM, NB1);
-      int it = 0;
-      for (int kb = 0; kb < NKB; ++kb) {
-        const int sa = kb % SA, pa = (kb / SA) & 1;
-        mbar_wait(&a_full[sa], pa);
+    // ===== MMA issuer: the whole warp runs the loop, one elected lane issues
+    constexpr uint32_t idesc0 = make_idesc_tf32(BM, NB0), idesc1 = make_idesc_tf32(BM, NB1);
+    int it = 0;
+    for (int kb = 0; kb < NKB; ++kb) {
+      const int sa = kb % SA, pa = (kb / SA) & 1;
+      mbar_wait(&a_full[sa], pa);
+      tc_fence_after();
+      const uint64_t ahi = make_desc_sw128(smem_u32(sA + sa * 2 * A_BYTES));
+      const uint64_t alo = make_desc_sw128(smem_u32(sA + sa * 2 * A_BYTES + A_BYTES));
+      const int ksteps = (kb == NKB - 1) ? (KTOT - (NKB - 1) * BK) / UMMA_K : BK / UMMA_K;
+      for (int q = 0; q < 4; ++q, ++it) {
+        const int s = it % SB, ph = (it / SB) & 1;
+        mbar_wait(&b_full[s], ph);
         tc_fence_after();
-        const uint64_t ahi = make_desc_sw128(smem_u32(sA + sa * 2 * A_BYTES));
-        const uint64_t alo = make_desc_sw128(smem_u32(sA + sa * 2 * A_BYTES + A_BYTES));
-        const int ksteps = (kb == NKB - 1) ? (KTOT - (NKB - 1) * BK) / UMMA_K : BK / UMMA_K;
-        for (int q = 0; q < 4; ++q, ++it) {
-          const int s = it % SB, ph = (it / SB) & 1;
-          mbar_wait(&b_full[s], ph);
-          tc_fence_after();
-          const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
-          const int nb = q >> 1;
-          const uint32_t d = tmem_base + nb * NB0;
-          const uint32_t idesc = nb ? idesc1 : idesc0;
+        const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+        const int nb = q >> 1;
+        const uint32_t d = tmem_base + nb * NB0;
+        const uint32_t idesc = nb ? idesc1 : idesc0;
+        if (elect_one()) {
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t ko = (uint64_t)(k * UMMA_K * 4 >> 4);
             if ((q & 1) == 0) {       // B_hi: A_hi.B_hi + A_lo.B_hi
@@ -146,10 +146,13 @@ dftmel_kernel(const __grid_constant__ CUtensorMap tmHi0, const __grid_constant__
             }
           }
           umma_commit(&b_empty[s]);
+          if (q == 3) {
+            umma_commit(&a_empty[sa]);
+            if (kb == NKB - 1) umma_commit(accum);
+          }
         }
-        umma_commit(&a_empty[sa]);
+        __syncwarp();
       }
-      umma_commit(accum);
     }
   } else {
     // ===== frame producers: warp w fills rows [32 w', 32 w' + 32) of every A stage, lanes along K (coalesced PCM reads)

@@ -415,16 +415,16 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
 
   const size_t blk0 = (size_t)tile * kVePartial * 2 * NSUB;                      // first tiled row of the tile
   if (warp == 0) {
-    // ===================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(128, NSUB);
-      for (int t = 0; t < kVePartial; ++t) {
+    // ===================== MMA issuer: the whole warp runs the loop, one elected lane issues
+    constexpr uint32_t idesc = make_idesc_tf32(128, NSUB);
+    for (int t = 0; t < kVePartial; ++t) {
 #pragma unroll 1
-        for (int x = 0; x < 2; ++x) {
-          if (t > 0) mbar_wait(&full[x], (t - 1) & 1);
-          tc_fence_after();
+      for (int x = 0; x < 2; ++x) {
+        if (t > 0) mbar_wait(&full[x], (t - 1) & 1);
+        tc_fence_after();
+        const uint32_t hb = smem_u32(hbuf + x * H_BYTES);
+        if (elect_one()) {
           if (tr) p.trace[(t * 2 + x) * 8 + 0] = clock64();
-          const uint32_t hb = smem_u32(hbuf + x * H_BYTES);
 #pragma unroll
           for (int kb = 0; kb < CL; ++kb) {
             const uint64_t bd = make_desc_sw128(hb + kb * KB_BYTES);
@@ -435,6 +435,7 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
           umma_commit(&accum[x]);
           if (tr) p.trace[(t * 2 + x) * 8 + 1] = clock64();
         }
+        __syncwarp();
       }
     }
   } else if (warp == 9) {

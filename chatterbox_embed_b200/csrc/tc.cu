@@ -46,21 +46,6 @@ CUtensorMap make_map_2d(const float* base, int64_t rows, int64_t cols, int64_t l
   return m;
 }
 
-CUtensorMap make_map_fcm(const float* base, int rows, int F, int P, int F_out, int BR) {
-  CUtensorMap m;
-  std::memset(&m, 0, sizeof m);
-  cuuint64_t dims[4] = {32, (cuuint64_t)P, (cuuint64_t)(F / P), (cuuint64_t)rows};
-  cuuint64_t strides[3] = {128, (cuuint64_t)128 * P, (cuuint64_t)128 * F};
-  cuuint32_t box[4] = {32, 1, (cuuint32_t)F_out, (cuuint32_t)BR};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  EncodeTiledFn fn = encode_fn();
-  CUresult r = fn ? fn(&m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
-                  : CUDA_ERROR_NOT_FOUND;
-  if (r != CUDA_SUCCESS) fprintf(stderr, "libcbx: cuTensorMapEncodeTiled(fcm) failed (%d) rows=%d F=%d P=%d\n", (int)r, rows, F, P);
-  return m;
-}
-
 }  // namespace tc
 }  // namespace cbx
 

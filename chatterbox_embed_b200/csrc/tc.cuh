@@ -52,6 +52,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// one lane of a fully converged warp (the warp-uniform tcgen05 / TMA instructions are issued from inside `if (elect_one())`
+// with the whole warp running the surrounding loop: that keeps the issue path free of divergence bookkeeping)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
@@ -60,6 +67,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uin
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// shared -> global tensor store (bulk async-group completion); elements of the box outside the tensor are not written
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -195,21 +214,22 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-        mbar_wait(Pro::kOn ? &ready[s] : &full[s], ph);
-        tc_fence_after();
-        const uint64_t ad = make_desc_sw128(smem_u32(sA + s * A_BYTES));
-        const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+    // ===== MMA issuer: the whole warp runs the loop, one elected lane issues =====
+    constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+      mbar_wait(Pro::kOn ? &ready[s] : &full[s], ph);
+      tc_fence_after();
+      const uint64_t ad = make_desc_sw128(smem_u32(sA + s * A_BYTES));
+      const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k)
           umma_tf32(tmem_base, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (kb | k) != 0);
         umma_commit(&empty[s]);
+        if (kb == nkb - 1) umma_commit(accum);
       }
-      umma_commit(accum);
+      __syncwarp();
     }
   } else if (warp < 6) {
     // ===== epilogue: TMEM -> registers -> global =====
@@ -312,21 +332,22 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-        mbar_wait(&afull[s], ph);
-        mbar_wait(&bfull[s], ph);
-        tc_fence_after();
-        const uint64_t ad = make_desc_sw128(smem_u32(sA + s * A_BYTES));
-        const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+    constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+      mbar_wait(&afull[s], ph);
+      mbar_wait(&bfull[s], ph);
+      tc_fence_after();
+      const uint64_t ad = make_desc_sw128(smem_u32(sA + s * A_BYTES));
+      const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < BK / UMMA_K; ++k)
           umma_tf32(tmem_base, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (kb | k) != 0);
         umma_commit(&empty[s]);
+        if (kb == nkb - 1) umma_commit(accum);
       }
-      umma_commit(accum);
+      __syncwarp();
     }
   } else if (warp < 6) {
     mbar_wait(accum, 0);
@@ -433,27 +454,28 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
-      int it = 0, ti = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-        const int a = ti & 1, pa = (ti >> 1) & 1;
-        mbar_wait(&tempty[a], pa ^ 1);
+    constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    int it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
+      const int a = ti & 1, pa = (ti >> 1) & 1;
+      mbar_wait(&tempty[a], pa ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + a * BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES, ph = (it / STAGES) & 1;
+        if (kPro) mbar_wait(&afull[s], ph);
+        mbar_wait(&bfull[s], ph);
         tc_fence_after();
-        const uint32_t d = tmem_base + a * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % STAGES, ph = (it / STAGES) & 1;
-          if (kPro) mbar_wait(&afull[s], ph);
-          mbar_wait(&bfull[s], ph);
-          tc_fence_after();
-          const uint64_t ad = make_desc_sw128(smem_u32(sA + s * A_BYTES));
-          const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+        const uint64_t ad = make_desc_sw128(smem_u32(sA + s * A_BYTES));
+        const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
             umma_tf32(d, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (kb | k) != 0);
           umma_commit(&empty[s]);
+          if (kb == nkb - 1) umma_commit(&tfull[a]);
         }
-        umma_commit(&tfull[a]);
+        __syncwarp();
       }
     }
   } else if (warp < 6) {
@@ -584,114 +606,3 @@ inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const fl
 }  // namespace tc
 }  // namespace cbx
 
-// =====================================================================================================================
-// FCM head 3x3 convolutions (xvector.py:61-127) as implicit GEMMs on tcgen05.
-// Activations are [row][F][32] (time-major, then frequency, channels contiguous).  One CTA computes BR time rows x F_out
-// frequencies (= 120 of the 128 UMMA rows) x 32 output channels.  Each of the 9 taps is one K block of 32 input
-// channels, fetched by ONE 4-D TMA box {32 ch, 1 parity, F_out freqs, BR rows}: the tensor is viewed as
-// [row][F/2][parity][32] for the frequency-stride-2 convs, so the stride disappears into the coordinates, and
-// frequency / time zero padding is TMA out-of-bounds fill.  A 10th tap (other tensor map) carries the residual block's
-// 1x1 stride-2 shortcut conv.
-namespace cbx {
-namespace tc {
-
-struct FcmTap { int src, parity, f0, dr; };
-struct FcmParams {
-  int ntaps; FcmTap tap[10];
-  int F_out, BR, rows, row_base;          // rows of this sub-chunk; row_base = row coordinate of sub-chunk row 0 in the maps
-  const float* bias; const float* res; float* out; const int32_t* row_clip;
-};
-
-constexpr int FCM_STAGES = 4;
-constexpr int fcm_smem_bytes() { return FCM_STAGES * (BM * BK * 4 + 32 * BK * 4) + 1024 + 256; }
-
-static __global__ void __launch_bounds__(192)
-fcm_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                   const __grid_constant__ CUtensorMap tmB, FcmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int STAGES = FCM_STAGES, BN = 32;
-  constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
-  uint64_t* empty = full + STAGES;
-  uint64_t* accum = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = blockIdx.x * p.BR;
-  const int m_valid = p.BR * p.F_out;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(accum, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 32);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < p.ntaps; ++kb) {
-        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], m_valid * BK * 4 + B_BYTES);
-        const FcmTap t = p.tap[kb];
-        tma_load_4d(sA + s * A_BYTES, t.src ? &tmA2 : &tmA, &full[s], 0, t.parity, t.f0, p.row_base + r0 + t.dr);
-        tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * BK, 0);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
-      for (int kb = 0; kb < p.ntaps; ++kb) {
-        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint64_t ad = make_desc_sw128(smem_u32(sA + s * A_BYTES));
-        const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
-#pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k)
-          umma_tf32(tmem_base, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (kb | k) != 0);
-        umma_commit(&empty[s]);
-      }
-      umma_commit(accum);
-    }
-  } else {
-    mbar_wait(accum, 0);
-    tc_fence_after();
-    const int q = warp & 3;
-    const int ml = q * 32 + lane;
-    float v[32];
-    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), v);
-    const int lr = ml / p.F_out;
-    const int row = r0 + lr;
-    if (ml < m_valid && row < p.rows) {
-      const size_t o = ((size_t)row * p.F_out + (ml - lr * p.F_out)) * kFcmC;
-      const bool live = p.row_clip[row] >= 0;
-      if (p.res) {
-        const float4* rr = reinterpret_cast<const float4*>(p.res + o);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { const float4 x = rr[i]; v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w; }
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = live ? fmaxf(v[i] + __ldg(p.bias + i), 0.f) : 0.f;
-      float4* oo = reinterpret_cast<float4*>(p.out + o);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) oo[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 32); }
-}
-
-// [rows][F][32] fp32 activation viewed as {32, P, F/P, rows}; box {32, 1, F_out, BR}
-CUtensorMap make_map_fcm(const float* base, int rows, int F, int P, int F_out, int BR);
-
-}  // namespace tc
-}  // namespace cbx

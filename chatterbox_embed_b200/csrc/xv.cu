@@ -400,10 +400,14 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
       else { Scope sc(L, st, "fcm_conv1_kernel"); fcm_conv1_kernel<<<(unsigned)((npos + 7) / 8), 256, 0, st>>>(ch.fbank, ch.cmn_sum, ch.fb_row_clip, W.conv1_w, W.conv1_b, b0, s.r0, rows, ch.fb_rows); }
     }
     // in: [row][F_in][32] (pad row in front), optional shortcut source sc [row][F_sc][32], residual res / out [row][F_out][32]
+    int conv_idx = 0;
+    static const char* kConvTags[9] = {"fcm_conv_gemm:l1b0c1", "fcm_conv_gemm:l1b0c2", "fcm_conv_gemm:l1b1c1", "fcm_conv_gemm:l1b1c2", "fcm_conv_gemm:l2b0c1",
+                                       "fcm_conv_gemm:l2b0c2", "fcm_conv_gemm:l2b1c1", "fcm_conv_gemm:l2b1c2", "fcm_conv_gemm:head2"};
     auto conv = [&](const ConvW& w, const CUtensorMap& tmw, const float* in, int F_in, int F_out, int sf, const float* sc, int F_sc,
                     const float* res, float* out) {
       if (c->mode == 1) {
-        run_fcm_conv_tc(c, st, tmw, w.bias, in, F_in, F_out, sf, sc, F_sc, res, out, rc, rows, ch.fcm_rows + 2, 2.0 * rows * F_out * kFcmC * w.K);
+        const char* tag = c->launches.prof ? kConvTags[conv_idx++ % 9] : "fcm_conv_gemm";
+        run_fcm_conv_tc(c, st, tmw, w.bias, in, F_in, F_out, sf, sc, F_sc, res, out, rc, rows, ch.fcm_rows + 2, 2.0 * rows * F_out * kFcmC * w.K, tag);
       } else {
         sgemm(L, st, "fcm_conv_gemm", rows * F_out, kFcmC, w.K, FcmConvA{in, F_in, F_out, sf, sc, F_sc}, w.w, w.K, FcmEpi{out, w.bias, res, rc, F_out});
       }
