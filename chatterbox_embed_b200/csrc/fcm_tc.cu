@@ -266,7 +266,7 @@ void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const 
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
   const int grid = p.ntiles < nsm ? p.ntiles : nsm;
-  Scope scp(c->launches, st, tag, flops);
+  Scope scp(c->launches, st, tag, flops, 128.0 * rows * (F_in + F_out + (sc ? F_out : 0) + (res ? F_out : 0)));   // in + out (+ shortcut / residual)
   fcm_conv_kernel<<<grid, 192, smem, st>>>(tm[0], tm[1], tm[2], tmW, tmOut, tmRes, p);
 }
 

@@ -591,7 +591,7 @@ void run_lstm_rec_tc(cbx_ctx* c, const float* xw, const int32_t* slot_row, const
   }
   lstm::Params p{xw, slot_row, whh_perm, hseq, hlast, n_slots, (long long*)c->lstm_trace, (int)c->lstm_dbg};
   const int tiles = (n_slots + lstm::TILE - 1) / lstm::TILE;
-  Scope sc(c->launches, st, "lstm_rec_tc_kernel", 2.0 * n_slots * kVePartial * kVeHidden * kVeGates);
+  Scope sc(c->launches, st, "lstm_rec_tc_kernel", 2.0 * n_slots * kVePartial * kVeHidden * kVeGates, 4.0 * n_slots * kVePartial * (kVeGates + kVeHidden));
   lstm::lstm_rec_tc_kernel<<<tiles * lstm::CL, lstm::THREADS, lstm::SMEM_BYTES, st>>>(p);
 }
 
@@ -632,7 +632,7 @@ void run_lstm_rec_tc2(cbx_ctx* c, const float* xw, const int32_t* slot_row, cons
   const int64_t rows = (int64_t)tiles * lstm::TILE * kVePartial;
   CUtensorMap tmH = tc::make_map_2d(hseq, rows, kVeHidden, kVeHidden, lstm::NSUB, false);
   lstm::Params2 p{xw, slot_row, whh_perm, hseq, hlast, n_slots, (long long*)c->lstm_trace};
-  Scope sc(c->launches, st, "lstm_rec_tc_kernel", 2.0 * n_slots * kVePartial * kVeHidden * kVeGates);
+  Scope sc(c->launches, st, "lstm_rec_tc_kernel", 2.0 * n_slots * kVePartial * kVeHidden * kVeGates, 4.0 * n_slots * kVePartial * (kVeGates + kVeHidden));
   if (slot_row) lstm::lstm_rec_tc2_kernel<true><<<tiles * lstm::CL, lstm::THREADS2, lstm::SMEM_BYTES, st>>>(tmH, p);
   else lstm::lstm_rec_tc2_kernel<false><<<tiles * lstm::CL, lstm::THREADS2, lstm::SMEM_BYTES, st>>>(tmH, p);
 }

@@ -560,7 +560,7 @@ inline void tgemm(Launches& L, cudaStream_t st, const char* tag, const CUtensorM
   if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
   const int nkb = tap.cpb * ntaps;
-  Scope sc(L, st, tag, 2.0 * M * N * K);
+  Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * (K / ntaps) + (double)M * N));   // algorithmic bytes: A once + C
   kern<<<grid, Pro::kOn ? 320 : 192, SMEM, st>>>(tmA, tmB, nkb, tap, pro, epi);
 }
 
@@ -574,7 +574,7 @@ inline void pgemm(Launches& L, cudaStream_t st, const char* tag, const CUtensorM
   static bool configured = false;
   if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
   const int tn = (N + BN - 1) / BN, tiles = ((M + BM - 1) / BM) * tn;
-  Scope sc(L, st, tag, 2.0 * M * N * K);
+  Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
   kern<<<tiles < sm_count() ? tiles : sm_count(), 192, SMEM, st>>>(tmA, tmB, nullptr, 0, nullptr, nullptr, M, tn, tiles, (K + BK - 1) / BK, epi);
 }
 template <int BN, int STAGES, class Epi>
@@ -586,7 +586,7 @@ inline void pgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const fl
   static bool configured = false;
   if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
   const int tn = (N + BN - 1) / BN, tiles = ((M + BM - 1) / BM) * tn;
-  Scope sc(L, st, tag, 2.0 * M * N * K);
+  Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
   kern<<<tiles < sm_count() ? tiles : sm_count(), 448, SMEM, st>>>(tmB, tmB, X, lda, bn_a, bn_b, M, tn, tiles, (K + BK - 1) / BK, epi);
 }
 
@@ -599,7 +599,7 @@ inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const fl
   static bool configured = false;
   if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-  Scope sc(L, st, tag, 2.0 * M * N * K);
+  Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
   kern<<<grid, 448, SMEM, st>>>(X, lda, M, bn_a, bn_b, tmB, (K + BK - 1) / BK, epi);
 }
 

@@ -259,3 +259,26 @@ def test_mode1_golden_stages(models, mode1, golden_dir):
     assert np.abs(ve - g["ve_emb"]).max() <= 1e-3 and min(cos(a, b) for a, b in zip(ve, g["ve_emb"])) >= 0.9999
     assert np.abs(xv - g["xv_emb"]).max() <= 1e-3 * max(1.0, np.abs(g["xv_emb"]).max())
     assert min(cos(a, b) for a, b in zip(xv, g["xv_emb"])) >= 0.9999
+
+
+def test_mode1_ragged_config3(models, mode1):
+    """BASELINE config 3 shape (ragged 3-30 s clips, variable partial counts, per-clip CMN / CAM means / stats pooling) at a
+    reduced clip count: a sample of clips -- including the shortest and the longest -- against the per-clip oracle (the
+    reference itself has no masking: ragged parity is defined against B=1 runs)."""
+    sdv, sdc, emb = _emb(models, "W1")
+    lens = [int(x) for x in synth.ragged_lengths(40)]
+    wavs = [synth.clip(i, n) for i, n in enumerate(lens)]
+    ve, xv = emb.embed_wavs(wavs)
+    assert np.isfinite(ve).all() and np.isfinite(xv).all()
+    assert np.abs(np.linalg.norm(ve, axis=1) - 1).max() < 1e-5
+    pick = sorted({int(np.argmin(lens)), int(np.argmax(lens)), 7, 23})
+    want_ve = nets.ve_embed_wavs(sdv, [wavs[i] for i in pick])
+    want_xv = nets.campplus_embed_wavs(sdc, [wavs[i] for i in pick])
+    scale = max(1.0, float(np.abs(want_xv).max()))
+    assert np.abs(ve[pick] - want_ve).max() <= 1e-3 and min(cos(a, b) for a, b in zip(ve[pick], want_ve)) >= 0.9999
+    assert np.abs(xv[pick] - want_xv).max() <= 1e-3 * scale and min(cos(a, b) for a, b in zip(xv[pick], want_xv)) >= 0.9999
+    # integer plan of every clip is the reference's arithmetic (bit-exact)
+    for n in lens:
+        pl = _lib.plan_clip(n)
+        assert (pl.ve_partials, pl.ve_target) == nets.num_wins(1 + n // 160)
+        assert pl.xv_frames == 1 + (n - 400) // 160 and pl.xv_tdnn == (pl.xv_frames - 1) // 2 + 1

@@ -6,5 +6,6 @@ tot = sum(v["ms_per_step"] for v in d["kernels"].values())
 print(f"sum of kernel ms/step {tot:.2f}")
 for k, v in d["kernels"].items():
     tf = v["tflops"]
-    print(f"  {k:28s} {v['ms_per_step']:9.3f} ms {100*v['ms_per_step']/tot:5.1f}%  n={v['launches_per_step']:6.0f}  {'' if tf is None else f'{tf:7.1f} TF/s'}")
+    gb = v.get("gbs")
+    print(f"  {k:28s} {v['ms_per_step']:9.3f} ms {100*v['ms_per_step']/tot:5.1f}%  n={v['launches_per_step']:6.0f}  {'' if tf is None else f'{tf:7.1f} TF/s'}  {'' if gb is None else f'{gb:7.0f} GB/s'}")
 if d.get("cpu_baseline"): print("cpu", d["cpu_baseline"])
