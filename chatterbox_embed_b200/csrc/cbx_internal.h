@@ -224,6 +224,8 @@ void run_ve_forward_partials(cbx_ctx* c, const float* mels, int n, float* out, v
 // frontend_tc.cu: frames -> 3xTF32 DFT GEMM -> power -> sparse mel (-> log) in one kernel
 void run_ve_mel_tc(cbx_ctx* c, const float* pcm, const VeChunk& ch, cudaStream_t st);
 void run_kaldi_fbank_tc(cbx_ctx* c, const float* pcm, const XvChunk& ch, cudaStream_t st);
+void run_local_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmU, const CUtensorMap& tmW, const CUtensorMap& tmOut, int M, int dil,
+                       int col0, const float* gate, const int32_t* row_seg);   // local_tc.cu
 int lstm_padded_slots(int n_slots);     // slots rounded up to whole 224-partial cluster tiles (lstm_tc.cu)
 void run_lstm_rec_tc2(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
                       int n_slots, cudaStream_t st);

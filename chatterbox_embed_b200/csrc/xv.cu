@@ -453,8 +453,8 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     CUtensorMap tm_cat, tm_u;
     tc::TapMap tap_local{};
     if (tcm) {
-      tm_cat = tc::make_map_2d(cat, M, ld, ld, tc::BM, false);        // fp32: the prologue warps round after BN+ReLU
-      tm_u = tc::make_map_2d(ch.u, M, kBnC, kBnC, tc::BM, true);
+      tm_u = tc::make_map_2d(ch.u, M, kBnC, kBnC, tc::BM + 2 * kDil[b], true);        // halo block: 128 + 2 d frames
+      tm_cat = tc::make_map_2d(cat, M, ld, ld, tc::BM, false);                           // store target of the 32 new channels
       tap_local.cpb = kBnC / tc::BK;
       for (int t = 0; t < 3; ++t) tap_local.shift[t] = (t - 1) * kDil[b];
     }
@@ -473,8 +473,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
         { Scope sc(L, st, "cam_gate_kernel"); cam_gate_kernel<<<ch.segs, 128, 0, st>>>(ch.seg_sum, ch.plan, ch.seg_clip, D, ch.gate); }
       }
       if (tcm)
-        tc::tgemm<32, 4>(L, st, "dense_local_gemm", tm_u, W.tm_wl[li], M, kGrowth, 3 * kBnC, tap_local, 3, tc::NoPrologue{},
-                         tc::EpiGate{cat, ld, D.cin, ch.gate, ch.td_row_seg, M});
+        run_local_conv_tc(c, st, tm_u, W.tm_wl[li], tm_cat, M, kDil[b], D.cin, ch.gate, ch.td_row_seg);
       else
         sgemm(L, st, "dense_local_gemm", M, kGrowth, 3 * kBnC, LocalConvA{ch.u, kDil[b], M}, D.wl, 3 * kBnC, GateEpi{cat, ld, D.cin, ch.gate, ch.td_row_seg});
     }
