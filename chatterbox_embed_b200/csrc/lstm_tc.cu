@@ -322,6 +322,13 @@ constexpr int HALF = NSUB / 2;             // partials per gate warp and half-st
 constexpr int CH2 = 8;                     // partials per tcgen05.ld in v2
 static_assert(HALF % CH2 == 0, "chunking");
 
+// streaming 4-byte load that does not allocate in L1: the unified L1 / shared-memory array is busy feeding the tensor core
+__device__ __forceinline__ float ldg_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 struct Params2 {
   const float* xw;            // layer 0: [mel rows][1024] gathered through slot_row; else tiled time-major [tiles*160*224][1024]
   const int32_t* slot_row;    // layer 0 only
@@ -446,7 +453,7 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
         for (int x = 0; x < 2; ++x) {
           const int hs = 2 * t + x;
           mbar_wait(&ready[x], t & 1);
-          fence_proxy_async();
+          asm volatile("fence.proxy.async.global;" ::: "memory");
           if (tr) p.trace[(t * 2 + x) * 8 + 5] = clock64();
           mbar_wait_cluster(&freeb[x], t & 1);
           if (tr) p.trace[(t * 2 + x) * 8 + 6] = clock64();
@@ -480,9 +487,9 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
     auto xw_load = [&](int hs, int n) -> float {     // input projection of partial n0 + n for half-step hs = 2 t + x
       if (kLayer0) {
         const int x = hs & 1, t = hs >> 1;
-        return __ldg(xq + (size_t)(rowbase[x * NSUB + n0 + n] + t) * kVeGates);
+        return ldg_stream_f32(xq + (size_t)(rowbase[x * NSUB + n0 + n] + t) * kVeGates);
       }
-      return __ldg(xq + ((size_t)hs * NSUB + n) * kVeGates);
+      return ldg_stream_f32(xq + ((size_t)hs * NSUB + n) * kVeGates);
     };
     // activations of one 8-column chunk: own gate of 8 partials; two shared reciprocals
     auto activate = [&](int x, int c, const float* xin, float* a) {
@@ -516,7 +523,7 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
           // publish the PREVIOUS half-step's slice now: its stores have had the whole accumulator wait to reach L2, so the
           // fence is cheap, and the exchange it triggers is not needed before this half-step's math is over anyway
           __threadfence();
-          fence_proxy_async();                        // generic-proxy stores ordered before the exchange warp's TMA read
+          asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy GLOBAL stores ordered before the exchange warp's TMA read
           mbar_arrive(&ready[x ^ 1]);
         }
         float* hrow = hq + (size_t)hs * NSUB * kVeHidden;

@@ -52,6 +52,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// streaming 16-byte global load that does not allocate in L1 (the unified L1 / shared-memory array is the scarce resource of
+// the producer-fed GEMMs: tensor-core operand reads, stage stores and TMA writes all go through it)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 // one lane of a fully converged warp (the warp-uniform tcgen05 / TMA instructions are issued from inside `if (elect_one())`
 // with the whole warp running the surrounding loop: that keeps the issue path free of divergence bookkeeping)
 __device__ __forceinline__ bool elect_one() {
@@ -297,7 +304,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 constexpr int PG = 2;     // producer groups
 
 template <int BN, int STAGES, class Epi>
-__global__ void __launch_bounds__(448, 2)
+__global__ void __launch_bounds__(320, 2)
 tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __restrict__ bn_a, const float* __restrict__ bn_b,
                     const __grid_constant__ CUtensorMap tmB, int nkb, Epi epi) {
   extern __shared__ uint8_t smem_raw[];
@@ -354,33 +361,28 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
       }
       __syncwarp();
     }
-  } else if (warp < 6) {
-    mbar_wait(accum, 0);
-    tc_fence_after();
-    const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      epi(row, n0 + c, v);
-    }
-    tc_fence_before();
   } else {
-    // ===== producers: thread = (16-byte chunk of the 128-byte row, row r0 + 16 i)
-    const int g = (warp - 6) >> 2;
-    const int t = (threadIdx.x - 192) & 127;
+    // ===== producers (warps 2..9, two groups of 4 alternating K blocks): thread = (16-byte chunk of the 128-byte row, row
+    // r0 + 16 i).  Two register buffers used in turn (the loop is unrolled by two so that no buffer is ever copied): the
+    // loads of the group's NEXT K block are in flight while the current one is transformed, four K blocks per CTA towards
+    // HBM.  (fence.proxy.async.shared::cta does not wait for outstanding global loads -- measured, tools/fencebench.cu.)
+    // Warps 2..5 run the epilogue once their K blocks are done.
+    const int g = (warp - 2) >> 2;
+    const int t = (threadIdx.x - 64) & 127;
     const int chunk = t & 7, r0 = t >> 3;
     const float* xp = X + (size_t)(m0 + r0) * lda + chunk * 4;
-    for (int kb = g; kb < nkb; kb += PG) {
-      const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+    float4 xa[BM / 16 + 2], xb[BM / 16 + 2];        // 8 rows of X plus the K block's BN scale / shift
+    auto load = [&](float4* dst, int kb) {
       const int kcol = kb * BK;
-      float4 x[BM / 16];
 #pragma unroll
       for (int i = 0; i < BM / 16; ++i)
-        x[i] = (m0 + r0 + i * 16 < M) ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)i * 16 * lda + kcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(bn_a + kcol + chunk * 4));
-      const float4 sh = __ldg(reinterpret_cast<const float4*>(bn_b + kcol + chunk * 4));
+        dst[i] = (m0 + r0 + i * 16 < M) ? ldg_stream(reinterpret_cast<const float4*>(xp + (size_t)i * 16 * lda + kcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      dst[BM / 16] = __ldg(reinterpret_cast<const float4*>(bn_a + kcol + chunk * 4));
+      dst[BM / 16 + 1] = __ldg(reinterpret_cast<const float4*>(bn_b + kcol + chunk * 4));
+    };
+    auto produce = [&](const float4* x, int kb) {
+      const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+      const float4 sc = x[BM / 16], sh = x[BM / 16 + 1];
       mbar_wait(&empty[s], ph ^ 1);
       float4* base = reinterpret_cast<float4*>(sA + s * A_BYTES);
 #pragma unroll
@@ -395,6 +397,28 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
       }
       fence_proxy_async();
       mbar_arrive(&afull[s]);
+    };
+    if (g < nkb) load(xa, g);
+    for (int kb = g; kb < nkb; kb += 2 * PG) {
+      if (kb + PG < nkb) load(xb, kb + PG);
+      produce(xa, kb);
+      if (kb + PG < nkb) {
+        if (kb + 2 * PG < nkb) load(xa, kb + 2 * PG);
+        produce(xb, kb + PG);
+      }
+    }
+    if (warp < 6) {
+      mbar_wait(accum, 0);
+      tc_fence_after();
+      const int q = warp & 3;
+      const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        epi(row, n0 + c, v);
+      }
+      tc_fence_before();
     }
   }
   __syncthreads();
@@ -605,7 +629,7 @@ inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const fl
   if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
   Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
-  kern<<<grid, 448, SMEM, st>>>(X, lda, M, bn_a, bn_b, tmB, (K + BK - 1) / BK, epi);
+  kern<<<grid, 320, SMEM, st>>>(X, lda, M, bn_a, bn_b, tmB, (K + BK - 1) / BK, epi);
 }
 
 }  // namespace tc
