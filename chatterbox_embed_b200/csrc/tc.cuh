@@ -436,9 +436,12 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
 // kPro = false: A tiles come by TMA (tf32 rounding in the tensor map); warps 0 = TMA, 1 = MMA, 2..5 = epilogue.
 // kPro = true:  A is produced by warps 6..13 (two groups alternating K blocks): coalesced 16-byte loads of X, BatchNorm +
 //               ReLU + tf32 rounding in registers, one store into the swizzled stage (pre-activation D-TDNN layers).
-template <int BN, int STAGES, bool kPro, class Epi>
+// kTmaC = true: the epilogue is "+ bias" and the C tile leaves through two 16 KB staging buffers and TMA tensor stores
+// (one 128 x 32 box per accumulator chunk) instead of per-thread 16-byte stores scattered over 32 rows.
+template <int BN, int STAGES, bool kPro, bool kTmaC, class Epi>
 __global__ void __launch_bounds__(kPro ? 448 : 192, 1)
-pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const float* __restrict__ X, int lda,
+pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+             const float* __restrict__ X, int lda,
              const float* __restrict__ bn_a, const float* __restrict__ bn_b, int M, int n_tiles_n, int n_tiles, int nkb, Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -453,10 +456,12 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tfull = empty + STAGES;          // [2] accumulator ready
   uint64_t* tempty = tfull + 2;              // [2] accumulator drained (4 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint8_t* sC = smem + STAGES * (A_BYTES + B_BYTES) + 1024;    // [2][128 rows x 128 B] C staging (kTmaC)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     if (!kPro) tma_prefetch_desc(&tmA);
+    if (kTmaC) tma_prefetch_desc(&tmC);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&afull[s], 128); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
@@ -525,9 +530,28 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[a]);
         }
-        epi(row, n0 + c, v);
+        if constexpr (kTmaC) {
+          const int i = q * 32 + lane;
+          const int buf = (c >> 5) & 1;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(epi.bias + n0 + c + j);
+          if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used `buf` has read it
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          float4* so = reinterpret_cast<float4*>(sC + buf * (BM * 128)) + i * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) so[j ^ (i & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_proxy_async();
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (warp == 2 && lane == 0) {
+            tma_store_2d(&tmC, sC + buf * (BM * 128), n0 + c, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else {
+          epi(row, n0 + c, v);
+        }
       }
     }
+    if (kTmaC && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (kPro) {
     const int g = (warp - 6) >> 2;
     const int t = (threadIdx.x - 192) & 127;
@@ -593,30 +617,46 @@ inline void tgemm(Launches& L, cudaStream_t st, const char* tag, const CUtensorM
   kern<<<grid, Pro::kOn ? 320 : 192, SMEM, st>>>(tmA, tmB, nkb, tap, pro, epi);
 }
 
+struct EpiBiasPtr { const float* bias; __device__ void operator()(int, int, float*) const {} };
+
 // persistent GEMM launchers: plain (A by TMA) and pre-activation (A = relu(bn(X)) produced by warps)
 int sm_count();
 template <int BN, int STAGES, class Epi>
 inline void pgemm(Launches& L, cudaStream_t st, const char* tag, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, Epi epi) {
   if (M <= 0 || N <= 0) return;
-  auto kern = pgemm_kernel<BN, STAGES, false, Epi>;
+  auto kern = pgemm_kernel<BN, STAGES, false, false, Epi>;
   constexpr int SMEM = smem_bytes(BN, STAGES);
   static bool configured = false;
   if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
   const int tn = (N + BN - 1) / BN, tiles = ((M + BM - 1) / BM) * tn;
   Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
-  kern<<<tiles < sm_count() ? tiles : sm_count(), 192, SMEM, st>>>(tmA, tmB, nullptr, 0, nullptr, nullptr, M, tn, tiles, (K + BK - 1) / BK, epi);
+  kern<<<tiles < sm_count() ? tiles : sm_count(), 192, SMEM, st>>>(tmA, tmB, tmB, nullptr, 0, nullptr, nullptr, M, tn, tiles, (K + BK - 1) / BK, epi);
+}
+// C[M][N] (row-major, leading dimension ldc) = A . W^T + bias, C written with TMA tensor stores
+template <int BN, int STAGES>
+inline void pgemm_bias_tma(Launches& L, cudaStream_t st, const char* tag, const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int ldc,
+                           const float* bias, int M, int N, int K) {
+  if (M <= 0 || N <= 0) return;
+  auto kern = pgemm_kernel<BN, STAGES, false, true, EpiBiasPtr>;
+  constexpr int SMEM = smem_bytes(BN, STAGES) + 1024 + 2 * BM * 128;
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
+  const int tn = (N + BN - 1) / BN, tiles = ((M + BM - 1) / BM) * tn;
+  CUtensorMap tmC = make_map_2d(C, M, N, ldc, BM, false);
+  Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
+  kern<<<tiles < sm_count() ? tiles : sm_count(), 192, SMEM, st>>>(tmA, tmB, tmC, nullptr, 0, nullptr, nullptr, M, tn, tiles, (K + BK - 1) / BK, EpiBiasPtr{bias});
 }
 template <int BN, int STAGES, class Epi>
 inline void pgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const float* X, int lda, const float* bn_a, const float* bn_b,
                          const CUtensorMap& tmB, int M, int N, int K, Epi epi) {
   if (M <= 0 || N <= 0) return;
-  auto kern = pgemm_kernel<BN, STAGES, true, Epi>;
+  auto kern = pgemm_kernel<BN, STAGES, true, false, Epi>;
   constexpr int SMEM = smem_bytes(BN, STAGES);
   static bool configured = false;
   if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
   const int tn = (N + BN - 1) / BN, tiles = ((M + BM - 1) / BM) * tn;
   Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
-  kern<<<tiles < sm_count() ? tiles : sm_count(), 448, SMEM, st>>>(tmB, tmB, X, lda, bn_a, bn_b, M, tn, tiles, (K + BK - 1) / BK, epi);
+  kern<<<tiles < sm_count() ? tiles : sm_count(), 448, SMEM, st>>>(tmB, tmB, tmB, X, lda, bn_a, bn_b, M, tn, tiles, (K + BK - 1) / BK, epi);
 }
 
 template <int BN, int STAGES, class Epi>
