@@ -45,6 +45,8 @@ _SIGS = {
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "cbx_embed_host": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_int, C.c_float, C.c_int, C.c_double,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "cbx_embed_host_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, _P(C.c_int64), C.c_int, C.c_float, C.c_int, C.c_double, C.c_int]),
+    "cbx_embed_host_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cbx_ve_forward_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "cbx_ve_forward_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int]),
     "cbx_locate": (C.c_int, [C.c_void_p, C.c_char_p, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64), _P(C.c_int64)]),
@@ -164,6 +166,25 @@ class Context:
                                          step, min_cov, ve.ctypes.data if ve is not None else None,
                                          xv.ctypes.data if xv is not None else None, status.ctypes.data, flags),
                     "cbx_embed_host")
+        return ve, xv, status
+
+    def embed_host_submit(self, slot: int, pcm: np.ndarray, offsets: np.ndarray, trim_top_db: float, step: int, min_cov: float, flags: int):
+        """Streaming form: enqueue copies + kernels for one batch in slot 0/1 and return at once.  ``pcm`` (and, with
+        PCM_PINNED, its contents) must stay alive until ``embed_host_wait(slot)``."""
+        n = len(offsets) - 1
+        assert pcm.dtype == np.float32 and pcm.flags.c_contiguous
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._check(lib().cbx_embed_host_submit(self._h, int(slot), pcm.ctypes.data, off.ctypes.data_as(_P(C.c_int64)), n,
+                                                float(trim_top_db), step, min_cov, flags), "cbx_embed_host_submit")
+        self.__dict__.setdefault("_pending", {})[int(slot)] = (n, flags, pcm)
+
+    def embed_host_wait(self, slot: int):
+        n, flags, _keepalive = self.__dict__.get("_pending", {}).pop(int(slot))
+        ve = np.empty((n, 256), np.float32) if flags & DO_VE else None
+        xv = np.empty((n, 192), np.float32) if flags & DO_XV else None
+        status = np.zeros(n, np.int32)
+        self._check(lib().cbx_embed_host_wait(self._h, int(slot), ve.ctypes.data if ve is not None else None,
+                                              xv.ctypes.data if xv is not None else None, status.ctypes.data), "cbx_embed_host_wait")
         return ve, xv, status
 
     def ve_forward_workspace_bytes(self, n: int) -> int:

@@ -206,6 +206,13 @@ int cbx_create(int device, cbx_ctx** out) {
   int rc = build_frontend_tables(c);
   if (rc) { g_create_err = c->err; delete c; return rc; }
   cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking);
+  for (auto& s : c->slot) {
+    cudaEventCreateWithFlags(&s.h2d, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.comp, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&s.d2h, cudaEventDisableTiming);
+  }
   *out = c;
   return CBX_OK;
 }
@@ -214,10 +221,19 @@ void cbx_destroy(cbx_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaFree(c->ve.blob); cudaFree(c->xv.blob); cudaFree(c->ft.blob);
-  cudaFree(c->own_ws); cudaFree(c->own_pcm); cudaFree(c->own_out);
-  if (c->pin_pcm) cudaFreeHost(c->pin_pcm);
-  if (c->pin_out) cudaFreeHost(c->pin_out);
+  cudaDeviceSynchronize();
+  cudaFree(c->own_ws);
+  for (auto& s : c->slot) {
+    cudaFree(s.dev_pcm); cudaFree(s.dev_out);
+    if (s.pin_pcm) cudaFreeHost(s.pin_pcm);
+    if (s.pin_out) cudaFreeHost(s.pin_out);
+    if (s.h2d) cudaEventDestroy(s.h2d);
+    if (s.comp) cudaEventDestroy(s.comp);
+    if (s.d2h) cudaEventDestroy(s.d2h);
+  }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   delete c;
 }
 
@@ -316,7 +332,7 @@ int cbx_embed(cbx_ctx* c, const float* pcm, const int64_t* off, int n, float tri
   return CBX_OK;
 }
 
-static int grow(cbx_ctx* c, void** p, int64_t* have, int64_t want, bool pinned) {
+static int grow(cbx_ctx* c, void** p, int64_t* have, int64_t want, bool pinned) {   // sizes in bytes
   if (*have >= want) return CBX_OK;
   if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *have = 0; }
   want = want + want / 8;
@@ -325,42 +341,72 @@ static int grow(cbx_ctx* c, void** p, int64_t* have, int64_t want, bool pinned) 
   return CBX_OK;
 }
 
-int cbx_embed_host(cbx_ctx* c, const float* pcm_host, const int64_t* off, int n, float trim_top_db, int step, double min_cov,
-                   float* ve_out_host, float* xv_out_host, int32_t* status_host, int flags) {
+int cbx_embed_host_submit(cbx_ctx* c, int slot_id, const float* pcm_host, const int64_t* off, int n, float trim_top_db, int step,
+                          double min_cov, int flags) {
   int rc = check_inputs(c, off, n, step, flags);
   if (rc) return rc;
   if (!pcm_host) { c->err = "null pcm"; return CBX_ERR_ARG; }
+  if (slot_id < 0 || slot_id > 1) { c->err = "slot must be 0 or 1"; return CBX_ERR_ARG; }
+  cbx_ctx::HostSlot& s = c->slot[slot_id];
+  if (s.busy) { c->err = "slot still holds an unclaimed batch: call cbx_embed_host_wait first"; return CBX_ERR_STATE; }
   cudaSetDevice(c->device);
-  cudaStream_t st = c->own_stream;
   const int64_t total = off[n] - off[0];
   Batch b{n, off, step, min_cov};
   const int64_t need_ws = workspace_bytes_for(c, b, flags);
-  int64_t bytes;
-  bytes = c->own_ws_bytes; if ((rc = grow(c, &c->own_ws, &bytes, need_ws, false))) return rc; c->own_ws_bytes = bytes;
-  bytes = c->own_pcm_floats * 4; if ((rc = grow(c, (void**)&c->own_pcm, &bytes, (total + 512) * 4, false))) return rc; c->own_pcm_floats = bytes / 4;
-  const int64_t out_floats = (int64_t)n * (kVeEmbed + kXvEmbed + 1);
-  bytes = c->own_out_floats * 4; if ((rc = grow(c, (void**)&c->own_out, &bytes, out_floats * 4, false))) return rc; c->own_out_floats = bytes / 4;
+  if (c->own_ws_bytes < need_ws) {
+    // growing the shared workspace: nothing may still be running in it
+    CBX_CUDA_OK(c, cudaStreamSynchronize(c->own_stream));
+    if ((rc = grow(c, &c->own_ws, &c->own_ws_bytes, need_ws, false))) return rc;
+  }
+  const int64_t out_bytes = (int64_t)n * (kVeEmbed + kXvEmbed + 1) * 4;
+  if ((rc = grow(c, (void**)&s.dev_pcm, &s.dev_pcm_bytes, (total + 512) * 4, false))) return rc;
+  if ((rc = grow(c, (void**)&s.dev_out, &s.dev_out_bytes, out_bytes, false))) return rc;
+  if ((rc = grow(c, (void**)&s.pin_out, &s.pin_out_bytes, out_bytes, true))) return rc;
   const bool pinned_in = (flags & CBX_PCM_PINNED) != 0;
-  if (!pinned_in) { bytes = c->pin_pcm_floats * 4; if ((rc = grow(c, (void**)&c->pin_pcm, &bytes, (total + 512) * 4, true))) return rc; c->pin_pcm_floats = bytes / 4; }
-  bytes = c->pin_out_floats * 4; if ((rc = grow(c, (void**)&c->pin_out, &bytes, out_floats * 4, true))) return rc; c->pin_out_floats = bytes / 4;
+  if (!pinned_in && (rc = grow(c, (void**)&s.pin_pcm, &s.pin_pcm_bytes, (total + 512) * 4, true))) return rc;
 
-  // offsets relative to the first clip
   std::vector<int64_t> rel(n + 1);
   for (int i = 0; i <= n; ++i) rel[i] = off[i] - off[0];
   const float* src = pcm_host + off[0];
-  if (!pinned_in) { std::memcpy(c->pin_pcm, src, total * sizeof(float)); src = c->pin_pcm; }
-  CBX_CUDA_OK(c, cudaMemcpyAsync(c->own_pcm, src, total * sizeof(float), cudaMemcpyHostToDevice, st));
-  float* ve_dev = c->own_out;
-  float* xv_dev = c->own_out + (int64_t)n * kVeEmbed;
-  int32_t* st_dev = (int32_t*)(c->own_out + (int64_t)n * (kVeEmbed + kXvEmbed));
-  rc = cbx_embed(c, c->own_pcm, rel.data(), n, trim_top_db, step, min_cov, ve_dev, xv_dev, st_dev, c->own_ws, c->own_ws_bytes, st, flags);
+  if (!pinned_in) { std::memcpy(s.pin_pcm, src, total * sizeof(float)); src = s.pin_pcm; }
+  // H2D on its own stream (the slot's previous kernels have been waited for in cbx_embed_host_wait, so dev_pcm is free)
+  CBX_CUDA_OK(c, cudaMemcpyAsync(s.dev_pcm, src, total * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
+  CBX_CUDA_OK(c, cudaEventRecord(s.h2d, c->h2d_stream));
+  CBX_CUDA_OK(c, cudaStreamWaitEvent(c->own_stream, s.h2d, 0));
+  float* ve_dev = s.dev_out;
+  float* xv_dev = s.dev_out + (int64_t)n * kVeEmbed;
+  int32_t* st_dev = (int32_t*)(s.dev_out + (int64_t)n * (kVeEmbed + kXvEmbed));
+  rc = cbx_embed(c, s.dev_pcm, rel.data(), n, trim_top_db, step, min_cov, ve_dev, xv_dev, st_dev, c->own_ws, c->own_ws_bytes, c->own_stream, flags);
   if (rc) return rc;
-  CBX_CUDA_OK(c, cudaMemcpyAsync(c->pin_out, c->own_out, out_floats * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CBX_CUDA_OK(c, cudaStreamSynchronize(st));
-  if ((flags & CBX_DO_VE) && ve_out_host) std::memcpy(ve_out_host, c->pin_out, (size_t)n * kVeEmbed * sizeof(float));
-  if ((flags & CBX_DO_XV) && xv_out_host) std::memcpy(xv_out_host, c->pin_out + (int64_t)n * kVeEmbed, (size_t)n * kXvEmbed * sizeof(float));
-  if (status_host) std::memcpy(status_host, c->pin_out + (int64_t)n * (kVeEmbed + kXvEmbed), (size_t)n * sizeof(int32_t));
+  CBX_CUDA_OK(c, cudaEventRecord(s.comp, c->own_stream));
+  CBX_CUDA_OK(c, cudaStreamWaitEvent(c->d2h_stream, s.comp, 0));
+  CBX_CUDA_OK(c, cudaMemcpyAsync(s.pin_out, s.dev_out, out_bytes, cudaMemcpyDeviceToHost, c->d2h_stream));
+  CBX_CUDA_OK(c, cudaEventRecord(s.d2h, c->d2h_stream));
+  s.n = n; s.flags = flags; s.busy = true;
   return CBX_OK;
+}
+
+int cbx_embed_host_wait(cbx_ctx* c, int slot_id, float* ve_out_host, float* xv_out_host, int32_t* status_host) {
+  if (!c) return CBX_ERR_ARG;
+  if (slot_id < 0 || slot_id > 1) { c->err = "slot must be 0 or 1"; return CBX_ERR_ARG; }
+  cbx_ctx::HostSlot& s = c->slot[slot_id];
+  if (!s.busy) { c->err = "nothing was submitted to this slot"; return CBX_ERR_STATE; }
+  cudaSetDevice(c->device);
+  CBX_CUDA_OK(c, cudaEventSynchronize(s.d2h));
+  s.busy = false;
+  const int n = s.n;
+  if ((s.flags & CBX_DO_VE) && ve_out_host) std::memcpy(ve_out_host, s.pin_out, (size_t)n * kVeEmbed * sizeof(float));
+  if ((s.flags & CBX_DO_XV) && xv_out_host) std::memcpy(xv_out_host, s.pin_out + (int64_t)n * kVeEmbed, (size_t)n * kXvEmbed * sizeof(float));
+  if (status_host) std::memcpy(status_host, s.pin_out + (int64_t)n * (kVeEmbed + kXvEmbed), (size_t)n * sizeof(int32_t));
+  return CBX_OK;
+}
+
+int cbx_embed_host(cbx_ctx* c, const float* pcm_host, const int64_t* off, int n, float trim_top_db, int step, double min_cov,
+                   float* ve_out_host, float* xv_out_host, int32_t* status_host, int flags) {
+  if (c && (c->slot[0].busy || c->slot[1].busy)) { c->err = "a submitted batch is pending: claim it with cbx_embed_host_wait first"; return CBX_ERR_STATE; }
+  int rc = cbx_embed_host_submit(c, 0, pcm_host, off, n, trim_top_db, step, min_cov, flags);
+  if (rc) return rc;
+  return cbx_embed_host_wait(c, 0, ve_out_host, xv_out_host, status_host);
 }
 
 int64_t cbx_ve_forward_workspace_bytes(cbx_ctx* c, int n) {

@@ -144,13 +144,19 @@ struct cbx_ctx {
   int64_t lstm_trace = 0;             // device pointer of the clock trace buffer
   int64_t lstm_impl = 2;              // 1: DSMEM-push recurrence, 2: L2 multicast-TMA recurrence
   int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)
-  // buffers owned by the library (cbx_embed_host)
+  // buffers owned by the library (cbx_embed_host / cbx_embed_host_submit): two slots so that the host<->device copies of
+  // one batch overlap the kernels of the other; the workspace is shared (kernels of both slots run on one compute stream)
   void* own_ws = nullptr; int64_t own_ws_bytes = 0;
-  float* own_pcm = nullptr; int64_t own_pcm_floats = 0;
-  float* own_out = nullptr; int64_t own_out_floats = 0;
-  float* pin_pcm = nullptr; int64_t pin_pcm_floats = 0;
-  float* pin_out = nullptr; int64_t pin_out_floats = 0;
-  cudaStream_t own_stream = nullptr;
+  struct HostSlot {
+    float* dev_pcm = nullptr; int64_t dev_pcm_bytes = 0;
+    float* dev_out = nullptr; int64_t dev_out_bytes = 0;
+    float* pin_pcm = nullptr; int64_t pin_pcm_bytes = 0;
+    float* pin_out = nullptr; int64_t pin_out_bytes = 0;
+    cudaEvent_t h2d = nullptr, comp = nullptr, d2h = nullptr;
+    int n = 0, flags = 0; bool busy = false;
+  } slot[2];
+  cudaStream_t own_stream = nullptr;     // compute
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   // last-run bookkeeping for the stage taps
   std::vector<cbx::ClipPlan> last_plan;
   std::map<std::string, std::vector<int64_t>> taps;   // name -> {byte_offset, rows, cols, ld}

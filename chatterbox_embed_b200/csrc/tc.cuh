@@ -320,7 +320,7 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;     // n fastest: the CTAs that share an X row tile run together (L2 reuse)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmB);
@@ -667,7 +667,7 @@ inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const fl
   constexpr int SMEM = smem_bytes(BN, STAGES);
   static bool configured = false;
   if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
-  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
   kern<<<grid, 320, SMEM, st>>>(X, lda, M, bn_a, bn_b, tmB, (K + BK - 1) / BK, epi);
 }

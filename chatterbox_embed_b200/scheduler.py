@@ -59,6 +59,21 @@ class SpeakerEmbedder:
         flags = _lib.DO_VE | _lib.DO_XV | (0 if trim_top_db else _lib.NO_TRIM)
         return self.ctx().embed_host(flat, offsets, float(trim_top_db or 0.0), step, min_coverage, flags)
 
+    def embed_stream(self, batches, trim_top_db: Optional[float] = 20.0, step: int = 77, min_coverage: float = 0.8, pinned: bool = False):
+        """Voice-bank extraction over many batches: ``batches`` yields (flat_pcm, offsets); yields (ve, xv, status) per
+        batch, in order.  Two batches are in flight (cbx_embed_host_submit / _wait), so the host<->device copies of one
+        overlap the kernels of the other."""
+        ctx = self.ctx()
+        flags = _lib.DO_VE | _lib.DO_XV | (0 if trim_top_db else _lib.NO_TRIM) | (_lib.PCM_PINNED if pinned else 0)
+        pending = []
+        for k, (flat, offsets) in enumerate(batches):
+            ctx.embed_host_submit(k & 1, flat, offsets, float(trim_top_db or 0.0), step, min_coverage, flags)
+            pending.append(k & 1)
+            if len(pending) == 2:
+                yield ctx.embed_host_wait(pending.pop(0))
+        while pending:
+            yield ctx.embed_host_wait(pending.pop(0))
+
     def embed_wavs(self, wavs: Sequence[np.ndarray], **kw):
         flat, off = _host.flatten_host(wavs)
         ve, xv, status = self.embed_host(flat, off, **kw)

@@ -111,6 +111,15 @@ int cbx_embed_host(cbx_ctx* ctx, const float* pcm_host, const int64_t* offsets_h
                    float trim_top_db, int ve_step, double min_coverage,
                    float* ve_out_host, float* xv_out_host, int32_t* status_host, int flags);
 
+/* Streaming form for voice-bank extraction (many batches): two slots.  submit() enqueues the host->device copy (own
+ * stream), the kernels (one compute stream shared by both slots) and the device->host copy of the results and returns
+ * without waiting; wait() blocks until that slot's results are on the host and copies them out.  With two batches in
+ * flight the copies of one overlap the kernels of the other.  pcm_host must stay valid (and, with CBX_PCM_PINNED,
+ * unmodified) until the slot's wait() returns.  cbx_embed_host == submit(slot 0) + wait(slot 0). */
+int cbx_embed_host_submit(cbx_ctx* ctx, int slot, const float* pcm_host, const int64_t* offsets_host, int n_clips,
+                          float trim_top_db, int ve_step, double min_coverage, int flags);
+int cbx_embed_host_wait(cbx_ctx* ctx, int slot, float* ve_out_host, float* xv_out_host, int32_t* status_host);
+
 /* VoiceEncoder.forward on already-cut partials (voice_encoder.py:139-160):
  * mels_dev [n_partials,160,40] -> out_dev [n_partials,256] (L2-normed). */
 int cbx_ve_forward_partials(cbx_ctx* ctx, const float* mels_dev, int n_partials, float* out_dev,

@@ -282,3 +282,19 @@ def test_mode1_ragged_config3(models, mode1):
         pl = _lib.plan_clip(n)
         assert (pl.ve_partials, pl.ve_target) == nets.num_wins(1 + n // 160)
         assert pl.xv_frames == 1 + (n - 400) // 160 and pl.xv_tdnn == (pl.xv_frames - 1) // 2 + 1
+
+
+def test_stream_api_equals_single_calls(models, mode1):
+    """cbx_embed_host_submit / _wait with two batches in flight returns what the one-shot call returns, in order."""
+    sdv, sdc, emb = _emb(models, "W1")
+    batches = []
+    for b in range(5):
+        wavs = [synth.clip(10 * b + i, n) for i, n in enumerate([16000 + 700 * b, 31000, 24000 + 100 * b])]
+        flat = np.concatenate(wavs); off = np.concatenate([[0], np.cumsum([len(w) for w in wavs])]).astype(np.int64)
+        batches.append((flat, off))
+    single = [emb.embed_host(f, o) for f, o in batches]
+    streamed = list(emb.embed_stream(iter(batches)))
+    assert len(streamed) == len(single)
+    for (ve_a, xv_a, st_a), (ve_b, xv_b, st_b) in zip(single, streamed):
+        assert (st_a == st_b).all()
+        assert np.abs(ve_a - ve_b).max() < 2e-5 and np.abs(xv_a - xv_b).max() < 5e-4 * max(1.0, float(np.abs(xv_a).max()))
