@@ -298,3 +298,21 @@ def test_stream_api_equals_single_calls(models, mode1):
     for (ve_a, xv_a, st_a), (ve_b, xv_b, st_b) in zip(single, streamed):
         assert (st_a == st_b).all()
         assert np.abs(ve_a - ve_b).max() < 2e-5 and np.abs(xv_a - xv_b).max() < 5e-4 * max(1.0, float(np.abs(xv_a).max()))
+
+
+def test_mode1_chunking_is_invisible_up_to_rounding(models, mode1):
+    """Tensor-core mode with tiny chunks (several CAMPPlus chunks, FCM sub-chunks and LSTM chunks per call): same result as
+    one chunk up to the rounding-order noise of that mode."""
+    sdv, sdc, emb = _emb(models, "W1")
+    wavs = [synth.clip(i, n) for i, n in enumerate([30000, 52000, 16000, 41000, 20000, 64000, 35000])]
+    ctx = emb.ctx()
+    ve_a, xv_a = emb.embed_wavs(wavs)
+    old = {k: ctx.get_option(k) for k in ("xv_chunk_rows", "fcm_chunk_rows", "lstm_chunk_partials")}
+    try:
+        ctx.set_option("xv_chunk_rows", 700); ctx.set_option("fcm_chunk_rows", 300); ctx.set_option("lstm_chunk_partials", 5)
+        ve_b, xv_b = emb.embed_wavs(wavs)
+    finally:
+        for k, v in old.items():
+            ctx.set_option(k, v)
+    scale = max(1.0, float(np.abs(xv_a).max()))
+    assert np.abs(ve_a - ve_b).max() < 2e-5 and np.abs(xv_a - xv_b).max() < 5e-4 * scale
