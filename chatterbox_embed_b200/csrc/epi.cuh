@@ -38,14 +38,14 @@ struct EpiBiasReluMask {         // out = row is a real frame ? relu(acc + bias)
 // holds are summed with a transposed butterfly (31 shuffles per 32 columns) and one 128-byte red.add per segment present.
 // Warp-collective: every lane of the warp must call it (rows >= M take part as "no segment").
 struct EpiBiasReluMaskSegsum {
-  float* out; int ld; const float* bias; const int32_t* row_seg; float* seg_sum; int M;
+  float* out; int ld; const float* bias; const int32_t* row_seg; float* seg_sum; int M;     // out == nullptr: the kernel stores (TMA)
   __device__ void operator()(int m, int n0, float* v) const {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int seg = m < M ? row_seg[m] : -1;
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = seg >= 0 ? fmaxf(v[i] + __ldg(bias + n0 + i), 0.f) : 0.f;
-    if (m < M) store32(out + (size_t)m * ld + n0, v);
+    if (out && m < M) store32(out + (size_t)m * ld + n0, v);
     unsigned rem = __ballot_sync(full, seg >= 0);
     while (rem) {
       const int s = __shfl_sync(full, seg, __ffs(rem) - 1);
@@ -83,13 +83,12 @@ struct EpiBiasReluMaskSegsum {
 };
 
 struct EpiMask {                 // out = row is a real frame ? acc : 0                (transit layers)
-  float* out; int ld; const int32_t* row_clip; int M;
+  float* out; int ld; const int32_t* row_clip; int M;           // out == nullptr: the kernel stores (TMA)
   __device__ void operator()(int m, int n0, float* v) const {
-    if (m >= M) return;
-    const bool live = row_clip[m] >= 0;
+    const bool live = m < M && row_clip[m] >= 0;
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = live ? v[i] : 0.f;
-    store32(out + (size_t)m * ld + n0, v);
+    if (out && m < M) store32(out + (size_t)m * ld + n0, v);
   }
 };
 

@@ -306,7 +306,7 @@ constexpr int PG = 2;     // producer groups
 template <int BN, int STAGES, class Epi>
 __global__ void __launch_bounds__(320, 2)
 tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __restrict__ bn_a, const float* __restrict__ bn_b,
-                    const __grid_constant__ CUtensorMap tmB, int nkb, Epi epi) {
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, int nkb, Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
@@ -412,12 +412,29 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
       tc_fence_after();
       const int q = warp & 3;
       const int row = m0 + q * 32 + lane;
+      // the C tile leaves through the (now idle) A stages and TMA tensor stores: one 128 x 32 box per accumulator chunk
+      const int i = q * 32 + lane;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-        epi(row, n0 + c, v);
+        epi(row, n0 + c, v);                               // transforms v in place (epi.out == nullptr: no store)
+        const int buf = (c >> 5) % STAGES;
+        if (c >= 32 * STAGES) {                            // buffer reuse: the store that last used it must have read it
+          if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        float4* so = reinterpret_cast<float4*>(sA + buf * A_BYTES) + i * 8;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) so[jj ^ (i & 7)] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+        fence_proxy_async();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+          tma_store_2d(&tmC, sA + buf * A_BYTES, n0 + c, m0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
+      if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       tc_fence_before();
     }
   }
@@ -661,7 +678,7 @@ inline void pgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const fl
 
 template <int BN, int STAGES, class Epi>
 inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const float* X, int lda, const float* bn_a, const float* bn_b,
-                         const CUtensorMap& tmB, int M, int N, int K, Epi epi) {
+                         const CUtensorMap& tmB, float* C, int ldc, int M, int N, int K, Epi epi) {
   if (M <= 0 || N <= 0) return;
   auto kern = tgemm_bnrelu_kernel<BN, STAGES, Epi>;
   constexpr int SMEM = smem_bytes(BN, STAGES);
@@ -669,7 +686,8 @@ inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const fl
   if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
-  kern<<<grid, 320, SMEM, st>>>(X, lda, M, bn_a, bn_b, tmB, (K + BK - 1) / BK, epi);
+  CUtensorMap tmC = make_map_2d(C, M, N, ldc, BM, false);
+  kern<<<grid, 320, SMEM, st>>>(X, lda, M, bn_a, bn_b, tmB, tmC, (K + BK - 1) / BK, epi);
 }
 
 }  // namespace tc

@@ -461,8 +461,8 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     for (int i = 0; i < kLayers[b]; ++i, ++li) {
       const DenseLayerW& D = W.dense[li];
       if (tcm)
-        tc::tgemm_bnrelu<128, 3>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], M, kBnC, D.cin,
-                                 tc::EpiBiasReluMaskSegsum{ch.u, kBnC, D.t2, ch.td_row_seg, ch.seg_sum, M});
+        tc::tgemm_bnrelu<128, 3>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
+                                 tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, ch.seg_sum, M});
       else
         sgemm(L, st, "dense_bottleneck_gemm", M, kBnC, D.cin, BnReluA{cat, ld, D.a1, D.b1}, D.w1, D.cin, BiasReluMaskEpi{ch.u, kBnC, D.t2, ch.td_row_clip});
       if (ch.segs > 0 && tcm) {
@@ -481,8 +481,8 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     float* out = b == 0 ? ch.cat2 : (b == 1 ? ch.cat3 : ch.tr3);
     const int ldo = b == 2 ? kStatsC : 1024;
     if (tcm)
-      tc::tgemm_bnrelu<128, 3>(L, st, "transit_gemm", cat, ld, T.a, T.b, W.tm_tr[b], M, T.cout, T.cin,
-                               tc::EpiMask{out, ldo, ch.td_row_clip, M});
+      tc::tgemm_bnrelu<128, 3>(L, st, "transit_gemm", cat, ld, T.a, T.b, W.tm_tr[b], out, ldo, M, T.cout, T.cin,
+                               tc::EpiMask{nullptr, ldo, ch.td_row_clip, M});
     else
       sgemm(L, st, "transit_gemm", M, T.cout, T.cin, BnReluA{cat, ld, T.a, T.b}, T.w, T.cin, MaskEpi{out, ldo, ch.td_row_clip});
   }
