@@ -206,6 +206,9 @@ int cbx_create(int device, cbx_ctx** out) {
   int rc = build_frontend_tables(c);
   if (rc) { g_create_err = c->err; delete c; return rc; }
   cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking);
   for (auto& s : c->slot) {
@@ -232,6 +235,9 @@ void cbx_destroy(cbx_ctx* c) {
     if (s.d2h) cudaEventDestroy(s.d2h);
   }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   delete c;
@@ -246,6 +252,7 @@ int cbx_set_option(cbx_ctx* c, const char* key, int64_t v) {
   else if (k == "fcm_chunk_rows" && v >= 64) c->fcm_chunk_rows = v;
   else if (k == "lstm_chunk_partials" && v >= 1) c->lstm_chunk_slots = v;
   else if (k == "mode" && (v == 0 || v == 1)) c->mode = v;
+  else if (k == "overlap" && (v == 0 || v == 1)) c->overlap = v;
   else if (k == "lstm_dbg") c->lstm_dbg = v;
   else if (k == "lstm_impl" && (v == 1 || v == 2)) c->lstm_impl = v;
   else if (k == "lstm_trace") c->lstm_trace = v;
@@ -260,6 +267,7 @@ int64_t cbx_get_option(const cbx_ctx* c, const char* key) {
   if (k == "fcm_chunk_rows") return c->fcm_chunk_rows;
   if (k == "lstm_chunk_partials") return c->lstm_chunk_slots;
   if (k == "mode") return c->mode;
+  if (k == "overlap") return c->overlap;
   return -1;
 }
 
@@ -301,6 +309,15 @@ int cbx_embed(cbx_ctx* c, const float* pcm, const int64_t* off, int n, float tri
   for (auto& r : cs.ve) { Carver cv(nullptr, 0); carve_ve(cv, plan_ve(b, r.first, r.second), nullptr); ve_region = std::max(ve_region, cv.off); }
   ve_region = (ve_region + 255) & ~int64_t(255);
 
+  // The two encoders are independent and use disjoint workspace regions: with both requested (and `overlap` on) CAMPPlus runs
+  // on a second stream, forked from and joined back into the caller's stream, so that its kernels fill the SMs the
+  // latency-bound LSTM recurrence (14 clusters = 112 of 148 SMs) leaves idle.  Stream order as seen by the caller is kept.
+  cudaStream_t sx = st;
+  if (c->overlap && !cs.ve.empty() && !cs.xv.empty()) {
+    sx = c->aux_stream;
+    CBX_CUDA_OK(c, cudaEventRecord(c->ev_fork, st));
+    CBX_CUDA_OK(c, cudaStreamWaitEvent(sx, c->ev_fork, 0));
+  }
   const bool no_trim = (flags & CBX_NO_TRIM) != 0 || !(trim_top_db > 0.f);
   for (auto& r : cs.ve) {
     VeLayout L = plan_ve(b, r.first, r.second);
@@ -321,12 +338,16 @@ int cbx_embed(cbx_ctx* c, const float* pcm, const int64_t* off, int n, float tri
     Carver cv_abs(ws, ws_bytes); cv_abs.off = ve_region;
     XvChunk ch = carve_xv(cv_abs, L, c);
     ch.hplan = L.plan.data();
-    CBX_CUDA_OK(c, cudaMemcpyAsync(ch.plan, L.plan.data(), sizeof(ClipPlan) * L.plan.size(), cudaMemcpyHostToDevice, st));
-    run_xv_chunk(c, pcm, ch, xv_out, status, st);
+    CBX_CUDA_OK(c, cudaMemcpyAsync(ch.plan, L.plan.data(), sizeof(ClipPlan) * L.plan.size(), cudaMemcpyHostToDevice, sx));
+    run_xv_chunk(c, pcm, ch, xv_out, status, sx);
     for (size_t i = 0; i < L.plan.size(); ++i) {
       ClipPlan& lp = c->last_plan[r.first + i];
       lp.fb_row = L.plan[i].fb_row; lp.td_row = L.plan[i].td_row; lp.xv_frames = L.plan[i].xv_frames; lp.xv_tdnn = L.plan[i].xv_tdnn;
     }
+  }
+  if (sx != st) {     // join: everything after this call on the caller's stream also follows the CAMPPlus work
+    CBX_CUDA_OK(c, cudaEventRecord(c->ev_join, sx));
+    CBX_CUDA_OK(c, cudaStreamWaitEvent(st, c->ev_join, 0));
   }
   CBX_CUDA_OK(c, cudaGetLastError());
   return CBX_OK;

@@ -157,6 +157,9 @@ struct cbx_ctx {
   } slot[2];
   cudaStream_t own_stream = nullptr;     // compute
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;     // CAMPPlus chain when it runs beside the VoiceEncoder chain
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int64_t overlap = 1;
   // last-run bookkeeping for the stage taps
   std::vector<cbx::ClipPlan> last_plan;
   std::map<std::string, std::vector<int64_t>> taps;   // name -> {byte_offset, rows, cols, ld}
