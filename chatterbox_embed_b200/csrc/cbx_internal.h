@@ -140,7 +140,7 @@ struct cbx_ctx {
   int64_t xv_chunk_rows = 300000;     // fbank rows per CAMPPlus chunk
   int64_t fcm_chunk_rows = 65536;     // fbank rows per FCM sub-chunk
   int64_t lstm_chunk_slots = 3072;    // partial slots per VoiceEncoder chunk
-  int64_t mode = 0;
+  int64_t mode = 1;                   // 1: tcgen05 (TF32) kernels, the product path; 0: strict-fp32 SIMT yardstick
   int64_t lstm_trace = 0;             // device pointer of the clock trace buffer
   int64_t lstm_impl = 2;              // 1: DSMEM-push recurrence, 2: L2 multicast-TMA recurrence
   int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)

@@ -79,8 +79,8 @@ void cbx_destroy(cbx_ctx* ctx);
 const char* cbx_last_error(const cbx_ctx* ctx);   /* ctx may be NULL: last error of cbx_create */
 const char* cbx_version(void);
 
-/* Tuning: key in {"xv_chunk_rows","fcm_chunk_rows","lstm_chunk_partials","mode","overlap"}.  mode: 0 = strict fp32
- * SIMT kernels everywhere, 1 = tensor-core (tcgen05) kernels where available.  overlap: 1 = with both encoders
+/* Tuning: key in {"xv_chunk_rows","fcm_chunk_rows","lstm_chunk_partials","mode","overlap"}.  mode: 1 (default) = tensor-core
+ * (tcgen05, TF32 / 3xTF32) kernels, 0 = strict fp32 SIMT kernels everywhere (the on-device fp32 yardstick).  overlap: 1 = with both encoders
  * requested, CAMPPlus runs on an internal second stream beside the VoiceEncoder chain (forked from / joined into the
  * caller's stream). */
 int cbx_set_option(cbx_ctx* ctx, const char* key, int64_t value);

@@ -26,6 +26,16 @@ def relerr(a, b):
     return float(np.abs(np.asarray(a, np.float64) - b).max() / (np.abs(b).max() + 1e-30))
 
 
+@pytest.fixture(autouse=True)
+def strict_mode_by_default():
+    """The library's default is the tensor-core mode; the tests of this file hold the strict-fp32 mode (mode 0) to fp32
+    tolerances unless they ask for the `mode1` fixture (which runs after this one)."""
+    ctx = _lib.context(0)
+    ctx.set_option("mode", 0)
+    yield
+    ctx.set_option("mode", 1)
+
+
 @pytest.fixture(scope="module")
 def models():
     out = {}
@@ -204,7 +214,6 @@ def mode1(models):
     ctx = _lib.context(0)
     ctx.set_option("mode", 1)
     yield ctx
-    ctx.set_option("mode", 0)
 
 
 @pytest.mark.parametrize("kind", ["W0", "W1"])
