@@ -47,6 +47,8 @@ _SIGS = {
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "cbx_embed_host_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, _P(C.c_int64), C.c_int, C.c_float, C.c_int, C.c_double, C.c_int]),
     "cbx_embed_host_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cbx_resample_out_len": (C.c_int64, [C.c_int, C.c_int, C.c_int64]),
+    "cbx_resample": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_void_p, _P(C.c_int64), C.c_void_p]),
     "cbx_ve_forward_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "cbx_ve_forward_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int]),
     "cbx_locate": (C.c_int, [C.c_void_p, C.c_char_p, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64), _P(C.c_int64)]),
@@ -95,6 +97,10 @@ def plan_clip(n_samples: int, step: int = 77, min_coverage: float = 0.8) -> Clip
     if lib().cbx_plan_clip(int(n_samples), int(step), float(min_coverage), C.byref(p)):
         raise CbxError("cbx_plan_clip: bad argument")
     return p
+
+
+def resample_out_len(src_sr: int, dst_sr: int, n_samples: int) -> int:
+    return int(lib().cbx_resample_out_len(int(src_sr), int(dst_sr), int(n_samples)))
 
 
 def clip_cost(n_samples: int) -> float:
@@ -186,6 +192,12 @@ class Context:
         self._check(lib().cbx_embed_host_wait(self._h, int(slot), ve.ctypes.data if ve is not None else None,
                                               xv.ctypes.data if xv is not None else None, status.ctypes.data), "cbx_embed_host_wait")
         return ve, xv, status
+
+    def resample(self, x_ptr: int, in_offsets: Sequence[int], src_sr: int, dst_sr: int, y_ptr: int, out_offsets: Sequence[int], stream: int):
+        n = len(in_offsets) - 1
+        a = (C.c_int64 * (n + 1))(*[int(v) for v in in_offsets])
+        b = (C.c_int64 * (n + 1))(*[int(v) for v in out_offsets])
+        self._check(lib().cbx_resample(self._h, x_ptr, a, n, int(src_sr), int(dst_sr), y_ptr, b, stream), "cbx_resample")
 
     def ve_forward_workspace_bytes(self, n: int) -> int:
         return self._check(lib().cbx_ve_forward_workspace_bytes(self._h, n), "cbx_ve_forward_workspace_bytes")

@@ -226,6 +226,8 @@ void cbx_destroy(cbx_ctx* c) {
   cudaFree(c->ve.blob); cudaFree(c->xv.blob); cudaFree(c->ft.blob);
   cudaDeviceSynchronize();
   cudaFree(c->own_ws);
+  for (auto& kv : c->resample_banks) cudaFree(kv.second);
+  cudaFree(c->resample_clips);
   for (auto& s : c->slot) {
     cudaFree(s.dev_pcm); cudaFree(s.dev_out);
     if (s.pin_pcm) cudaFreeHost(s.pin_pcm);

@@ -160,6 +160,9 @@ struct cbx_ctx {
   cudaStream_t aux_stream = nullptr;     // CAMPPlus chain when it runs beside the VoiceEncoder chain
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int64_t overlap = 1;
+  // resampler (resample.cu): filter banks per (orig, new) and the clip table
+  std::map<long long, float*> resample_banks;
+  void* resample_clips = nullptr; int resample_clips_cap = 0;
   // last-run bookkeeping for the stage taps
   std::vector<cbx::ClipPlan> last_plan;
   std::map<std::string, std::vector<int64_t>> taps;   // name -> {byte_offset, rows, cols, ld}

@@ -1,0 +1,107 @@
+// torchaudio.transforms.Resample(src_sr, dst_sr) with its defaults (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99),
+// the resampler behind get_resampler() of the reference (s3gen/s3gen.py:41-44, used at :116 and :175-183).
+//   orig = src / gcd, new = dst / gcd, width = ceil(6 * orig / (min(orig, new) * 0.99))
+//   y[i * new + j] = sum_k kernel[j][k] * xpad[i * orig + k],  xpad = x zero padded by (width, width + orig),  k < 2 width + orig
+//   length = ceil(new * L / orig)        (torchaudio functional.py: _get_sinc_resample_kernel / _apply_sinc_resample_kernel)
+// The filter bank is built in float64 on the host exactly as torchaudio does and rounded to fp32; the kernel is a plain
+// HBM-bound polyphase FIR: one thread per output sample, clips back to back with per-clip offsets (ragged batches).
+#include <cmath>
+#include <numeric>
+
+#include "cbx_internal.h"
+
+namespace cbx {
+
+struct ResampleClip { long long in_off, out_off; int in_len, out_len; };
+
+__global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__ x, const ResampleClip* __restrict__ clips, const float* __restrict__ bank,
+                                                       int orig, int nnew, int width, int taps, float* __restrict__ y) {
+  const ResampleClip c = clips[blockIdx.y];
+  const float* xin = x + c.in_off;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < c.out_len; n += gridDim.x * blockDim.x) {
+    const int i = n / nnew, j = n - i * nnew;
+    const float* kj = bank + (size_t)j * taps;
+    const int base = i * orig - width;
+    const int k0 = max(0, -base), k1 = min(taps, c.in_len - base);
+    float acc = 0.f;
+    for (int k = k0; k < k1; ++k) acc = fmaf(__ldg(kj + k), __ldg(xin + base + k), acc);
+    y[c.out_off + n] = acc;
+  }
+}
+
+static int64_t resample_len(int64_t n, int orig, int nnew) { return (n * nnew + orig - 1) / orig; }
+
+}  // namespace cbx
+
+using namespace cbx;
+
+extern "C" {
+
+int64_t cbx_resample_out_len(int src_sr, int dst_sr, int64_t n_samples) {
+  if (src_sr <= 0 || dst_sr <= 0 || n_samples < 0) return CBX_ERR_ARG;
+  const int g = std::gcd(src_sr, dst_sr);
+  return resample_len(n_samples, src_sr / g, dst_sr / g);
+}
+
+int cbx_resample(cbx_ctx* c, const float* x_dev, const int64_t* in_offsets_host, int n_clips, int src_sr, int dst_sr,
+                 float* y_dev, const int64_t* out_offsets_host, void* stream) {
+  if (!c) return CBX_ERR_ARG;
+  if (!x_dev || !y_dev || !in_offsets_host || !out_offsets_host || n_clips <= 0 || src_sr <= 0 || dst_sr <= 0) { c->err = "bad argument"; return CBX_ERR_ARG; }
+  cudaSetDevice(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = std::gcd(src_sr, dst_sr);
+  const int orig = src_sr / g, nnew = dst_sr / g;
+  const double lpw = 6.0, rolloff = 0.99;
+  const double base_freq = std::min(orig, nnew) * rolloff;
+  const int width = (int)std::ceil(lpw * orig / base_freq);
+  const int taps = 2 * width + orig;
+  // filter bank, cached per (orig, new)
+  const long long key = ((long long)orig << 32) | (unsigned)nnew;
+  auto it = c->resample_banks.find(key);
+  if (it == c->resample_banks.end()) {
+    std::vector<float> bank((size_t)nnew * taps);
+    const double PI = 3.14159265358979323846;
+    for (int j = 0; j < nnew; ++j)
+      for (int k = 0; k < taps; ++k) {
+        // torchaudio divides an int64 arange by new_freq in float32 (default dtype) before adding the float64 index grid
+        double t = ((double)((float)(-j) / (float)nnew) + (double)(k - width) / orig) * base_freq;
+        t = std::fmin(std::fmax(t, -lpw), lpw);
+        const double w = std::cos(t * PI / lpw / 2.0);
+        const double window = w * w;
+        t *= PI;
+        const double sinc = t == 0.0 ? 1.0 : std::sin(t) / t;
+        bank[(size_t)j * taps + k] = (float)(sinc * window * (base_freq / orig));
+      }
+    float* d = nullptr;
+    CBX_CUDA_OK(c, cudaMalloc((void**)&d, bank.size() * sizeof(float)));
+    CBX_CUDA_OK(c, cudaMemcpy(d, bank.data(), bank.size() * sizeof(float), cudaMemcpyHostToDevice));
+    it = c->resample_banks.emplace(key, d).first;
+  }
+  std::vector<ResampleClip> clips(n_clips);
+  int max_out = 0;
+  for (int i = 0; i < n_clips; ++i) {
+    const int64_t len = in_offsets_host[i + 1] - in_offsets_host[i];
+    if (len < 0 || len > ((int64_t)1 << 30)) { c->err = "offsets must be non-decreasing"; return CBX_ERR_ARG; }
+    const int64_t out_len = resample_len(len, orig, nnew);
+    if (out_offsets_host[i + 1] - out_offsets_host[i] != out_len) { c->err = "out_offsets do not match cbx_resample_out_len"; return CBX_ERR_ARG; }
+    clips[i] = ResampleClip{(long long)in_offsets_host[i], (long long)out_offsets_host[i], (int)len, (int)out_len};
+    max_out = std::max<int>(max_out, (int)out_len);
+  }
+  if (max_out == 0) return CBX_OK;
+  // clip table: grown on demand, owned by the context
+  if (c->resample_clips_cap < n_clips) {
+    if (c->resample_clips) cudaFree(c->resample_clips);
+    c->resample_clips_cap = n_clips + n_clips / 2 + 16;
+    CBX_CUDA_OK(c, cudaMalloc(&c->resample_clips, sizeof(ResampleClip) * c->resample_clips_cap));
+  }
+  CBX_CUDA_OK(c, cudaMemcpyAsync(c->resample_clips, clips.data(), sizeof(ResampleClip) * n_clips, cudaMemcpyHostToDevice, st));
+  dim3 grid(std::min((max_out + 255) / 256, 4096), n_clips);
+  {
+    Scope sc(c->launches, st, "resample_kernel");
+    resample_kernel<<<grid, 256, 0, st>>>(x_dev, (const ResampleClip*)c->resample_clips, it->second, orig, nnew, width, taps, y_dev);
+  }
+  CBX_CUDA_OK(c, cudaGetLastError());
+  return CBX_OK;
+}
+
+}  // extern "C"

@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 from .campplus import CAMPPlus
+from .resample import get_resampler
 
 S3_SR = 16000
 
@@ -29,10 +30,9 @@ class SpeakerConditioner:
             ref_wav = torch.from_numpy(ref_wav).float()
         if len(ref_wav.shape) == 1:
             ref_wav = ref_wav.unsqueeze(0)
-        if ref_sr != S3_SR:
-            raise NotImplementedError("resampling to 16 kHz (s3gen.py:116, torchaudio Resample) is a 'next' row of the "
-                                      "scope table; pass 16 kHz audio")
-        embedding = self.speaker_encoder.inference(ref_wav.to(self.device))
+        ref_wav = ref_wav.to(self.device)
+        ref_wav_16 = get_resampler(ref_sr, S3_SR, self.device)(ref_wav)        # s3gen.py:116 (identity at 16 kHz)
+        embedding = self.speaker_encoder.inference(ref_wav_16)
         np.save(save_path, embedding.detach().cpu().numpy())
 
     @torch.inference_mode()

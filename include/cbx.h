@@ -122,6 +122,15 @@ int cbx_embed_host_submit(cbx_ctx* ctx, int slot, const float* pcm_host, const i
                           float trim_top_db, int ve_step, double min_coverage, int flags);
 int cbx_embed_host_wait(cbx_ctx* ctx, int slot, float* ve_out_host, float* xv_out_host, int32_t* status_host);
 
+/* ---- resampling ("next" row 1) ------------------------------------------------------------------- */
+/* torchaudio.transforms.Resample(src_sr, dst_sr) with its defaults, the resampler behind get_resampler()
+ * (s3gen/s3gen.py:41-44, called at :116 and :175-183).  Ragged batch: clips back to back, offsets in samples (host
+ * arrays of n_clips+1); out_offsets[i+1]-out_offsets[i] must equal cbx_resample_out_len(src, dst, len_i)
+ * = ceil(len_i * dst / src) on the reduced ratio.  Stream ordered. */
+int64_t cbx_resample_out_len(int src_sr, int dst_sr, int64_t n_samples);
+int cbx_resample(cbx_ctx* ctx, const float* x_dev, const int64_t* in_offsets_host, int n_clips, int src_sr, int dst_sr,
+                 float* y_dev, const int64_t* out_offsets_host, void* stream);
+
 /* VoiceEncoder.forward on already-cut partials (voice_encoder.py:139-160):
  * mels_dev [n_partials,160,40] -> out_dev [n_partials,256] (L2-normed). */
 int cbx_ve_forward_partials(cbx_ctx* ctx, const float* mels_dev, int n_partials, float* out_dev,

@@ -207,3 +207,47 @@ def campplus_features(wav, use_torchaudio=True):
     """fbank minus its own column mean (xvector.py:50-51)."""
     f = kaldi_fbank_torchaudio(wav) if use_torchaudio else kaldi_fbank_numpy(wav)
     return (f - f.mean(axis=0, keepdims=True)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------
+# torchaudio.transforms.Resample (get_resampler, s3gen/s3gen.py:41-44): restatement + the library itself
+# ----------------------------------------------------------------------------
+def resample_bank(src_sr, dst_sr, lowpass_filter_width=6, rolloff=0.99):
+    """(bank [new][2*width+orig] float32, width) exactly as torchaudio functional.py:_get_sinc_resample_kernel builds it."""
+    import math
+    g = math.gcd(int(src_sr), int(dst_sr))
+    orig, new = int(src_sr) // g, int(dst_sr) // g
+    base = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base)
+    idx = np.arange(-width, width + orig, dtype=np.float64)[None, :] / orig
+    # torchaudio divides an int64 arange by new_freq: that quotient is float32 (default dtype) before it meets the float64 idx
+    t = ((np.arange(0, -new, -1).astype(np.float32) / np.float32(new)).astype(np.float64)[:, None] + idx) * base
+    t = np.clip(t, -lowpass_filter_width, lowpass_filter_width)
+    window = np.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    kern = np.where(t == 0, 1.0, np.sin(t) / np.where(t == 0, 1.0, t)) * window * (base / orig)
+    return kern.astype(np.float32), width
+
+
+def resample_numpy(wav, src_sr, dst_sr):
+    """sinc_interp_hann polyphase FIR as torchaudio applies it (functional.py:_apply_sinc_resample_kernel), accumulated in
+    float64 (torch's conv1d accumulates in float32)."""
+    import math
+    wav = np.asarray(wav, dtype=np.float32)
+    if src_sr == dst_sr:
+        return wav
+    g = math.gcd(int(src_sr), int(dst_sr))
+    orig, new = int(src_sr) // g, int(dst_sr) // g
+    kern, width = resample_bank(src_sr, dst_sr)
+    L = len(wav)
+    xp = np.concatenate([np.zeros(width, np.float32), wav, np.zeros(width + orig, np.float32)])
+    n_frames = (len(xp) - kern.shape[1]) // orig + 1
+    frames = np.lib.stride_tricks.as_strided(xp, shape=(n_frames, kern.shape[1]), strides=(xp.strides[0] * orig, xp.strides[0]))
+    out = (frames.astype(np.float64) @ kern.T.astype(np.float64)).astype(np.float32).reshape(-1)
+    return out[: int(math.ceil(new * L / orig))]
+
+
+def resample_torchaudio(wav, src_sr, dst_sr):
+    import torch
+    import torchaudio
+    return torchaudio.functional.resample(torch.as_tensor(np.asarray(wav, dtype=np.float32)), int(src_sr), int(dst_sr)).numpy()

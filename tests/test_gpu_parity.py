@@ -325,3 +325,39 @@ def test_mode1_chunking_is_invisible_up_to_rounding(models, mode1):
             ctx.set_option(k, v)
     scale = max(1.0, float(np.abs(xv_a).max()))
     assert np.abs(ve_a - ve_b).max() < 2e-5 and np.abs(xv_a - xv_b).max() < 5e-4 * scale
+
+
+# ---- "next" row 1 of the scope table: the resampler in front of the encoders (get_resampler, s3gen.py:41-44) ---------------
+@pytest.mark.parametrize("src,dst", [(24000, 16000), (44100, 16000), (22050, 16000), (48000, 16000), (16000, 24000), (16000, 16000)])
+def test_resample_matches_torchaudio(src, dst):
+    from chatterbox_embed_b200 import Resample
+    rng = np.random.RandomState(11)
+    lens = [src * 2 + 13, src // 7, 5, 1, 3 * src + 1]
+    wavs = [(0.3 * rng.randn(n)).astype(np.float32) for n in lens]
+    rs = Resample(src, dst)
+    outs = rs.ragged([torch.from_numpy(w).to(DEV) for w in wavs]) if src != dst else [torch.from_numpy(w).to(DEV) for w in wavs]
+    for w, o in zip(wavs, outs):
+        want = frontend.resample_torchaudio(w, src, dst)
+        assert o.shape[0] == want.shape[0] == _lib.resample_out_len(src, dst, len(w))          # lengths: bit-exact
+        # against the float64-accumulated restatement (same filter bank bit for bit) and against torchaudio itself, whose
+        # CPU conv1d accumulates the up to 475 taps in float32 (tests/test_oracle.py)
+        assert np.abs(o.cpu().numpy() - frontend.resample_numpy(w, src, dst)).max() < 3e-6
+        assert np.abs(o.cpu().numpy() - want).max() < 3e-5
+    batch = torch.from_numpy(np.stack([wavs[0], wavs[0][::-1].copy()])).to(DEV)                  # (B, L) call surface
+    got = rs(batch)
+    assert got.shape == (2, _lib.resample_out_len(src, dst, lens[0]))
+    assert np.abs(got[1].cpu().numpy() - frontend.resample_torchaudio(wavs[0][::-1].copy(), src, dst)).max() < 3e-5
+
+
+def test_save_voice_clone_resamples_like_the_reference(models, tmp_path):
+    """S3Token2Mel.save_voice_clone (s3gen.py:107-119) on 24 kHz input: resample -> CAMPPlus -> .npy."""
+    sdv, sdc, ve, cp = models["W1"]
+    rng = np.random.RandomState(3)
+    w24 = (0.1 * rng.randn(3 * 24000)).astype(np.float32)
+    cond = SpeakerConditioner(cp)
+    p = str(tmp_path / "clone24.npy")
+    cond.save_voice_clone(w24, 24000, p)
+    emb = np.load(p)
+    assert emb.shape == (1, 192) and emb.dtype == np.float32
+    want = nets.campplus_embed_wavs(sdc, [frontend.resample_torchaudio(w24, 24000, 16000)])
+    assert np.abs(emb - want).max() < 1e-4 * max(1.0, float(np.abs(want).max()))

@@ -130,3 +130,22 @@ def test_w2_is_sensitive():
     a = nets.ve_embed_wavs(sdv, [synth.clip(0, 32000)])[0]
     b = nets.ve_embed_mels(sdv, [np.zeros((201, 40), np.float32)])[0]
     assert float(a @ b) < 0.99
+
+
+@pytest.mark.parametrize("src,dst", [(24000, 16000), (44100, 16000), (22050, 16000), (48000, 16000), (16000, 24000)])
+def test_resample_restatement_matches_torchaudio(src, dst):
+    """get_resampler (s3gen.py:41-44) = torchaudio.transforms.Resample with defaults: the oracle's restatement against the
+    library installed here (torchaudio is importable in the container and on the GPU box)."""
+    rng = np.random.RandomState(7)
+    wav = (0.3 * rng.randn(src // 3 + 17)).astype(np.float32)
+    a = frontend.resample_numpy(wav, src, dst)
+    b = frontend.resample_torchaudio(wav, src, dst)
+    # the filter banks are identical (checked below); what differs is the accumulation: torch's CPU conv1d sums the up to 475
+    # taps in float32 (noise ~1e-5 on O(1) signals, not even stable between two conv1d call shapes), the restatement in float64
+    assert a.shape == b.shape and np.abs(a - b).max() < 3e-5
+    import math
+    import torch
+    import torchaudio.functional.functional as TF
+    g = math.gcd(src, dst)
+    bank, width = TF._get_sinc_resample_kernel(src, dst, g)
+    assert np.abs(frontend.resample_bank(src, dst)[0] - bank.numpy()[:, 0, :]).max() == 0.0 and frontend.resample_bank(src, dst)[1] == width
