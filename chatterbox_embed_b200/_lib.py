@@ -48,6 +48,8 @@ _SIGS = {
     "cbx_embed_host_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, _P(C.c_int64), C.c_int, C.c_float, C.c_int, C.c_double, C.c_int]),
     "cbx_embed_host_wait": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cbx_resample_out_len": (C.c_int64, [C.c_int, C.c_int, C.c_int64]),
+    "cbx_prompt_mel_frames": (C.c_int64, [C.c_int64]),
+    "cbx_prompt_mel": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_int, C.c_void_p, C.c_void_p]),
     "cbx_resample": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_void_p, _P(C.c_int64), C.c_void_p]),
     "cbx_ve_forward_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "cbx_ve_forward_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int]),
@@ -101,6 +103,10 @@ def plan_clip(n_samples: int, step: int = 77, min_coverage: float = 0.8) -> Clip
 
 def resample_out_len(src_sr: int, dst_sr: int, n_samples: int) -> int:
     return int(lib().cbx_resample_out_len(int(src_sr), int(dst_sr), int(n_samples)))
+
+
+def prompt_mel_frames(n_samples: int) -> int:
+    return int(lib().cbx_prompt_mel_frames(int(n_samples)))
 
 
 def clip_cost(n_samples: int) -> float:
@@ -198,6 +204,11 @@ class Context:
         a = (C.c_int64 * (n + 1))(*[int(v) for v in in_offsets])
         b = (C.c_int64 * (n + 1))(*[int(v) for v in out_offsets])
         self._check(lib().cbx_resample(self._h, x_ptr, a, n, int(src_sr), int(dst_sr), y_ptr, b, stream), "cbx_resample")
+
+    def prompt_mel(self, pcm_ptr: int, offsets: Sequence[int], out_ptr: int, stream: int):
+        n = len(offsets) - 1
+        a = (C.c_int64 * (n + 1))(*[int(v) for v in offsets])
+        self._check(lib().cbx_prompt_mel(self._h, pcm_ptr, a, n, out_ptr, stream), "cbx_prompt_mel")
 
     def ve_forward_workspace_bytes(self, n: int) -> int:
         return self._check(lib().cbx_ve_forward_workspace_bytes(self._h, n), "cbx_ve_forward_workspace_bytes")

@@ -126,6 +126,14 @@ struct FrontendTables {
   const float *ve_bins, *k_bins;        // [200][4], [256][4]
   CUtensorMap tm_ve_hi[2], tm_ve_lo[2], tm_k_hi, tm_k_lo;
 };
+// S3Gen prompt mel (promptmel_tc.cu), built on first use: Hann-folded 1920-point DFT rows of bins 1..639 split hi/lo, bin -> mel table
+struct PromptMelTables {
+  bool ready = false;
+  float* blob = nullptr;
+  const float *hi = nullptr, *lo = nullptr, *bins = nullptr;   // [1280][1920] x2, [640][4]
+  CUtensorMap tm_hi, tm_lo;
+  void* clips = nullptr; int clips_cap = 0;
+};
 
 }  // namespace cbx
 
@@ -163,6 +171,7 @@ struct cbx_ctx {
   // resampler (resample.cu): filter banks per (orig, new) and the clip table
   std::map<long long, float*> resample_banks;
   void* resample_clips = nullptr; int resample_clips_cap = 0;
+  cbx::PromptMelTables pm;
   // last-run bookkeeping for the stage taps
   std::vector<cbx::ClipPlan> last_plan;
   std::map<std::string, std::vector<int64_t>> taps;   // name -> {byte_offset, rows, cols, ld}

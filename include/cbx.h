@@ -131,6 +131,16 @@ int64_t cbx_resample_out_len(int src_sr, int dst_sr, int64_t n_samples);
 int cbx_resample(cbx_ctx* ctx, const float* x_dev, const int64_t* in_offsets_host, int n_clips, int src_sr, int dst_sr,
                  float* y_dev, const int64_t* out_offsets_host, void* stream);
 
+/* ---- S3Gen prompt mel ("next" row 1) ------------------------------------------------------------- */
+/* mel_spectrogram() of s3gen/utils/mel.py:33-81 with its defaults (24 kHz, n_fft = win = 1920, hop 480, 80 Slaney mels
+ * 0..8 kHz, reflect pad 720, sqrt(power + 1e-9), log(clamp(., 1e-5))): the prompt_feat of S3Token2Mel.embed_ref
+ * (s3gen.py:177).  Ragged batch of 24 kHz clips back to back (offsets in samples, host array of n_clips+1); out_dev
+ * is [sum_i frames_i][80] fp32, clip after clip, frames_i = cbx_prompt_mel_frames(len_i) = 1 + (len_i - 480) / 480 --
+ * the (T, 80) layout embed_ref hands on after its transpose(1, 2).  Clips of <= 720 samples are refused like torch's
+ * reflect pad refuses them.  Stream ordered. */
+int64_t cbx_prompt_mel_frames(int64_t n_samples);
+int cbx_prompt_mel(cbx_ctx* ctx, const float* pcm_dev, const int64_t* offsets_host, int n_clips, float* out_dev, void* stream);
+
 /* VoiceEncoder.forward on already-cut partials (voice_encoder.py:139-160):
  * mels_dev [n_partials,160,40] -> out_dev [n_partials,256] (L2-normed). */
 int cbx_ve_forward_partials(cbx_ctx* ctx, const float* mels_dev, int n_partials, float* out_dev,

@@ -129,6 +129,18 @@ def make_librosa_shim():
     return mod
 
 
+def register_librosa_shim():
+    """``import librosa`` and ``from librosa.filters import mel`` (s3gen/utils/mel.py:2) both resolve to the shim."""
+    import sys
+    mod = sys.modules.get("librosa")
+    if mod is None or not str(getattr(mod, "__version__", "")).endswith("oracle-shim"):
+        mod = make_librosa_shim()
+        sys.modules["librosa"] = mod
+    sys.modules.setdefault("librosa.filters", mod.filters)
+    sys.modules.setdefault("librosa.effects", mod.effects)
+    return mod
+
+
 # ----------------------------------------------------------------------------
 # VoiceEncoder mel -- melspec.py:26-51 with hp of config.py:1-18
 # ----------------------------------------------------------------------------
@@ -251,3 +263,46 @@ def resample_torchaudio(wav, src_sr, dst_sr):
     import torch
     import torchaudio
     return torchaudio.functional.resample(torch.as_tensor(np.asarray(wav, dtype=np.float32)), int(src_sr), int(dst_sr)).numpy()
+
+
+# ----------------------------------------------------------------------------
+# S3Gen prompt mel (24 kHz) -- s3gen/utils/mel.py:33-81 with the defaults of :20-29
+# ----------------------------------------------------------------------------
+PM_SR, PM_NFFT, PM_HOP, PM_NMEL, PM_FMAX = 24000, 1920, 480, 80, 8000.0
+PM_PAD = (PM_NFFT - PM_HOP) // 2
+_pm_basis = None
+
+
+def prompt_mel_basis():
+    global _pm_basis
+    if _pm_basis is None:
+        _pm_basis = filters_mel(PM_SR, PM_NFFT, PM_NMEL, 0.0, PM_FMAX)
+    return _pm_basis
+
+
+def prompt_mel_num_frames(n_samples):
+    """mel.py:56-74: reflect pad by 720 each side, then non-centred frames of 1920 every 480."""
+    if n_samples <= PM_PAD:
+        raise ValueError("reflect padding needs more than 720 samples")
+    return 1 + (n_samples + 2 * PM_PAD - PM_NFFT) // PM_HOP
+
+
+def prompt_mel_numpy(wav):
+    """(L,) float32 at 24 kHz -> (T, 80) float32 = mel_spectrogram(wav)[0].T, float64 DFT."""
+    y = np.pad(np.asarray(wav, dtype=np.float32), PM_PAD, mode="reflect")
+    spec = stft(y, PM_NFFT, PM_HOP, PM_NFFT, False)                      # hann_window(1920) is periodic, like ours
+    mag = np.sqrt(spec.real.astype(np.float64) ** 2 + spec.imag.astype(np.float64) ** 2 + 1e-9).astype(np.float32)
+    mel = prompt_mel_basis().astype(np.float32) @ mag
+    return np.ascontiguousarray(np.log(np.maximum(mel, 1e-5)).T.astype(np.float32))
+
+
+def prompt_mel_torch(wav):
+    """The same through torch.stft (fp32), operation for operation what mel.py does."""
+    import torch
+    y = torch.as_tensor(np.asarray(wav, dtype=np.float32))[None]
+    y = torch.nn.functional.pad(y.unsqueeze(1), (PM_PAD, PM_PAD), mode="reflect").squeeze(1)
+    spec = torch.view_as_real(torch.stft(y, PM_NFFT, hop_length=PM_HOP, win_length=PM_NFFT, window=torch.hann_window(PM_NFFT),
+                                         center=False, pad_mode="reflect", normalized=False, onesided=True, return_complex=True))
+    spec = torch.sqrt(spec.pow(2).sum(-1) + 1e-9)
+    mel = torch.matmul(torch.from_numpy(prompt_mel_basis()).float(), spec)
+    return np.ascontiguousarray(torch.log(torch.clamp(mel, min=1e-5))[0].T.numpy())

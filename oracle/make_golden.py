@@ -28,6 +28,28 @@ def golden_wavs():
     return [synth.with_silence(i, n, a, b) if (a or b) else synth.clip(i, n) for i, n, a, b in CLIPS]
 
 
+def prompt_mel_wavs():
+    """24 kHz inputs of the prompt-mel fixture: synthetic voice, white noise (every bin above the clamp), a chirp with
+    near-empty bins (exercises the clamp and the 3xTF32 split), the shortest legal clip and a length that is not a hop multiple."""
+    rng = np.random.RandomState(24)
+    t = np.arange(36000) / 24000.0
+    chirp = (0.5 * np.sin(2 * np.pi * (200.0 * t + 0.5 * 6000.0 * t * t / t[-1]))).astype(np.float32)
+    return [synth.clip(7, 72000), (0.2 * rng.randn(30001)).astype(np.float32), chirp, synth.clip(8, 721), synth.clip(9, 4799)]
+
+
+def main_prompt_mel():
+    """tests/golden/ref_prompt_mel.npz from the verbatim s3gen/utils/mel.py (torch fp32 stft)."""
+    assert refload.available(), "reference tree not found"
+    mel = refload.mel_module()
+    out = {}
+    for i, w in enumerate(prompt_mel_wavs()):
+        out[f"mel_{i}"] = mel.mel_spectrogram(torch.from_numpy(w))[0].T.contiguous().numpy()     # (T, 80), as embed_ref hands it on
+    batch = np.stack([prompt_mel_wavs()[0][:24000], prompt_mel_wavs()[1][:24000]])
+    out["mel_batch"] = mel.mel_spectrogram(batch).numpy()                                        # (2, 80, 50): the numpy / batch branch
+    np.savez_compressed(os.path.join(OUT, "ref_prompt_mel.npz"), **out)
+    print("prompt_mel", {k: v.shape for k, v in out.items()})
+
+
 def main():
     assert refload.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
@@ -73,4 +95,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    if "--prompt-mel" in sys.argv:          # only this fixture (the others stay byte-identical in git)
+        main_prompt_mel()
+    else:
+        main()
+        main_prompt_mel()

@@ -35,11 +35,23 @@ def xvector_module():
 def voice_encoder_module():
     if "ref_ve_pkg.voice_encoder" in sys.modules:
         return sys.modules["ref_ve_pkg.voice_encoder"]
-    sys.modules.setdefault("librosa", frontend.make_librosa_shim())
+    frontend.register_librosa_shim()
     pkg = types.ModuleType("ref_ve_pkg")
     pkg.__path__ = [os.path.join(_MODELS, "voice_encoder")]
     sys.modules["ref_ve_pkg"] = pkg
     return importlib.import_module("ref_ve_pkg.voice_encoder")
+
+
+def mel_module():
+    """s3gen/utils/mel.py verbatim (its ``from librosa.filters import mel`` resolves to the oracle shim)."""
+    if "ref_s3gen_mel" in sys.modules:
+        return sys.modules["ref_s3gen_mel"]
+    frontend.register_librosa_shim()
+    spec = importlib.util.spec_from_file_location("ref_s3gen_mel", os.path.join(_MODELS, "s3gen", "utils", "mel.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ref_s3gen_mel"] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def make_voice_encoder(sd):

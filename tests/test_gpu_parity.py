@@ -361,3 +361,78 @@ def test_save_voice_clone_resamples_like_the_reference(models, tmp_path):
     assert emb.shape == (1, 192) and emb.dtype == np.float32
     want = nets.campplus_embed_wavs(sdc, [frontend.resample_torchaudio(w24, 24000, 16000)])
     assert np.abs(emb - want).max() < 1e-4 * max(1.0, float(np.abs(want).max()))
+
+
+# ---- "next" row 1, second half: the 24 kHz prompt mel of embed_ref (s3gen/utils/mel.py:33-81) -------------------------------
+def _pm_close(got, ref):
+    """Linear-domain bound |d mel| <= 1e-5 + 5e-4 * mel (the reference's own fp32 FFT is 2.6e-6 from exact near the 1e-5 clamp,
+    i.e. ~1e-2 in the log domain there; see tests/test_oracle.py)."""
+    g, r = np.exp(np.asarray(got, np.float64)), np.exp(np.asarray(ref, np.float64))
+    return got.shape == ref.shape and bool(np.all(np.abs(g - r) <= 1e-5 + 5e-4 * r))
+
+
+def test_prompt_mel_golden_and_oracle(golden_dir):
+    from chatterbox_embed_b200 import mel as pmel
+    g = np.load(os.path.join(golden_dir, "ref_prompt_mel.npz"))
+    wavs = make_golden.prompt_mel_wavs()
+    outs = pmel.mel_spectrogram_ragged([torch.from_numpy(w).to(DEV) for w in wavs])            # one ragged launch
+    for i, (w, o) in enumerate(zip(wavs, outs)):
+        o = o.cpu().numpy()
+        assert o.shape == (_lib.prompt_mel_frames(len(w)), 80) == g[f"mel_{i}"].shape            # frame counts: bit-exact
+        assert _pm_close(o, g[f"mel_{i}"]), i                                                    # what the verbatim reference produced
+        exact = frontend.prompt_mel_numpy(w)                                                     # float64 DFT
+        big = exact > np.log(1e-3)
+        assert np.abs(o - exact)[big].max() < 2e-4 and _pm_close(o, exact), i
+    # the reference call surface: numpy / (B, L) tensor in, (B, 80, T) out
+    batch = np.stack([wavs[0][:24000], wavs[1][:24000]])
+    got = pmel.mel_spectrogram(torch.from_numpy(batch).to(DEV))
+    assert tuple(got.shape) == (2, 80, 50) and _pm_close(got.cpu().numpy(), g["mel_batch"])
+    one = pmel.mel_spectrogram(wavs[1])                                                          # 1-D numpy branch (mel.py:40-44)
+    assert tuple(one.shape) == (1, 80, 62) and _pm_close(one[0].T.cpu().numpy(), g["mel_1"])
+
+
+def test_prompt_mel_errors_and_edges():
+    from chatterbox_embed_b200 import mel as pmel
+    with pytest.raises(RuntimeError):
+        pmel.mel_spectrogram(torch.zeros(1, 720, device=DEV))                                    # torch's reflect pad refuses it too
+    with pytest.raises(NotImplementedError):
+        pmel.mel_spectrogram(torch.zeros(1, 24000, device=DEV), n_fft=1024)
+    assert _lib.prompt_mel_frames(720) < 0 and _lib.prompt_mel_frames(721) == 1 and _lib.prompt_mel_frames(240000) == 500
+    z = pmel.mel_spectrogram(torch.zeros(1, 5000, device=DEV))                                   # silence: sqrt(1e-9) * sum(w) < 1e-5 -> the clamp
+    want = np.log(np.maximum(frontend.prompt_mel_basis().astype(np.float32).sum(1) * np.float32(np.sqrt(1e-9)), 1e-5))
+    assert np.abs(z[0].cpu().numpy() - want[:, None]).max() < 1e-5
+
+
+def test_prompt_mel_full_size_properties():
+    """BASELINE-size batch (256 clips x 10 s at 24 kHz = DEC_COND_LEN): shift invariance by one hop, gain linearity above the
+    clamp, batch invariance (bit-exact: no atomics on this path), and the float64 oracle on a sample of clips."""
+    from chatterbox_embed_b200 import mel as pmel
+    n = 240000
+    base = torch.from_numpy(np.stack([synth.clip(100 + i, n + 480) for i in range(8)])).to(DEV)
+    noise = 0.05 * torch.randn(256, n + 480, device=DEV, generator=torch.Generator(DEV).manual_seed(5))
+    x = noise + base.repeat(32, 1)
+    a = pmel.mel_spectrogram(x[:, :n])
+    b = pmel.mel_spectrogram(x[:, 480:])
+    assert tuple(a.shape) == (256, 80, 500)
+    # frames whose window does not touch the reflected edges see the same samples one hop apart
+    assert torch.equal(a[:, :, 3:-2], b[:, :, 2:-3])
+    c = pmel.mel_spectrogram(0.5 * x[:, :n])
+    live = a > float(np.log(4e-5))
+    assert (c - (a + float(np.log(0.5))))[live].abs().max() < 2e-3
+    assert torch.equal(pmel.mel_spectrogram(x[37:38, :n])[0], a[37])
+    for i in (0, 131, 255):
+        assert _pm_close(a[i].T.cpu().numpy(), frontend.prompt_mel_numpy(x[i, :n].cpu().numpy())), i
+
+
+def test_embed_ref_matches_reference_pipeline(models):
+    """S3Token2Mel.embed_ref (s3gen.py:150-207) without the tokenizer: 22.05 kHz in -> prompt_feat (24 kHz mel) + x-vector (16 kHz)."""
+    sdv, sdc, ve, cp = models["W1"]
+    rng = np.random.RandomState(8)
+    w = (0.1 * rng.randn(2 * 22050)).astype(np.float32)
+    d = SpeakerConditioner(cp).embed_ref(w, 22050)
+    w24 = frontend.resample_torchaudio(w, 22050, 24000)
+    assert d["prompt_token"] is None and d["prompt_feat_len"] is None
+    assert tuple(d["prompt_feat"].shape) == (1, frontend.prompt_mel_num_frames(len(w24)), 80)
+    assert _pm_close(d["prompt_feat"][0].cpu().numpy(), frontend.prompt_mel_torch(w24))
+    want = nets.campplus_embed_wavs(sdc, [frontend.resample_torchaudio(w, 22050, 16000)])
+    assert np.abs(d["embedding"].cpu().numpy() - want).max() < 1e-4 * max(1.0, float(np.abs(want).max()))

@@ -149,3 +149,33 @@ def test_resample_restatement_matches_torchaudio(src, dst):
     g = math.gcd(src, dst)
     bank, width = TF._get_sinc_resample_kernel(src, dst, g)
     assert np.abs(frontend.resample_bank(src, dst)[0] - bank.numpy()[:, 0, :]).max() == 0.0 and frontend.resample_bank(src, dst)[1] == width
+
+
+# ---- S3Gen prompt mel (s3gen/utils/mel.py:33-81): restatements against the fixture the verbatim reference produced ----------
+def prompt_mel_close(got, ref):
+    """The reference computes the 1920-point FFT in fp32: near the 1e-5 clamp its own log-mels sit up to ~1e-2 from the exact
+    value (2.6e-6 in the linear domain), so parity is stated in the linear domain: |d mel| <= 1e-5 + 5e-4 * mel."""
+    g, r = np.exp(np.asarray(got, np.float64)), np.exp(np.asarray(ref, np.float64))
+    return got.shape == ref.shape and bool(np.all(np.abs(g - r) <= 1e-5 + 5e-4 * r))
+
+
+def test_prompt_mel_oracle_vs_reference_fixture(golden_dir):
+    g = _load(golden_dir, "ref_prompt_mel.npz")
+    wavs = make_golden.prompt_mel_wavs()
+    for i, w in enumerate(wavs):
+        ref = g[f"mel_{i}"]
+        assert ref.shape == (frontend.prompt_mel_num_frames(len(w)), 80)
+        assert np.abs(frontend.prompt_mel_torch(w) - ref).max() < 1e-5          # same torch ops: equal up to thread-count effects
+        assert prompt_mel_close(frontend.prompt_mel_numpy(w), ref)             # float64 DFT restatement
+    assert np.abs(g["mel_batch"][0].T - frontend.prompt_mel_torch(wavs[0][:24000])).max() < 1e-5
+    with pytest.raises(ValueError):
+        frontend.prompt_mel_num_frames(720)
+    assert [frontend.prompt_mel_num_frames(n) for n in (721, 959, 960, 240000)] == [1, 1, 2, 500]
+
+
+def test_prompt_mel_basis_is_two_sparse():
+    """The kernel's epilogue relies on every DFT bin feeding at most two of the 80 filters and on bins 0 and >= 640 having no weight."""
+    B = frontend.prompt_mel_basis()
+    assert B.shape == (80, 961) and (B != 0).sum(0).max() == 2
+    used = np.flatnonzero((B != 0).any(0))
+    assert used[0] == 1 and used[-1] == 639
