@@ -50,6 +50,9 @@ _SIGS = {
     "cbx_resample_out_len": (C.c_int64, [C.c_int, C.c_int, C.c_int64]),
     "cbx_prompt_mel_frames": (C.c_int64, [C.c_int64]),
     "cbx_prompt_mel": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_int, C.c_void_p, C.c_void_p]),
+    "cbx_s3_log_mel_frames": (C.c_int64, [C.c_int64]),
+    "cbx_s3_log_mel": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_int, C.c_void_p, C.c_void_p]),
+    "cbx_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cbx_resample": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_void_p, _P(C.c_int64), C.c_void_p]),
     "cbx_ve_forward_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "cbx_ve_forward_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int]),
@@ -107,6 +110,10 @@ def resample_out_len(src_sr: int, dst_sr: int, n_samples: int) -> int:
 
 def prompt_mel_frames(n_samples: int) -> int:
     return int(lib().cbx_prompt_mel_frames(int(n_samples)))
+
+
+def s3_log_mel_frames(n_samples: int) -> int:
+    return int(lib().cbx_s3_log_mel_frames(int(n_samples)))
 
 
 def clip_cost(n_samples: int) -> float:
@@ -209,6 +216,14 @@ class Context:
         n = len(offsets) - 1
         a = (C.c_int64 * (n + 1))(*[int(v) for v in offsets])
         self._check(lib().cbx_prompt_mel(self._h, pcm_ptr, a, n, out_ptr, stream), "cbx_prompt_mel")
+
+    def s3_log_mel(self, pcm_ptr: int, offsets: Sequence[int], out_ptr: int, stream: int):
+        n = len(offsets) - 1
+        a = (C.c_int64 * (n + 1))(*[int(v) for v in offsets])
+        self._check(lib().cbx_s3_log_mel(self._h, pcm_ptr, a, n, out_ptr, stream), "cbx_s3_log_mel")
+
+    def project(self, x_ptr: int, n: int, in_dim: int, w_ptr: int, b_ptr: Optional[int], out_dim: int, normalize: bool, y_ptr: int, stream: int):
+        self._check(lib().cbx_project(self._h, x_ptr, int(n), int(in_dim), w_ptr, b_ptr, int(out_dim), int(bool(normalize)), y_ptr, stream), "cbx_project")
 
     def ve_forward_workspace_bytes(self, n: int) -> int:
         return self._check(lib().cbx_ve_forward_workspace_bytes(self._h, n), "cbx_ve_forward_workspace_bytes")

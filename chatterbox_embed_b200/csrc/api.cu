@@ -228,6 +228,8 @@ void cbx_destroy(cbx_ctx* c) {
   cudaFree(c->own_ws);
   for (auto& kv : c->resample_banks) cudaFree(kv.second);
   cudaFree(c->resample_clips);
+  cudaFree(c->s3_clips);
+  cudaFree(c->s3_tmp);
   cudaFree(c->pm.blob);
   cudaFree(c->pm.clips);
   for (auto& s : c->slot) {

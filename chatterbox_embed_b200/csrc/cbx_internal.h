@@ -18,6 +18,7 @@ constexpr int kSR = 16000;
 constexpr int kVeNfft = 400, kVeHop = 160, kVeBins = 201, kVeMels = 40;
 constexpr int kVePartial = 160, kVeHidden = 256, kVeEmbed = 256, kVeGates = 1024;
 constexpr int kVeSpecN = 2 * kVeBins;      // interleaved re/im columns of the DFT GEMM
+constexpr int kS3Mels = 128;                // S3Tokenizer log-mel (s3tokenizer.py:39-47): the VoiceEncoder STFT with 128 mels
 constexpr int kVeTcBins = 200, kKTcBins = 256;   // bins (incl. one zero pad) of the tensor-core front-end GEMMs
 // Kaldi fbank as called by xvector.py:50 (torchaudio kaldi.py defaults, 80 bins)
 constexpr int kKWin = 400, kKHop = 160, kKPad = 512, kKBins = 257, kKMels = 80;
@@ -124,6 +125,7 @@ struct FrontendTables {
   const float *ve_dft_hi, *ve_dft_lo;   // [400][400]  bins 1..199 + one zero pair
   const float *k_dft_hi, *k_dft_lo;     // [512][400]  bins 1..255 + one zero pair
   const float *ve_bins, *k_bins;        // [200][4], [256][4]
+  const float *s3_bins;                 // [200][4]
   CUtensorMap tm_ve_hi[2], tm_ve_lo[2], tm_k_hi, tm_k_lo;
 };
 // S3Gen prompt mel (promptmel_tc.cu), built on first use: Hann-folded 1920-point DFT rows of bins 1..639 split hi/lo, bin -> mel table
@@ -172,6 +174,9 @@ struct cbx_ctx {
   std::map<long long, float*> resample_banks;
   void* resample_clips = nullptr; int resample_clips_cap = 0;
   cbx::PromptMelTables pm;
+  // S3Tokenizer log-mel (frontend_tc.cu): clip table, per-clip maxima, [frames][128] scratch
+  void* s3_clips = nullptr; int s3_clips_cap = 0;
+  float* s3_tmp = nullptr; int64_t s3_tmp_cap = 0;
   // last-run bookkeeping for the stage taps
   std::vector<cbx::ClipPlan> last_plan;
   std::map<std::string, std::vector<int64_t>> taps;   // name -> {byte_offset, rows, cols, ld}

@@ -5,6 +5,9 @@
 //   Kaldi fbank       (xvector.py:50, torchaudio kaldi.py:514-645):
 //                                           raw frames [T x 400] . (DC-removal/pre-emphasis/Povey-folded 512-pt DFT)^T [400 x 2*255]
 //                                           -> 80 HTK mels -> log(max(., eps))
+//   S3Tokenizer log-mel (s3tokenizer.py:128-168): the VoiceEncoder's frames and DFT (torch.stft 400/160, centred, reflect),
+//                                           last frame dropped -> 128 Slaney mels -> log10(max(., 1e-10)), per-clip max - 8 floor
+//                                           and (x + 4) / 4 in a second, transposing pass (the consumer wants [128][T])
 //
 // Precision: plain TF32 is not acceptable here (the log exposes near-empty bins: errors of 4.5 in the log domain on chirps,
 // SURVEY.md 8d hazard 3), so both operands are split hi + lo and the product is 3 MMAs: A_hi.B_hi + A_lo.B_hi + A_hi.B_lo.
@@ -58,8 +61,35 @@ struct VeRows {
   }
   __device__ bool live(int) const { return true; }      // rows past the clip are zero frames -> zero mels (voice_encoder.py:176-179)
 };
+// S3Tokenizer frames: ragged clips back to back, centred reflect pad 200, frames 0 .. L/160 - 1 (s3tokenizer.py:158-163)
+struct S3Clip { long long pcm_off; int n; int row0; int frames; int pad; };
+struct S3Rows {
+  const S3Clip* clips; int n_clips; float* cmax;
+  __device__ int clip_of(int row) const {
+    int lo = 0, hi = n_clips - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (clips[mid].row0 <= row) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+  }
+  __device__ RowDesc operator()(int row) const {
+    const S3Clip c = clips[clip_of(row)];
+    const int t = row - c.row0;
+    if (t >= c.frames) return RowDesc{0, 0, 0};
+    return RowDesc{c.pcm_off, t * kVeHop - kVeNfft / 2, c.n};
+  }
+  __device__ bool live(int) const { return true; }
+  // float max through integer atomics (init -inf): positive values by signed max, negative ones by unsigned min
+  __device__ void note_max(int row, float v) const {
+    float* a = cmax + clip_of(row);
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(a), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(a), __float_as_uint(v));
+  }
+};
 
-template <class Rows, int NB1, int NMEL, bool LOG>
+// LOG: 0 = power mel, 1 = ln(max(., eps)) (Kaldi), 2 = log10(max(., 1e-10)) + per-clip maximum (S3Tokenizer)
+template <class Rows, int NB1, int NMEL, int LOG>
 __global__ void __launch_bounds__(192, 1)
 dftmel_kernel(const __grid_constant__ CUtensorMap tmHi0, const __grid_constant__ CUtensorMap tmLo0,
               const __grid_constant__ CUtensorMap tmHi1, const __grid_constant__ CUtensorMap tmLo1,
@@ -67,7 +97,7 @@ dftmel_kernel(const __grid_constant__ CUtensorMap tmHi0, const __grid_constant__
   constexpr int NB0 = 256;
   constexpr int NTOT = NB0 + NB1;
   constexpr int MELLD = NMEL + 1;
-  static_assert(BM * MELLD * 4 <= SA * 2 * A_BYTES, "mel accumulators overlay the A stages");
+  static_assert(BM * MELLD * 4 <= SA * 2 * A_BYTES + SB * B_BYTES, "mel accumulators overlay the (drained) A and B stages");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                                   // [SA][hi | lo][128 x 128 B]
@@ -222,10 +252,17 @@ dftmel_kernel(const __grid_constant__ CUtensorMap tmHi0, const __grid_constant__
       const int gr = m0 + r;
       if (gr >= rows) break;
       const bool live = rows_fn.live(gr);
+      float mx = -INFINITY;
       for (int m = lane; m < NMEL; m += 32) {
         float val = melacc[r * MELLD + m];
-        if (LOG) val = logf(fmaxf(val, 1.1920928955078125e-07f));
+        if (LOG == 1) val = logf(fmaxf(val, 1.1920928955078125e-07f));
+        if (LOG == 2) { val = log10f(fmaxf(val, 1e-10f)); mx = fmaxf(mx, val); }
         out[(size_t)gr * NMEL + m] = live ? val : 0.f;
+      }
+      if constexpr (LOG == 2) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) rows_fn.note_max(gr, mx);
       }
     }
   }
@@ -233,7 +270,7 @@ dftmel_kernel(const __grid_constant__ CUtensorMap tmHi0, const __grid_constant__
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-template <class Rows, int NB1, int NMEL, bool LOG>
+template <class Rows, int NB1, int NMEL, int LOG>
 void launch(cbx_ctx* c, cudaStream_t st, const char* tag, const CUtensorMap& hi0, const CUtensorMap& lo0, const CUtensorMap& hi1,
             const CUtensorMap& lo1, const float* pcm, Rows rf, const float* bintab, float* out, int rows) {
   if (rows <= 0) return;
@@ -244,18 +281,98 @@ void launch(cbx_ctx* c, cudaStream_t st, const char* tag, const CUtensorMap& hi0
   kern<<<(rows + BM - 1) / BM, 192, SMEM_BYTES, st>>>(hi0, lo0, hi1, lo1, pcm, rf, reinterpret_cast<const float4*>(bintab), out, rows);
 }
 
+// second pass of the S3Tokenizer log-mel: floor at (clip max - 8), (x + 4) / 4, [T][128] -> [128][T] through a 32 x 32 tile
+__global__ void __launch_bounds__(256) s3_finish_kernel(const float* __restrict__ tmp, const S3Clip* __restrict__ clips, const float* __restrict__ cmax,
+                                                        float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const S3Clip c = clips[blockIdx.z];
+  const int t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  if (t0 >= c.frames) return;
+  const float floor_v = cmax[blockIdx.z] - 8.0f;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i;
+    tile[i][tx] = t < c.frames ? tmp[((size_t)c.row0 + t) * kS3Mels + m0 + tx] : 0.f;
+  }
+  __syncthreads();
+  float* o = out + (size_t)c.row0 * kS3Mels;            // clip block: [128][frames]
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + tx;
+    if (t < c.frames) o[(size_t)(m0 + i) * c.frames + t] = (fmaxf(tile[tx][i], floor_v) + 4.0f) / 4.0f;
+  }
+}
+
 }  // namespace fe
 
 void run_ve_mel_tc(cbx_ctx* c, const float* pcm, const VeChunk& ch, cudaStream_t st) {
   const FrontendTables& F = c->ft;
-  fe::launch<fe::VeRows, 2 * kVeTcBins - 256, kVeMels, false>(c, st, "ve_dftmel_tc_kernel", F.tm_ve_hi[0], F.tm_ve_lo[0], F.tm_ve_hi[1], F.tm_ve_lo[1],
+  fe::launch<fe::VeRows, 2 * kVeTcBins - 256, kVeMels, 0>(c, st, "ve_dftmel_tc_kernel", F.tm_ve_hi[0], F.tm_ve_lo[0], F.tm_ve_hi[1], F.tm_ve_lo[1],
                                                             pcm, fe::VeRows{ch.plan, ch.dyn, ch.mel_row_clip}, F.ve_bins, ch.mel, ch.mel_rows);
 }
 
 void run_kaldi_fbank_tc(cbx_ctx* c, const float* pcm, const XvChunk& ch, cudaStream_t st) {
   const FrontendTables& F = c->ft;
-  fe::launch<fe::KaldiRows, 2 * kKTcBins - 256, kKMels, true>(c, st, "kaldi_dftmel_tc_kernel", F.tm_k_hi, F.tm_k_lo, F.tm_k_hi, F.tm_k_lo,
+  fe::launch<fe::KaldiRows, 2 * kKTcBins - 256, kKMels, 1>(c, st, "kaldi_dftmel_tc_kernel", F.tm_k_hi, F.tm_k_lo, F.tm_k_hi, F.tm_k_lo,
                                                              pcm, fe::KaldiRows{ch.plan, ch.fb_row_clip}, F.k_bins, ch.fbank, ch.fb_rows);
 }
 
 }  // namespace cbx
+
+using namespace cbx;
+
+extern "C" {
+
+int64_t cbx_s3_log_mel_frames(int64_t n_samples) {
+  if (n_samples <= kVeNfft / 2) return CBX_ERR_ARG;      // torch.stft(center=True) reflect pad needs more than n_fft / 2 samples
+  return n_samples / kVeHop;                             // 1 + L / 160 frames, the last one dropped (s3tokenizer.py:163)
+}
+
+int cbx_s3_log_mel(cbx_ctx* c, const float* pcm_dev, const int64_t* offsets_host, int n_clips, float* out_dev, void* stream) {
+  if (!c) return CBX_ERR_ARG;
+  if (!pcm_dev || !out_dev || !offsets_host || n_clips <= 0) { c->err = "bad argument"; return CBX_ERR_ARG; }
+  cudaSetDevice(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  // host image of the device table: n_clips S3Clip records followed by n_clips floats of -inf (the identity of note_max)
+  const size_t table_bytes = (sizeof(fe::S3Clip) + sizeof(float)) * (size_t)n_clips;
+  std::vector<uint8_t> host(table_bytes);
+  fe::S3Clip* clips = reinterpret_cast<fe::S3Clip*>(host.data());
+  float* ninf = reinterpret_cast<float*>(clips + n_clips);
+  int64_t rows = 0; int max_frames = 0;
+  for (int i = 0; i < n_clips; ++i) {
+    const int64_t len = offsets_host[i + 1] - offsets_host[i];
+    if (len <= kVeNfft / 2) { c->err = "s3 log-mel: clip of " + std::to_string(len) + " samples; the centred STFT's reflect padding needs more than 200"; return CBX_ERR_ARG; }
+    if (len > ((int64_t)1 << 30)) { c->err = "s3 log-mel: clip too long"; return CBX_ERR_ARG; }
+    const int fr = (int)(len / kVeHop);
+    clips[i] = fe::S3Clip{(long long)offsets_host[i], (int)len, (int)rows, fr, 0};
+    ninf[i] = -INFINITY;
+    rows += fr;
+    max_frames = std::max(max_frames, fr);
+    if (rows > 0x7fffffffLL / kS3Mels) { c->err = "s3 log-mel: too many frames in one call"; return CBX_ERR_ARG; }
+  }
+  if (rows == 0) return CBX_OK;
+  if (c->s3_clips_cap < n_clips) {
+    if (c->s3_clips) cudaFree(c->s3_clips);
+    c->s3_clips_cap = n_clips + n_clips / 2 + 16;
+    CBX_CUDA_OK(c, cudaMalloc(&c->s3_clips, (sizeof(fe::S3Clip) + sizeof(float)) * c->s3_clips_cap));
+  }
+  if (c->s3_tmp_cap < rows * kS3Mels) {
+    if (c->s3_tmp) cudaFree(c->s3_tmp);
+    c->s3_tmp_cap = rows * kS3Mels + rows * kS3Mels / 4;
+    CBX_CUDA_OK(c, cudaMalloc((void**)&c->s3_tmp, sizeof(float) * c->s3_tmp_cap));
+  }
+  fe::S3Clip* dclips = (fe::S3Clip*)c->s3_clips;
+  float* cmax = reinterpret_cast<float*>(dclips + n_clips);
+  CBX_CUDA_OK(c, cudaMemcpyAsync(dclips, host.data(), table_bytes, cudaMemcpyHostToDevice, st));
+  const FrontendTables& F = c->ft;
+  fe::launch<fe::S3Rows, 2 * kVeTcBins - 256, kS3Mels, 2>(c, st, "s3_dftmel_tc_kernel", F.tm_ve_hi[0], F.tm_ve_lo[0], F.tm_ve_hi[1], F.tm_ve_lo[1],
+                                                          pcm_dev, fe::S3Rows{dclips, n_clips, cmax}, F.s3_bins, c->s3_tmp, (int)rows);
+  for (int z0 = 0; z0 < n_clips; z0 += 65535) {
+    const int nz = std::min(65535, n_clips - z0);
+    Scope sc(c->launches, st, "s3_finish_kernel", 0.0, 8.0 * rows * kS3Mels * nz / n_clips);
+    fe::s3_finish_kernel<<<dim3((max_frames + 31) / 32, kS3Mels / 32, nz), 256, 0, st>>>(c->s3_tmp, dclips + z0, cmax + z0, out_dev);
+  }
+  CBX_CUDA_OK(c, cudaGetLastError());
+  return CBX_OK;
+}
+
+}  // extern "C"

@@ -355,21 +355,27 @@ int build_frontend_tables(cbx_ctx* c) {
     for (size_t i = 0; i < d.size(); ++i) d[i] = (float)dd[i];
     pk.add(&F.ve_dft, d);
     split_dft(pk, dd, kVeNfft, 1, kVeTcBins, &F.ve_dft_hi, &F.ve_dft_lo);
-    // librosa.filters.mel(sr=16000,n_fft=400,n_mels=40,fmin=0,fmax=8000): Slaney scale + area norm (melspec.py:11-16)
-    std::vector<double> edges(kVeMels + 2);
-    const double m_lo = slaney_hz_to_mel(0.0), m_hi = slaney_hz_to_mel(8000.0);
-    for (int i = 0; i < kVeMels + 2; ++i) edges[i] = slaney_mel_to_hz(m_lo + (m_hi - m_lo) * i / (kVeMels + 1));
-    std::vector<float> mel((size_t)kVeMels * kVeBins);
-    for (int m = 0; m < kVeMels; ++m)
-      for (int k = 0; k < kVeBins; ++k) {
-        double f = (double)kSR / 2.0 * k / (kVeBins - 1);
-        double up = (f - edges[m]) / (edges[m + 1] - edges[m]);
-        double dn = (edges[m + 2] - f) / (edges[m + 2] - edges[m + 1]);
-        float tri = (float)std::fmax(0.0, std::fmin(up, dn));
-        mel[(size_t)m * kVeBins + k] = (float)((double)tri * (2.0 / (edges[m + 2] - edges[m])));
-      }
+    // librosa.filters.mel(sr=16000,n_fft=400,n_mels,fmin=0,fmax=8000): Slaney scale + area norm (melspec.py:11-16)
+    auto slaney_bank = [](int nmels) {
+      std::vector<double> edges(nmels + 2);
+      const double m_lo = slaney_hz_to_mel(0.0), m_hi = slaney_hz_to_mel(8000.0);
+      for (int i = 0; i < nmels + 2; ++i) edges[i] = slaney_mel_to_hz(m_lo + (m_hi - m_lo) * i / (nmels + 1));
+      std::vector<float> mel((size_t)nmels * kVeBins);
+      for (int m = 0; m < nmels; ++m)
+        for (int k = 0; k < kVeBins; ++k) {
+          double f = (double)kSR / 2.0 * k / (kVeBins - 1);
+          double up = (f - edges[m]) / (edges[m + 1] - edges[m]);
+          double dn = (edges[m + 2] - f) / (edges[m + 2] - edges[m + 1]);
+          float tri = (float)std::fmax(0.0, std::fmin(up, dn));
+          mel[(size_t)m * kVeBins + k] = (float)((double)tri * (2.0 / (edges[m + 2] - edges[m])));
+        }
+      return mel;
+    };
+    std::vector<float> mel = slaney_bank(kVeMels);
     pk.add(&F.ve_mel, mel);
     bin_table(pk, mel, kVeMels, kVeBins, 1, kVeTcBins, &F.ve_bins);
+    // S3Tokenizer: same STFT, 128 mels (s3tokenizer.py:39-47)
+    bin_table(pk, slaney_bank(kS3Mels), kS3Mels, kVeBins, 1, kVeTcBins, &F.s3_bins);
   }
   {  // Kaldi: DC removal, pre-emphasis 0.97 (replicate-left), Povey window and zero-pad to 512 folded into
      // one [514][400] matrix (torchaudio kaldi.py:183-211).

@@ -141,6 +141,25 @@ int cbx_resample(cbx_ctx* ctx, const float* x_dev, const int64_t* in_offsets_hos
 int64_t cbx_prompt_mel_frames(int64_t n_samples);
 int cbx_prompt_mel(cbx_ctx* ctx, const float* pcm_dev, const int64_t* offsets_host, int n_clips, float* out_dev, void* stream);
 
+/* ---- S3Tokenizer front-end ("next" row 3) ------------------------------------------------------------ */
+/* S3Tokenizer.log_mel_spectrogram (s3tokenizer/s3tokenizer.py:128-168): torch.stft(400, 160, Hann, centred/reflect) with
+ * the last frame dropped, power, 128 Slaney mels, log10(clamp(., 1e-10)), floor at (clip maximum - 8), (x + 4) / 4.
+ * Ragged batch of 16 kHz clips back to back; out_dev holds one [128][T_i] block per clip, clip after clip,
+ * T_i = cbx_s3_log_mel_frames(len_i) = len_i / 160 -- the [F, T] layout quantize() takes.  The maximum is per clip (the
+ * reference calls the method one clip at a time, s3tokenizer.py:107-113).  Clips of <= 200 samples are refused like
+ * torch.stft's reflect pad refuses them.  The tokenizer network itself (third-party s3tokenizer package) is not part of
+ * this library.  Stream ordered. */
+int64_t cbx_s3_log_mel_frames(int64_t n_samples);
+int cbx_s3_log_mel(cbx_ctx* ctx, const float* pcm_dev, const int64_t* offsets_host, int n_clips, float* out_dev, void* stream);
+
+/* ---- consumer projections ("next" row 4) ------------------------------------------------------------ */
+/* y[i] = W . (normalize ? x[i] / max(||x[i]||, 1e-12) : x[i]) + b for n embedding rows: T3CondEnc.spkr_enc
+ * Linear(256 -> 1024) on the VoiceEncoder embedding (t3/modules/cond_enc.py:50,70; normalize = 0) and F.normalize +
+ * spk_embed_affine_layer Linear(192 -> 80) on the x-vector (s3gen/flow.py:252-253; normalize = 1).  x_dev [n][in_dim],
+ * w_dev [out_dim][in_dim] (torch Linear layout), b_dev [out_dim] or NULL, y_dev [n][out_dim]; in_dim <= 1024. */
+int cbx_project(cbx_ctx* ctx, const float* x_dev, int64_t n, int in_dim, const float* w_dev, const float* b_dev, int out_dim,
+                int normalize, float* y_dev, void* stream);
+
 /* VoiceEncoder.forward on already-cut partials (voice_encoder.py:139-160):
  * mels_dev [n_partials,160,40] -> out_dev [n_partials,256] (L2-normed). */
 int cbx_ve_forward_partials(cbx_ctx* ctx, const float* mels_dev, int n_partials, float* out_dev,

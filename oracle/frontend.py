@@ -306,3 +306,38 @@ def prompt_mel_torch(wav):
     spec = torch.sqrt(spec.pow(2).sum(-1) + 1e-9)
     mel = torch.matmul(torch.from_numpy(prompt_mel_basis()).float(), spec)
     return np.ascontiguousarray(torch.log(torch.clamp(mel, min=1e-5))[0].T.numpy())
+
+
+# ----------------------------------------------------------------------------
+# S3Tokenizer log-mel (16 kHz, 128 bins) -- s3tokenizer/s3tokenizer.py:128-168 (filters :39-47)
+# ----------------------------------------------------------------------------
+_s3_basis = None
+
+
+def s3_mel_basis():
+    global _s3_basis
+    if _s3_basis is None:
+        _s3_basis = filters_mel(16000, 400, 128)
+    return _s3_basis
+
+
+def s3_log_mel_numpy(wav):
+    """(L,) float32 -> (128, L // 160) float32, float64 DFT."""
+    spec = stft(np.asarray(wav, dtype=np.float32), 400, 160, 400, True, "reflect")
+    mag = (np.abs(spec.astype(np.complex128))[:, :-1] ** 2).astype(np.float32)
+    mel = s3_mel_basis().astype(np.float32) @ mag
+    log_spec = np.log10(np.maximum(mel, 1e-10))
+    log_spec = np.maximum(log_spec, log_spec.max() - 8.0)
+    return ((log_spec + 4.0) / 4.0).astype(np.float32)
+
+
+def s3_log_mel_torch(wav):
+    """The same with the reference's torch ops (fp32 torch.stft)."""
+    import torch
+    audio = torch.as_tensor(np.asarray(wav, dtype=np.float32))
+    st = torch.stft(audio, 400, 160, window=torch.hann_window(400), return_complex=True)
+    magnitudes = st[..., :-1].abs() ** 2
+    mel_spec = torch.from_numpy(s3_mel_basis()).float() @ magnitudes
+    log_spec = torch.clamp(mel_spec, min=1e-10).log10()
+    log_spec = torch.maximum(log_spec, log_spec.max() - 8.0)
+    return ((log_spec + 4.0) / 4.0).numpy()

@@ -50,6 +50,31 @@ def main_prompt_mel():
     print("prompt_mel", {k: v.shape for k, v in out.items()})
 
 
+def s3_wavs():
+    """16 kHz inputs of the S3Tokenizer log-mel fixture: voice-like, white noise, a chirp (bins 8 decades below the peak: the
+    max - 8 floor), the shortest legal clip, a length that is not a hop multiple."""
+    rng = np.random.RandomState(16)
+    t = np.arange(40000) / 16000.0
+    chirp = (0.5 * np.sin(2 * np.pi * (100.0 * t + 0.5 * 7000.0 * t * t / t[-1]))).astype(np.float32)
+    return [synth.clip(11, 48000), (0.1 * rng.randn(16001)).astype(np.float32), chirp, synth.clip(12, 201), synth.clip(13, 25599)]
+
+
+def main_s3():
+    """tests/golden/ref_s3_log_mel.npz from the verbatim s3tokenizer.py (its third-party base class stubbed, refload.py)."""
+    assert refload.available(), "reference tree not found"
+    tok = refload.s3tokenizer_module().S3Tokenizer()
+    out = {}
+    for i, w in enumerate(s3_wavs()):
+        out[f"mel_{i}"] = tok.log_mel_spectrogram(torch.from_numpy(w)[None])[0].numpy()           # (128, L // 160)
+    batch = np.stack([s3_wavs()[0][:16000], s3_wavs()[1][:16000] * 1e-3])
+    out["mel_batch"] = tok.log_mel_spectrogram(torch.from_numpy(batch)).numpy()                  # one call: the floor is global
+    lens = [1, 639, 640, 641, 16000, 16001, 25599, 160000]
+    out["pad_in"] = np.array(lens)
+    out["pad_out"] = np.array([tok.pad([np.zeros(n, np.float32)], 16000)[0].shape[1] for n in lens])
+    np.savez_compressed(os.path.join(OUT, "ref_s3_log_mel.npz"), **out)
+    print("s3_log_mel", {k: v.shape for k, v in out.items()})
+
+
 def main():
     assert refload.available(), "reference tree not found"
     os.makedirs(OUT, exist_ok=True)
@@ -98,6 +123,9 @@ if __name__ == "__main__":
     import sys
     if "--prompt-mel" in sys.argv:          # only this fixture (the others stay byte-identical in git)
         main_prompt_mel()
+    elif "--s3" in sys.argv:
+        main_s3()
     else:
         main()
         main_prompt_mel()
+        main_s3()

@@ -54,6 +54,40 @@ def mel_module():
     return mod
 
 
+def s3tokenizer_module():
+    """s3tokenizer/s3tokenizer.py verbatim.  Its base class comes from the third-party ``s3tokenizer`` package (pip, unpinned
+    in the reference's pyproject, absent here): a stub with the three names the file imports stands in, so that the
+    reference's own ``pad`` / ``log_mel_spectrogram`` run unmodified.  ``quantize`` (the network) is not available."""
+    if "ref_s3tokenizer" in sys.modules:
+        return sys.modules["ref_s3tokenizer"]
+    import torch
+    frontend.register_librosa_shim()
+
+    class ModelConfig:
+        n_mels = 128
+
+    class S3TokenizerV2(torch.nn.Module):
+        def __init__(self, name, config=ModelConfig()):
+            super().__init__()
+
+        @property
+        def device(self):
+            return torch.device("cpu")
+
+    stub = types.ModuleType("s3tokenizer")
+    stub.utils = types.ModuleType("s3tokenizer.utils")
+    stub.utils.padding = None
+    stub.model_v2 = types.ModuleType("s3tokenizer.model_v2")
+    stub.model_v2.S3TokenizerV2, stub.model_v2.ModelConfig = S3TokenizerV2, ModelConfig
+    for k, v in (("s3tokenizer", stub), ("s3tokenizer.utils", stub.utils), ("s3tokenizer.model_v2", stub.model_v2)):
+        sys.modules.setdefault(k, v)
+    spec = importlib.util.spec_from_file_location("ref_s3tokenizer", os.path.join(_MODELS, "s3tokenizer", "s3tokenizer.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ref_s3tokenizer"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_voice_encoder(sd):
     ve = voice_encoder_module().VoiceEncoder()
     ve.load_state_dict(sd, strict=True)

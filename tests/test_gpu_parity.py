@@ -436,3 +436,95 @@ def test_embed_ref_matches_reference_pipeline(models):
     assert _pm_close(d["prompt_feat"][0].cpu().numpy(), frontend.prompt_mel_torch(w24))
     want = nets.campplus_embed_wavs(sdc, [frontend.resample_torchaudio(w, 22050, 16000)])
     assert np.abs(d["embedding"].cpu().numpy() - want).max() < 1e-4 * max(1.0, float(np.abs(want).max()))
+
+
+# ---- "next" row 2: voice-profile container and batched profile creation (tts.py:510-553, vc.py:606-671) --------------------
+def test_voice_profiles_batched(models, tmp_path):
+    from chatterbox_embed_b200 import VoiceProfiler, load_voice_profile
+    sdv, sdc, ve, cp = models["W1"]
+    rng = np.random.RandomState(21)
+    srs = [16000, 24000, 22050, 16000]
+    wavs = [(0.1 * rng.randn(int(sr * d))).astype(np.float32) for sr, d in zip(srs, (2.0, 1.5, 3.1, 1.0))]
+    paths = [str(tmp_path / f"p{i}.npy") for i in range(4)]
+    prof = VoiceProfiler(ve, cp)
+    prof.save_voice_profiles(wavs, srs, paths)
+    for w, sr, p in zip(wavs, srs, paths):
+        got = load_voice_profile(p)
+        w16 = w if sr == 16000 else frontend.resample_torchaudio(w, sr, 16000)
+        w24 = w if sr == 24000 else frontend.resample_torchaudio(w, sr, 24000)
+        assert got.prompt_token is None and tuple(got.prompt_feat.shape) == (1, frontend.prompt_mel_num_frames(len(w24)), 80)
+        assert _pm_close(got.prompt_feat[0].numpy(), frontend.prompt_mel_torch(w24))
+        want_xv = nets.campplus_embed_wavs(sdc, [w16])
+        want_ve = nets.ve_embed_wavs(sdv, [w16])
+        assert tuple(got.embedding.shape) == (1, 192) and tuple(got.ve_embedding.shape) == (1, 256)
+        assert np.abs(got.embedding.numpy() - want_xv).max() < 1e-4 * max(1.0, float(np.abs(want_xv).max()))
+        assert np.abs(got.ve_embedding.numpy() - want_ve).max() < 1e-4
+    # the single-clip call of the reference writes the same file as the batch
+    prof.save_voice_profile((wavs[2], srs[2]), str(tmp_path / "single.npy"))
+    one = load_voice_profile(str(tmp_path / "single.npy"))
+    two = load_voice_profile(paths[2])
+    assert torch.equal(one.prompt_feat, two.prompt_feat) and float((one.embedding - two.embedding).abs().max()) < 1e-5
+
+
+# ---- "next" row 4: the consumers' first projections (cond_enc.py:50,70; flow.py:252-253) -----------------------------------
+@pytest.mark.parametrize("n", [1, 5, 33, 4096])
+def test_consumer_projections(n):
+    from chatterbox_embed_b200 import SpeakerProjections
+    torch.manual_seed(4)
+    m = SpeakerProjections().to(DEV)
+    ve = torch.nn.functional.normalize(torch.randn(n, 256), dim=1)
+    xv = 14.0 * torch.randn(n, 192)
+    if n > 1:
+        xv[1] = 0.0                                                    # F.normalize's eps branch: 0 / max(0, 1e-12)
+    lin1 = torch.nn.Linear(256, 1024); lin1.load_state_dict({k: v.cpu() for k, v in m.spkr_enc.state_dict().items()})
+    lin2 = torch.nn.Linear(192, 80); lin2.load_state_dict({k: v.cpu() for k, v in m.spk_embed_affine_layer.state_dict().items()})
+    with torch.no_grad():
+        want1 = lin1.double()(ve.double())[:, None]
+        want2 = lin2.double()(torch.nn.functional.normalize(xv.double(), dim=1))
+    got1 = m.t3_speaker_cond(ve.to(DEV)).cpu()
+    got2 = m.flow_speaker_cond(xv.to(DEV)).cpu()
+    assert tuple(got1.shape) == (n, 1, 1024) and tuple(got2.shape) == (n, 80)
+    assert (got1.double() - want1).abs().max() < 2e-6 and (got2.double() - want2).abs().max() < 2e-6
+
+
+# ---- "next" row 3: the S3Tokenizer front-end (s3tokenizer.py:52-74, 128-168) ------------------------------------------------
+def test_s3_log_mel_golden_and_oracle(golden_dir):
+    from chatterbox_embed_b200 import s3tokenizer as s3
+    g = np.load(os.path.join(golden_dir, "ref_s3_log_mel.npz"))
+    wavs = make_golden.s3_wavs()
+    outs = s3.log_mel_spectrogram_ragged([torch.from_numpy(w).to(DEV) for w in wavs])
+    for i, (w, o) in enumerate(zip(wavs, outs)):
+        o = o.cpu().numpy()
+        assert o.shape == (128, _lib.s3_log_mel_frames(len(w))) == g[f"mel_{i}"].shape
+        # values are (log10 + 4) / 4; the reference's own fp32 FFT sits up to 6e-5 from the float64 result
+        assert np.abs(o - g[f"mel_{i}"]).max() < 2e-4, i
+        assert np.abs(o - frontend.s3_log_mel_numpy(w)).max() < 1e-4, i
+    fe = s3.S3TokenizerFrontend(DEV)
+    batch = np.stack([wavs[0][:16000], wavs[1][:16000] * 1e-3])
+    got = fe.log_mel_spectrogram(torch.from_numpy(batch))                         # one call, two rows: global floor
+    assert tuple(got.shape) == (2, 128, 100) and np.abs(got.cpu().numpy() - g["mel_batch"]).max() < 2e-4
+    assert [fe.pad([np.zeros(int(n), np.float32)], 16000)[0].shape[1] for n in g["pad_in"]] == g["pad_out"].tolist()
+    mels, lens = fe.mels(wavs, max_len=50)
+    assert tuple(mels.shape) == (5, 128, 200) and lens.tolist() == [200, 100, 200, 1, 159]
+    assert torch.equal(mels[3, :, :1], outs[3]) and float(mels[3, :, 1:].abs().max()) == 0.0
+    with pytest.raises(NotImplementedError):
+        fe.forward(wavs)
+    with pytest.raises(RuntimeError):
+        s3.log_mel_spectrogram_ragged([torch.zeros(200, device=DEV)])
+
+
+def test_s3_log_mel_full_size_properties():
+    """256 clips x 10 s: batch invariance and hop-shift invariance (bit-exact away from the floor / edges), float64 oracle on a sample."""
+    from chatterbox_embed_b200 import s3tokenizer as s3
+    n = 160000
+    x = 0.1 * torch.randn(256, n + 160, device=DEV, generator=torch.Generator(DEV).manual_seed(9))
+    a = torch.stack(s3.log_mel_spectrogram_ragged([r for r in x[:, :n]]))
+    assert tuple(a.shape) == (256, 128, 1000)
+    b = torch.stack(s3.log_mel_spectrogram_ragged([r for r in x[:, 160:]]))
+    assert torch.equal(a[:, :, 3:-2], b[:, :, 2:-3])                             # white noise: nothing reaches the max - 8 floor
+    assert torch.equal(s3.log_mel_spectrogram_ragged([x[77, :n]])[0], a[77])
+    for i in (0, 255):
+        # the 3xTF32 DFT carries ~2^-22 of the frame's energy as noise (fp32 FFT: ~2^-24): a narrow filter whose single bin
+        # happens to be ~1000x below the frame's typical magnitude (a few of the 128 000 values) shows it in the log domain
+        d = np.abs(a[i].cpu().numpy() - frontend.s3_log_mel_numpy(x[i, :n].cpu().numpy()))
+        assert d.max() < 1e-3 and np.quantile(d, 0.9999) < 3e-5 and np.median(d) < 2e-6

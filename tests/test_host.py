@@ -84,3 +84,42 @@ def test_scheduler_partition_balances_and_inverts():
         inv = scheduler.inverse_permutation(shards, len(lens))
         gathered = np.concatenate([np.pad(s, (0, max(sizes) - len(s)), constant_values=-1) for s in shards])
         assert (gathered[inv] == np.arange(len(lens))).all()
+
+
+def test_voice_profile_container_round_trip(tmp_path):
+    """The .npy pickle-dict container of s3gen.py:427-470 / tts.py:537-586: keys, shapes, dtypes, optional fields, old-format files."""
+    import torch
+    from chatterbox_embed_b200 import voice_profile as vp
+    rng = np.random.RandomState(0)
+    emb, ve = rng.randn(1, 192).astype(np.float32), rng.randn(1, 256).astype(np.float32)
+    feat = rng.randn(1, 37, 80).astype(np.float32)
+    tok, tok_len = rng.randint(0, 6561, (1, 18)).astype(np.int64), np.array([18], np.int64)
+    prof = vp.VoiceProfile(torch.from_numpy(emb), torch.from_numpy(feat), None, torch.from_numpy(tok), torch.from_numpy(tok_len))
+    p = str(tmp_path / "profile.npy")
+    np.save(p, vp.profile_dict(prof, ve_embedding=torch.from_numpy(ve)))
+    raw = np.load(p, allow_pickle=True).item()                     # what the reference's readers do (tts.py:559, s3gen.py:449)
+    assert list(raw) == ["embedding", "ve_embedding", "prompt_feat", "prompt_token", "prompt_token_len"]
+    assert raw["embedding"].dtype == np.float32 and raw["embedding"].shape == (1, 192) and raw["prompt_token"].dtype == np.int64
+    back = vp.load_voice_profile(p)
+    assert torch.equal(back.embedding, torch.from_numpy(emb)) and torch.equal(back.ve_embedding, torch.from_numpy(ve))
+    assert torch.equal(back.prompt_feat, torch.from_numpy(feat)) and back.prompt_feat_len is None
+    assert torch.equal(back.prompt_token, torch.from_numpy(tok)) and torch.equal(back.prompt_token_len, torch.from_numpy(tok_len))
+    # VoiceProfile.save / .load (no ve_embedding key: the "old format" branch of vc.py:697-700)
+    p2 = str(tmp_path / "plain.npy")
+    vp.VoiceProfile(torch.from_numpy(emb)).save(p2)
+    assert list(np.load(p2, allow_pickle=True).item()) == ["embedding"]
+    old = vp.load_voice_profile(p2)
+    assert old.ve_embedding is None and old.prompt_feat is None and old.prompt_token is None
+    assert torch.equal(vp.VoiceProfile.load(p2).embedding, torch.from_numpy(emb))
+
+
+def test_load_audio_like_librosa_load(tmp_path):
+    from scipy.io import wavfile
+    from chatterbox_embed_b200 import voice_profile as vp
+    rng = np.random.RandomState(1)
+    pcm = rng.randint(-32768, 32767, (1000, 2)).astype(np.int16)
+    p = str(tmp_path / "a.wav")
+    wavfile.write(p, 22050, pcm)
+    y, sr = vp.load_audio(p)
+    assert sr == 22050 and y.dtype == np.float32 and y.shape == (1000,)
+    assert np.array_equal(y, (pcm.astype(np.float32) / 32768.0).mean(axis=1))         # soundfile scaling + librosa to_mono

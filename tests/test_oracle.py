@@ -179,3 +179,17 @@ def test_prompt_mel_basis_is_two_sparse():
     assert B.shape == (80, 961) and (B != 0).sum(0).max() == 2
     used = np.flatnonzero((B != 0).any(0))
     assert used[0] == 1 and used[-1] == 639
+
+
+# ---- S3Tokenizer front-end (s3tokenizer/s3tokenizer.py:52-74, 128-168) ------------------------------------------------------
+def test_s3_log_mel_oracle_vs_reference_fixture(golden_dir):
+    g = _load(golden_dir, "ref_s3_log_mel.npz")
+    for i, w in enumerate(make_golden.s3_wavs()):
+        ref = g[f"mel_{i}"]
+        assert ref.shape == (128, len(w) // 160)
+        assert np.abs(frontend.s3_log_mel_torch(w) - ref).max() < 1e-5           # the reference's own torch ops
+        assert np.abs(frontend.s3_log_mel_numpy(w) - ref).max() < 2e-4           # float64 DFT; the reference's fp32 FFT is ~6e-5 away
+    B = frontend.s3_mel_basis()
+    assert B.shape == (128, 201) and (B != 0).sum(0).max() == 2                  # what the kernel's 2-sparse epilogue relies on
+    used = np.flatnonzero((B != 0).any(0))
+    assert used[0] == 1 and used[-1] == 199
