@@ -1,5 +1,7 @@
 // Host side of the tcgen05 GEMM engine: tensor-map encoding (driver entry point fetched through the runtime, so the
 // library has no link-time dependency on libcuda) and the raw GEMM entry points used by the kernel unit tests.
+#include <vector>
+
 #include "tc.cuh"
 #include "epi.cuh"
 
@@ -51,6 +53,10 @@ CUtensorMap make_map_2d(const float* base, int64_t rows, int64_t cols, int64_t l
 
 using namespace cbx;
 
+// same functor under a type of this translation unit: the kernel template is then instantiated HERE (next to the trace pointer
+// this file sets) instead of being merged with xv.cu's instantiation
+namespace { struct EpiSegsumProbe : tc::EpiBiasReluMaskSegsum {}; }
+
 extern "C" int cbx_test_tgemm(cbx_ctx* c, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
                               int M, int N, int K, const float* bias, const float* pro_a, const float* pro_b, int variant,
                               int shift1, void* stream) {
@@ -75,6 +81,29 @@ extern "C" int cbx_test_tgemm(cbx_ctx* c, const float* A, int64_t lda, const flo
   } else if (variant == 2) {
     CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 32, true);
     tc::tgemm<32, 4>(c->launches, st, "test_tgemm_n32", tmA, tmB, M, N, K, tap, 1, tc::NoPrologue{}, epi);
+  } else if (variant == 6) {    // set / clear the timeline probe of the pre-activation GEMM: C = trace buffer (8 x u64 per CTA) or NULL
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(C);
+    CBX_CUDA_OK(c, cudaMemcpyToSymbol(tc::g_gemm_trace, &p, sizeof(p)));
+  } else if (variant == 7) {    // the bottleneck layer's production epilogue (bias + ReLU + mask + segment sums, TMA-stored C)
+    static int32_t* row_seg = nullptr; static float* seg_sum = nullptr; static int cap = 0;
+    if (cap < M) {
+      cudaFree(row_seg); cudaFree(seg_sum);
+      std::vector<int32_t> h(M);
+      for (int i = 0; i < M; ++i) h[i] = (i % 501 == 500) ? -1 : (i / 501) * 5 + (i % 501) / 100;     // 500-frame clips, one guard row, 100-frame segments
+      CBX_CUDA_OK(c, cudaMalloc((void**)&row_seg, sizeof(int32_t) * M));
+      CBX_CUDA_OK(c, cudaMalloc((void**)&seg_sum, sizeof(float) * 128 * (size_t)(M / 100 + 8)));
+      CBX_CUDA_OK(c, cudaMemcpy(row_seg, h.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice));
+      cap = M;
+    }
+    CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 128, true);
+    tc::tgemm_bnrelu<128, 3>(c->launches, st, "test_tgemm_bnrelu", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K,
+                             EpiSegsumProbe{{nullptr, (int)ldc, bias, row_seg, seg_sum, M}});
+  } else if (variant == 4) {    // pre-activation GEMM (register producers), single CTA
+    CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 128, true);
+    tc::tgemm_bnrelu<128, 3>(c->launches, st, "test_tgemm_bnrelu", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K, epi);
+  } else if (variant == 5) {    // the same as CTA pairs (cta_group::2)
+    CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 64, true);
+    tc::tgemm_bnrelu2<128, 4>(c->launches, st, "test_tgemm_bnrelu2", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K, epi);
   } else {
     c->err = "bad variant"; return CBX_ERR_ARG;
   }
