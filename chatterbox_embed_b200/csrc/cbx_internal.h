@@ -156,6 +156,7 @@ struct cbx_ctx {
   int64_t lstm_impl = 2;              // 1: DSMEM-push recurrence, 2: L2 multicast-TMA recurrence
   int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)
   int64_t gemm_pair = 0;              // 1: pre-activation GEMMs as CTA pairs (tcgen05 cta_group::2)
+  int64_t pdl = 1;                    // programmatic dependent launch along the dense-layer chain
   // buffers owned by the library (cbx_embed_host / cbx_embed_host_submit): two slots so that the host<->device copies of
   // one batch overlap the kernels of the other; the workspace is shared (kernels of both slots run on one compute stream)
   void* own_ws = nullptr; int64_t own_ws_bytes = 0;
@@ -253,7 +254,7 @@ void run_ve_forward_partials(cbx_ctx* c, const float* mels, int n, float* out, v
 void run_ve_mel_tc(cbx_ctx* c, const float* pcm, const VeChunk& ch, cudaStream_t st);
 void run_kaldi_fbank_tc(cbx_ctx* c, const float* pcm, const XvChunk& ch, cudaStream_t st);
 void run_local_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmU, const CUtensorMap& tmW, const CUtensorMap& tmOut, int M, int dil,
-                       int col0, const float* gate, const int32_t* row_seg);   // local_tc.cu
+                       int col0, const float* gate, const int32_t* row_seg, bool pdl = false);   // local_tc.cu
 int lstm_padded_slots(int n_slots);     // slots rounded up to whole 224-partial cluster tiles (lstm_tc.cu)
 void run_lstm_rec_tc2(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
                       int n_slots, cudaStream_t st);

@@ -62,6 +62,7 @@ local_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
     if (lane == 0) {
       mbar_expect_tx(wfull, W_BYTES);
       for (int kb = 0; kb < 12; ++kb) tma_load_2d(sW + kb * 4096, &tmW, wfull, kb * 32, 0);
+      pdl_wait();                   // u comes from the bottleneck GEMM, two kernels back (the weights above do not)
       int it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
@@ -105,6 +106,7 @@ local_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
     const int q = warp & 3;
     const int i = q * 32 + lane;
     float4* so = reinterpret_cast<float4*>(sOut) + i * 8;
+    pdl_wait();                     // the gate comes from the kernel in front
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int a = it & 1, pa = (it >> 1) & 1;
@@ -137,6 +139,7 @@ local_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
     }
+    pdl_trigger();                  // the last tile's store is on its way: the next layer's GEMM may start setting up
     if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   __syncthreads();
@@ -148,7 +151,7 @@ local_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
 // u [M][128] -> cat[:, col0 : col0 + 32] = conv_k3_dil(u) * gate[segment]; tmU: {128 cols, M rows} box {32, 128 + 2 dil} (tf32),
 // tmOut: {ld cols, M rows} box {32, 128} (fp32) over the concat buffer
 void run_local_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmU, const CUtensorMap& tmW, const CUtensorMap& tmOut, int M, int dil,
-                       int col0, const float* gate, const int32_t* row_seg) {
+                       int col0, const float* gate, const int32_t* row_seg, bool pdl) {
   using namespace lconv;
   if (M <= 0) return;
   static bool configured = false;
@@ -156,7 +159,7 @@ void run_local_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmU, cons
   Params p{M, dil, col0, (M + 127) / 128, gate, row_seg};
   const int grid = p.ntiles < tc::sm_count() ? p.ntiles : tc::sm_count();
   Scope sc(c->launches, st, "dense_local_gemm", 2.0 * M * kGrowth * 3 * kBnC, 4.0 * M * (kBnC + kGrowth));
-  local_conv_kernel<<<grid, 192, SMEM_BYTES, st>>>(tmU, tmW, tmOut, p);
+  tc::launch_pdl(local_conv_kernel, dim3(grid), dim3(192), SMEM_BYTES, st, pdl, tmU, tmW, tmOut, p);
 }
 
 }  // namespace cbx

@@ -121,6 +121,25 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The dense-layer chain (bottleneck GEMM -> CAM gate -> local conv, 52 times) is ~150 short dependent kernels: each one is
+// launched with programmatic stream serialization, does its set-up (barriers, TMEM, weight loads) while the previous kernel
+// drains, and calls pdl_wait() before it touches anything the previous kernels produced (or overwrites anything they read).
+// A kernel launched without the attribute sees both instructions as no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------- CTA-pair (cta_group::2) wrappers
 // Two CTAs of a cluster on the two SMs of one TPC run ONE M = 256 MMA: each holds its own 128 rows of A and HALF of the B
 // tile; the leader (cluster rank 0) issues, both tensor cores execute, each writes its 128 accumulator rows to its own TMEM.
@@ -460,6 +479,7 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
       fence_proxy_async();
       mbar_arrive(&afull[s]);
     };
+    pdl_wait();                 // X, the segment sums and C belong to the kernels before this one; the weights do not
     if (g < nkb) load(xa, g);
     for (int kb = g; kb < nkb; kb += 2 * PG) {
       if (kb + PG < nkb) load(xb, kb + PG);
@@ -469,6 +489,7 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
         produce(xb, kb + PG);
       }
     }
+    pdl_trigger();              // every CTA has its loads behind it: the next kernel may start setting up
     {
       // ===== epilogue, all eight producer warps: group g takes the 32-column chunks c = g, g + 2, ... (a warp may only read
       // TMEM lanes 32 (warp % 4) ..., which both groups cover).  The C tile leaves through the idle A / B stages and TMA
@@ -917,7 +938,7 @@ inline void pgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const fl
 
 template <int BN, int STAGES, class Epi>
 inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const float* X, int lda, const float* bn_a, const float* bn_b,
-                         const CUtensorMap& tmB, float* C, int ldc, int M, int N, int K, Epi epi) {
+                         const CUtensorMap& tmB, float* C, int ldc, int M, int N, int K, Epi epi, bool pdl = false) {
   if (M <= 0 || N <= 0) return;
   auto kern = tgemm_bnrelu_kernel<BN, STAGES, Epi>;
   constexpr int SMEM = smem_bytes(BN, STAGES);
@@ -926,7 +947,7 @@ inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const fl
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
   CUtensorMap tmC = make_map_2d(C, M, N, ldc, BM, false);
-  kern<<<grid, 320, SMEM, st>>>(X, lda, M, bn_a, bn_b, tmB, tmC, (K + BK - 1) / BK, epi);
+  launch_pdl(kern, grid, dim3(320), SMEM, st, pdl, X, lda, M, bn_a, bn_b, tmB, tmC, (K + BK - 1) / BK, epi);
 }
 
 // CTA-pair launch: tmB must have a box of BN/2 rows; grid = (pair, n tiles, row-tile pairs) -- an odd last row tile gets a CTA with no rows

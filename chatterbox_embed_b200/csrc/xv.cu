@@ -263,6 +263,8 @@ __global__ void __launch_bounds__(256) cam_gate_clip_kernel(float* __restrict__ 
   // weights -> shared memory (coalesced 16-byte loads, all in flight at once)
   for (int i = tid; i < kBnC * kCamHid / 4; i += 256) reinterpret_cast<float4*>(w1)[i] = __ldg(reinterpret_cast<const float4*>(L.wc1T) + i);
   for (int i = tid; i < kCamHid * kGrowth / 4; i += 256) reinterpret_cast<float4*>(w2)[i] = __ldg(reinterpret_cast<const float4*>(L.wc2T) + i);
+  tc::pdl_trigger();            // short kernel: the local conv behind it may set up right away
+  tc::pdl_wait();               // the segment sums come from the bottleneck GEMM in front (the weights above do not)
   float* ss = seg_sum + (size_t)cp.seg0 * kBnC;
   if (tid < kBnC) {
     float t = 0.f;
@@ -428,6 +430,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
 
   const int M = ch.td_rows;
   const bool tcm = c->mode == 1;
+  const bool pdl = c->pdl != 0 && !c->launches.prof;      // event-bracketed launches (profiling) serialise anyway
   if (tcm) {
     // stride-2 conv: view the FCM output as [fb_rows/2][640] so that output row m reads the row pairs m-1, m, m+1
     CUtensorMap tmA = tc::make_map_2d(ch.fcm_out, ch.fb_rows / 2, 2 * kFcmOut, 2 * kFcmOut, tc::BM, true);
@@ -465,18 +468,18 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
                                   tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, ch.seg_sum, M});
       else if (tcm)
         tc::tgemm_bnrelu<128, 3>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
-                                 tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, ch.seg_sum, M});
+                                 tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, ch.seg_sum, M}, pdl);
       else
         sgemm(L, st, "dense_bottleneck_gemm", M, kBnC, D.cin, BnReluA{cat, ld, D.a1, D.b1}, D.w1, D.cin, BiasReluMaskEpi{ch.u, kBnC, D.t2, ch.td_row_clip});
       if (ch.segs > 0 && tcm) {
         Scope sc(L, st, "cam_gate_kernel");
-        cam_gate_clip_kernel<<<ch.n_clips, 256, 0, st>>>(ch.seg_sum, ch.plan, D, ch.gate);
+        tc::launch_pdl(cam_gate_clip_kernel, dim3(ch.n_clips), dim3(256), 0, st, pdl, ch.seg_sum, ch.plan, D, ch.gate);
       } else if (ch.segs > 0) {
         { Scope sc(L, st, "seg_sum_kernel"); seg_sum_kernel<<<ch.segs, 128, 0, st>>>(ch.u, ch.plan, ch.seg_clip, ch.seg_sum); }
         { Scope sc(L, st, "cam_gate_kernel"); cam_gate_kernel<<<ch.segs, 128, 0, st>>>(ch.seg_sum, ch.plan, ch.seg_clip, D, ch.gate); }
       }
       if (tcm)
-        run_local_conv_tc(c, st, tm_u, W.tm_wl[li], tm_cat, M, kDil[b], D.cin, ch.gate, ch.td_row_seg);
+        run_local_conv_tc(c, st, tm_u, W.tm_wl[li], tm_cat, M, kDil[b], D.cin, ch.gate, ch.td_row_seg, pdl);
       else
         sgemm(L, st, "dense_local_gemm", M, kGrowth, 3 * kBnC, LocalConvA{ch.u, kDil[b], M}, D.wl, 3 * kBnC, GateEpi{cat, ld, D.cin, ch.gate, ch.td_row_seg});
     }
@@ -488,7 +491,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
                                 tc::EpiMask{nullptr, ldo, ch.td_row_clip, M});
     else if (tcm)
       tc::tgemm_bnrelu<128, 3>(L, st, "transit_gemm", cat, ld, T.a, T.b, W.tm_tr[b], out, ldo, M, T.cout, T.cin,
-                               tc::EpiMask{nullptr, ldo, ch.td_row_clip, M});
+                               tc::EpiMask{nullptr, ldo, ch.td_row_clip, M}, pdl);
     else
       sgemm(L, st, "transit_gemm", M, T.cout, T.cin, BnReluA{cat, ld, T.a, T.b}, T.w, T.cin, MaskEpi{out, ldo, ch.td_row_clip});
   }

@@ -28,7 +28,7 @@ def run(M, N, K, variant, lda):
         print("   bad rows", rows[:6].tolist(), "...", rows[-3:].tolist(), "n", len(rows), " bad cols", cols[:6].tolist(), "...", cols[-3:].tolist(), "n", len(cols))
         print("   got", Cc[rows[0], :4].tolist(), "want", ref[rows[0], :4].tolist())
     return Cc
-for (M, N, K) in [(256, 128, 32), (256, 128, 128), (128, 128, 64), (1000, 128, 480), (512, 256, 512), (100000, 128, 1024)]:
+for (M, N, K) in [(256, 128, 32), (256, 128, 128), (128, 128, 64), (300, 128, 96), (129, 128, 160), (1000, 128, 480), (512, 256, 512), (100000, 128, 1024)]:
     c4 = run(M, N, K, 4, 1024)
     c5 = run(M, N, K, 5, 1024)
 
