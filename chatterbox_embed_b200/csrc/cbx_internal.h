@@ -260,7 +260,7 @@ void run_lstm_rec_tc2(cbx_ctx* c, const float* xw, const int32_t* slot_row, cons
                       int n_slots, cudaStream_t st);
 void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const float* bias, const float* in, int F_in, int F_out, int sf,
                      const float* sc, int F_sc, const float* res, float* out, const int32_t* row_clip, int rows, int prows, double flops,
-                     const char* tag = "fcm_conv_gemm");   // fcm_tc.cu
+                     const char* tag = "fcm_conv_gemm", bool pdl = false);   // fcm_tc.cu
 void run_lstm_rec_tc(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
                      int n_slots, cudaStream_t st);   // lstm_tc.cu
 void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out, int32_t* status, cudaStream_t st);

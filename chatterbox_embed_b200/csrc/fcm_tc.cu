@@ -71,6 +71,7 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
     if (lane == 0) {
       mbar_expect_tx(wfull, p.ntaps * 32 * 128);
       for (int t = 0; t < p.ntaps; ++t) tma_load_2d(sW + t * 4096, &tmW, wfull, t * 32, 0);
+      pdl_wait();                   // the activations come from the convolution in front (the weights above do not)
       int it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
@@ -134,6 +135,7 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
 #pragma unroll
     for (int c = 0; c < 32; ++c) bias[c] = __ldg(p.bias + c);
     float4* so = reinterpret_cast<float4*>(sOut) + i * 8;
+    pdl_wait();                     // the output buffer may still be an input of the kernel in front
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const int a = it & 1, pa = (it >> 1) & 1;
@@ -167,6 +169,7 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
     }
+    pdl_trigger();                  // the next convolution may load its weights and set up
     if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   __syncthreads();
@@ -210,7 +213,7 @@ static CUtensorMap make_map_out(const float* base, int rows, int F, int pitch, i
 // in: [rows][F_in][32] with one pad row in front (in points at row 0, the map starts one row earlier); prows = rows of the
 // buffer including both pad rows; sf = frequency stride; sc: optional 1x1 stride-2 shortcut source [rows][2*F_out][32].
 void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const float* bias, const float* in, int F_in, int F_out, int sf,
-                     const float* sc, int F_sc, const float* res, float* out, const int32_t* row_clip, int rows, int prows, double flops, const char* tag) {
+                     const float* sc, int F_sc, const float* res, float* out, const int32_t* row_clip, int rows, int prows, double flops, const char* tag, bool pdl) {
   using namespace fcm;
   Params p{};
   const int pitch = sf == 1 ? F_out + 2 : F_out + 1;
@@ -267,7 +270,7 @@ void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const 
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
   const int grid = p.ntiles < nsm ? p.ntiles : nsm;
   Scope scp(c->launches, st, tag, flops, 128.0 * rows * (F_in + F_out + (sc ? F_out : 0) + (res ? F_out : 0)));   // in + out (+ shortcut / residual)
-  fcm_conv_kernel<<<grid, 192, smem, st>>>(tm[0], tm[1], tm[2], tmW, tmOut, tmRes, p);
+  tc::launch_pdl(fcm_conv_kernel, dim3(grid), dim3(192), smem, st, pdl, tm[0], tm[1], tm[2], tmW, tmOut, tmRes, p);
 }
 
 }  // namespace cbx

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(256) fcm_conv1_rows_kernel(const float* __rest
   __shared__ float xin[8][3][kKMels + 2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lr = blockIdx.x * 8 + warp;
+  tc::pdl_trigger();            // the first residual conv may load its weights meanwhile (this kernel itself is launched serialised)
   if (lr >= rows) return;
   const int r = row0 + lr;
   const int c = row_clip[r];
@@ -409,7 +410,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
                     const float* res, float* out) {
       if (c->mode == 1) {
         const char* tag = c->launches.prof ? kConvTags[conv_idx++ % 9] : "fcm_conv_gemm";
-        run_fcm_conv_tc(c, st, tmw, w.bias, in, F_in, F_out, sf, sc, F_sc, res, out, rc, rows, ch.fcm_rows + 2, 2.0 * rows * F_out * kFcmC * w.K, tag);
+        run_fcm_conv_tc(c, st, tmw, w.bias, in, F_in, F_out, sf, sc, F_sc, res, out, rc, rows, ch.fcm_rows + 2, 2.0 * rows * F_out * kFcmC * w.K, tag, c->pdl != 0 && !c->launches.prof);
       } else {
         sgemm(L, st, "fcm_conv_gemm", rows * F_out, kFcmC, w.K, FcmConvA{in, F_in, F_out, sf, sc, F_sc}, w.w, w.K, FcmEpi{out, w.bias, res, rc, F_out});
       }
