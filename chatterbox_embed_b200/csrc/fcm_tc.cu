@@ -10,7 +10,9 @@
 // the stride disappears into the TMA coordinates; a residual block's 1x1 stride-2 shortcut conv is a tenth tap on its own
 // plane.  Weights ([32][taps*32], BN folded) stay resident in shared memory for the CTA's lifetime; the fp32 accumulator
 // [128 x 32] is double-buffered in TMEM so the epilogue (bias, residual, ReLU, guard-row mask, 128-byte stores) of one tile
-// overlaps the MMAs of the next.
+// overlaps the MMAs of the next.  The epilogue is a latency-bound dependent chain (TMEM load, residual, bias, ReLU, staging,
+// barrier, TMA store: ~1 us per tile for one warp per SMSP), and it -- not HBM or the tensor pipe -- bounded this kernel, so
+// TWO epilogue groups of four warps work on alternate tiles, each on its own accumulator and staging buffer.
 #include "cbx_internal.h"
 #include "tc.cuh"
 
@@ -19,10 +21,10 @@ namespace fcm {
 
 using namespace tc;
 
-constexpr int STAGES = 3;
+constexpr int STAGES = 3;                         // at most; a conv whose stage is too large for three runs with two (Params::nstages)
 constexpr int MAX_TAPS = 10;
 constexpr int W_BYTES = MAX_TAPS * 32 * 128;       // 40 KB: [tap][32 out channels][32 in channels]
-constexpr int OUT_BYTES = 128 * 128;               // 16 KB
+constexpr int OUT_BYTES = 2 * 128 * 128;           // 2 x 16 KB: one output staging tile per epilogue group
 
 struct Plane { int par, f0, dr, nrows; uint32_t bytes, offset; };   // TMA box {32, 1, pitch, nrows} at (0, par, f0, row + dr)
 struct Tap { int plane, start; };                  // A rows start at row `start` of the plane
@@ -30,21 +32,21 @@ struct Params {
   int nplanes, ntaps;
   Plane plane[3];
   Tap tap[MAX_TAPS];
-  int pitch, BR, F_out, rows, row_base, ntiles, res_plane;
+  int pitch, BR, F_out, rows, row_base, ntiles, res_plane, nstages, ngroups;
   uint32_t stage_bytes;
   const float* bias; const float* res; float* out; const int32_t* row_clip;
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                 const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = smem;
-  uint8_t* sOut = smem + W_BYTES;                       // [128 positions][128 B] output staging (swizzled), one tile
-  uint8_t* sIn = sOut + OUT_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + STAGES * p.stage_bytes + 2048);
+  uint8_t* sOut = smem + W_BYTES;                       // [2][128 positions][128 B] output staging (swizzled), one tile per group
+  uint8_t* sIn = sOut + p.ngroups * (OUT_BYTES / 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + p.nstages * p.stage_bytes + 2048);
   uint64_t* full = bars;              // [STAGES]
   uint64_t* empty = bars + STAGES;    // [STAGES]
   uint64_t* tfull = empty + STAGES;   // [2] accumulator ready
@@ -74,7 +76,7 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
       pdl_wait();                   // the activations come from the convolution in front (the weights above do not)
       int it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int s = it % STAGES, ph = (it / STAGES) & 1;
+        const int s = it % p.nstages, ph = (it / p.nstages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         uint32_t bytes = 0;
         for (int q = 0; q < p.nplanes; ++q) bytes += p.plane[q].bytes;
@@ -102,7 +104,7 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
     mbar_wait(wfull, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int s = it % STAGES, ph = (it / STAGES) & 1;
+      const int s = it % p.nstages, ph = (it / p.nstages) & 1;
       const int a = it & 1, pa = (it >> 1) & 1;
       mbar_wait(&tempty[a], pa ^ 1);
       mbar_wait(&full[s], ph);
@@ -129,17 +131,20 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
     // traffic is TMA: the residual tile arrives as one more plane of the stage, the output tile leaves through a staging
     // buffer and ONE tensor store whose box is clipped by the tensor's bounds (padding positions / rows past the end).
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;                    // epilogue group = accumulator = parity of the CTA's tile counter
     const int i = q * 32 + lane;
     const int t = i / p.pitch;
     float bias[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) bias[c] = __ldg(p.bias + c);
-    float4* so = reinterpret_cast<float4*>(sOut) + i * 8;
+    uint8_t* const stage_out = sOut + grp * (128 * 128);
+    float4* so = reinterpret_cast<float4*>(stage_out) + i * 8;
+    const bool issuer = (warp == 2 || warp == 6) && lane == 0;
     pdl_wait();                     // the output buffer may still be an input of the kernel in front
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int ng = p.ngroups;       // 2, or 1 when three input stages only fit beside ONE staging tile (group 1 then idles)
+    for (int it = grp, tile = blockIdx.x + grp * gridDim.x; grp < ng && tile < p.ntiles; tile += ng * gridDim.x, it += ng) {
       const int a = it & 1, pa = (it >> 1) & 1;
-      const int s = it % STAGES;
+      const int s = it % p.nstages;
       mbar_wait(&tfull[a], pa);
       tc_fence_after();
       float v[32];
@@ -158,19 +163,20 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
       const bool live = p.row_clip[row] >= 0;
 #pragma unroll
       for (int c = 0; c < 32; ++c) v[c] = live ? fmaxf(v[c] + bias[c], 0.f) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");                      // the previous tile's store has read the staging buffer
+      // the group's previous store has read the staging buffer (its issuer waited for that before arriving here)
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
 #pragma unroll
       for (int c = 0; c < 8; ++c) so[c ^ (i & 7)] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
       fence_proxy_async();
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (warp == 2 && lane == 0) {
-        tma_store_3d(&tmOut, sOut, 0, 0, tile * p.BR);
+      if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
+      if (issuer) {
+        tma_store_3d(&tmOut, stage_out, 0, 0, tile * p.BR);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
     }
     pdl_trigger();                  // the next convolution may load its weights and set up
-    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
@@ -263,14 +269,19 @@ void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const 
   for (int q = np; q < 3; ++q) tm[q] = tm[0];
   p.nplanes = np;
   p.stage_bytes = off;
-  const int smem = W_BYTES + OUT_BYTES + STAGES * (int)off + 2048 + 1024 + 256;
-  static int configured = 0;
-  if (configured < smem) { cudaFuncSetAttribute(fcm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); configured = 220 * 1024; }
+  constexpr int kSmemMax = 227 * 1024;
+  p.nstages = STAGES; p.ngroups = 2;
+  auto need = [&]() { return W_BYTES + p.ngroups * (OUT_BYTES / 2) + p.nstages * (int)off + 2048 + 1024 + 256; };
+  if (need() > kSmemMax) p.ngroups = 1;             // the stride-2 convs of layer 1: two 26 KB parity planes per stage
+  if (need() > kSmemMax) p.nstages = 2;
+  const int smem = need();
+  static bool configured = false;
+  if (!configured) { cudaFuncSetAttribute(fcm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax); configured = true; }
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
   const int grid = p.ntiles < nsm ? p.ntiles : nsm;
   Scope scp(c->launches, st, tag, flops, 128.0 * rows * (F_in + F_out + (sc ? F_out : 0) + (res ? F_out : 0)));   // in + out (+ shortcut / residual)
-  tc::launch_pdl(fcm_conv_kernel, dim3(grid), dim3(192), smem, st, pdl, tm[0], tm[1], tm[2], tmW, tmOut, tmRes, p);
+  tc::launch_pdl(fcm_conv_kernel, dim3(grid), dim3(320), smem, st, pdl, tm[0], tm[1], tm[2], tmW, tmOut, tmRes, p);
 }
 
 }  // namespace cbx

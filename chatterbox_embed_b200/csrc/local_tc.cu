@@ -19,7 +19,7 @@ constexpr int STAGES = 2;
 constexpr int PLANE_BYTES = 17 * 1024;            // (128 + 2*2) rows x 128 B rounded up to the 1 KB swizzle atom
 constexpr int STAGE_BYTES = 4 * PLANE_BYTES;
 constexpr int W_BYTES = 12 * 4096;                // [tap][k block][32 x 128 B]
-constexpr int OUT_BYTES = 128 * 128;
+constexpr int OUT_BYTES = 2 * 128 * 128;          // one staging tile per epilogue group
 constexpr int SMEM_BYTES = W_BYTES + OUT_BYTES + STAGES * STAGE_BYTES + 1024 + 256;
 
 struct Params {
@@ -27,7 +27,7 @@ struct Params {
   const float* gate; const int32_t* row_seg;
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 local_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
                   const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -103,13 +103,16 @@ local_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
       __syncwarp();
     }
   } else {
+    // two epilogue groups of four warps on alternate tiles (group = accumulator): the epilogue is a latency-bound chain
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int i = q * 32 + lane;
-    float4* so = reinterpret_cast<float4*>(sOut) + i * 8;
+    uint8_t* const stage_out = sOut + grp * (128 * 128);
+    float4* so = reinterpret_cast<float4*>(stage_out) + i * 8;
+    const bool issuer = (warp == 2 || warp == 6) && lane == 0;
     pdl_wait();                     // the gate comes from the kernel in front
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int a = it & 1, pa = (it >> 1) & 1;
+    for (int it = grp, tile = blockIdx.x + grp * gridDim.x; tile < p.ntiles; tile += 2 * gridDim.x, it += 2) {
+      const int a = grp, pa = (it >> 1) & 1;
       mbar_wait(&tfull[a], pa);
       tc_fence_after();
       float v[32];
@@ -128,19 +131,20 @@ local_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
         v[4 * c + 2] = seg >= 0 ? v[4 * c + 2] * gg.z : 0.f;
         v[4 * c + 3] = seg >= 0 ? v[4 * c + 3] * gg.w : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");                      // the previous tile's store has read the staging tile
+      // the group's previous store has read the staging tile
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
 #pragma unroll
       for (int c = 0; c < 8; ++c) so[c ^ (i & 7)] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
       fence_proxy_async();
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (warp == 2 && lane == 0) {
-        tma_store_2d(&tmOut, sOut, p.col0, tile * 128);
+      if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 4, 128;" ::: "memory");
+      if (issuer) {
+        tma_store_2d(&tmOut, stage_out, p.col0, tile * 128);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
     }
     pdl_trigger();                  // the last tile's store is on its way: the next layer's GEMM may start setting up
-    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
@@ -159,7 +163,7 @@ void run_local_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmU, cons
   Params p{M, dil, col0, (M + 127) / 128, gate, row_seg};
   const int grid = p.ntiles < tc::sm_count() ? p.ntiles : tc::sm_count();
   Scope sc(c->launches, st, "dense_local_gemm", 2.0 * M * kGrowth * 3 * kBnC, 4.0 * M * (kBnC + kGrowth));
-  tc::launch_pdl(local_conv_kernel, dim3(grid), dim3(192), SMEM_BYTES, st, pdl, tmU, tmW, tmOut, p);
+  tc::launch_pdl(local_conv_kernel, dim3(grid), dim3(320), SMEM_BYTES, st, pdl, tmU, tmW, tmOut, p);
 }
 
 }  // namespace cbx
