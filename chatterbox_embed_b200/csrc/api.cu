@@ -105,13 +105,15 @@ XvChunk carve_xv(Carver& cv, const XvLayout& L, cbx_ctx* c) {
   ch.b2 = cv.take<float>(pr * 40 * kFcmC);
   ch.b4 = cv.take<float>(pr * 20 * kFcmC);
   ch.b5 = cv.take<float>(pr * 20 * kFcmC);
+  ch.b3 = cv.take<float>(pr * 40 * kFcmC);
+  ch.b6 = cv.take<float>(pr * 20 * kFcmC);
   ch.fcm_out = cv.take<float>((int64_t)L.fb_rows * kFcmOut);
   ch.cat1 = cv.take<float>((int64_t)L.td_rows * 512);
   ch.cat2 = cv.take<float>((int64_t)L.td_rows * 1024);
   ch.cat3 = cv.take<float>((int64_t)L.td_rows * 1024);
   ch.u = cv.take<float>((int64_t)L.td_rows * kBnC);
   ch.tr3 = cv.take<float>((int64_t)L.td_rows * kStatsC);
-  ch.seg_sum = cv.take<float>((int64_t)std::max(L.segs, 1) * kBnC);
+  ch.seg_sum = cv.take<float>((int64_t)std::max(L.segs, 1) * kBnC * 2);      // fp32 in the strict mode, 64-bit fixed point in the tensor-core mode
   ch.gate = cv.take<float>((int64_t)std::max(L.segs, 1) * kGrowth);
   ch.stats = cv.take<float>((int64_t)ch.n_clips * 2 * kStatsC);
   if (cv.base && c) {
@@ -121,6 +123,14 @@ XvChunk carve_xv(Carver& cv, const XvLayout& L, cbx_ctx* c) {
     tap("xv_fbank", ch.fbank, L.fb_rows, kKMels, kKMels);
     tap("xv_cmn_mean", ch.cmn_sum, ch.n_clips, kKMels, kKMels);
     tap("xv_fcm", ch.fcm_out, L.fb_rows, kFcmOut, kFcmOut);
+    // FCM sub-chunk buffers (state after the LAST sub-chunk; one pad row in front): conv1 out, layer-1 / layer-2 ping-pong
+    tap("xv_fcm_b0", ch.b0, pr, 80 * kFcmC, 80 * kFcmC);
+    tap("xv_fcm_b1", ch.b1, pr, 40 * kFcmC, 40 * kFcmC);
+    tap("xv_fcm_b2", ch.b2, pr, 40 * kFcmC, 40 * kFcmC);
+    tap("xv_fcm_b4", ch.b4, pr, 20 * kFcmC, 20 * kFcmC);
+    tap("xv_fcm_b5", ch.b5, pr, 20 * kFcmC, 20 * kFcmC);
+    tap("xv_fcm_b3", ch.b3, pr, 40 * kFcmC, 40 * kFcmC);
+    tap("xv_fcm_b6", ch.b6, pr, 20 * kFcmC, 20 * kFcmC);
     tap("xv_cat1", ch.cat1, L.td_rows, 512, 512);
     tap("xv_cat2", ch.cat2, L.td_rows, 1024, 1024);
     tap("xv_cat3", ch.cat3, L.td_rows, 1024, 1024);

@@ -235,12 +235,12 @@ struct XvChunk {
   float* spec;              // [fcm_rows][514]   (sub-chunk)
   float* fbank;             // [fb_rows][80]
   float* cmn_sum;           // [n_clips][80]
-  float *b0, *b1, *b2, *b4, *b5;   // FCM activations of one sub-chunk
+  float *b0, *b1, *b2, *b3, *b4, *b5, *b6;   // FCM activations of one sub-chunk
   float* fcm_out;           // [fb_rows][320]
   float *cat1, *cat2, *cat3;   // [td_rows][512|1024|1024]
   float* u;                 // [td_rows][128]
   float* tr3;               // [td_rows][512]
-  float* seg_sum;           // [segs][128]
+  float* seg_sum;           // [segs][128] fp32 (strict mode) or 64-bit fixed point (tensor-core mode: 2 floats per entry)
   float* gate;              // [segs][32]
   float* stats;             // [n_clips][1024]
 };

@@ -8,7 +8,8 @@
 // of nine times.  The GEMM's M index therefore runs over (t, f') with f' in [0, F+2): the two extra positions per time row
 // are computed and dropped.  Frequency-stride-2 convs read two parity planes ({32, parity, F/2, rows} view of the tensor) so
 // the stride disappears into the TMA coordinates; a residual block's 1x1 stride-2 shortcut conv is a tenth tap on its own
-// plane.  Weights ([32][taps*32], BN folded) stay resident in shared memory for the CTA's lifetime; the fp32 accumulator
+// plane.  An identity residual is read by the epilogue threads straight from global memory (one coalesced 128-byte row per
+// position, issued before the accumulator wait).  Weights ([32][taps*32], BN folded) stay resident in shared memory for the CTA's lifetime; the fp32 accumulator
 // [128 x 32] is double-buffered in TMEM so the epilogue (bias, residual, ReLU, guard-row mask, 128-byte stores) of one tile
 // overlaps the MMAs of the next.  The epilogue is a latency-bound dependent chain (TMEM load, residual, bias, ReLU, staging,
 // barrier, TMA store: ~1 us per tile for one warp per SMSP), and it -- not HBM or the tensor pipe -- bounded this kernel, so
@@ -32,15 +33,14 @@ struct Params {
   int nplanes, ntaps;
   Plane plane[3];
   Tap tap[MAX_TAPS];
-  int pitch, BR, F_out, rows, row_base, ntiles, res_plane, nstages, ngroups;
+  int pitch, BR, F_out, rows, row_base, ntiles, nstages, ngroups;
   uint32_t stage_bytes;
   const float* bias; const float* res; float* out; const int32_t* row_clip;
 };
 
 __global__ void __launch_bounds__(320, 1)
 fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
-                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
-                const __grid_constant__ Params p) {
+                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = smem;
@@ -57,8 +57,7 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm0); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmOut);
-    // a stage is free when its MMAs have completed and, if it carries a residual plane, the 4 epilogue warps have read it
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], p.res_plane >= 0 ? 5 : 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }     // a stage is free when its MMAs have completed
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     mbar_init(wfull, 1);
     fence_barrier_init();
@@ -85,8 +84,7 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
         for (int q = 0; q < p.nplanes; ++q) {
           const Plane& pl = p.plane[q];
           const CUtensorMap* tm = q == 0 ? &tm0 : (q == 1 ? &tm1 : &tm2);
-          if (q == p.res_plane) tma_load_3d(sIn + s * p.stage_bytes + pl.offset, &tmRes, &full[s], 0, 0, tile * p.BR);
-          else tma_load_4d(sIn + s * p.stage_bytes + pl.offset, tm, &full[s], 0, pl.par, pl.f0, r0 + pl.dr);
+          tma_load_4d(sIn + s * p.stage_bytes + pl.offset, tm, &full[s], 0, pl.par, pl.f0, r0 + pl.dr);
         }
       }
     }
@@ -127,9 +125,10 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
       __syncwarp();
     }
   } else {
-    // ===== epilogue: thread = output position i = (t, f') of the tile (f' >= F_out are the padding positions).  All global
-    // traffic is TMA: the residual tile arrives as one more plane of the stage, the output tile leaves through a staging
-    // buffer and ONE tensor store whose box is clipped by the tensor's bounds (padding positions / rows past the end).
+    // ===== epilogue: thread = output position i = (t, f') of the tile (f' >= F_out are the padding positions).  The output
+    // tile leaves through a staging buffer and ONE tensor store whose box is clipped by the tensor's bounds (padding
+    // positions / rows past the end).  (An earlier version brought the residual tile in as one more TMA plane of the input
+    // stage; its results were not reproducible from run to run -- tools/determinism.py -- and the direct loads are no slower.)
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;                    // epilogue group = accumulator = parity of the CTA's tile counter
     const int i = q * 32 + lane;
@@ -144,7 +143,14 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
     const int ng = p.ngroups;       // 2, or 1 when three input stages only fit beside ONE staging tile (group 1 then idles)
     for (int it = grp, tile = blockIdx.x + grp * gridDim.x; grp < ng && tile < p.ntiles; tile += ng * gridDim.x, it += ng) {
       const int a = it & 1, pa = (it >> 1) & 1;
-      const int s = it % p.nstages;
+      float4 resv[8];
+      const int fr = i - t * p.pitch;
+      const bool has_res = p.res != nullptr && fr < p.F_out && t < p.BR && tile * p.BR + t < p.rows;
+      if (has_res) {                                        // in flight while the tile's MMAs finish
+        const float4* rr = reinterpret_cast<const float4*>(p.res + ((size_t)(tile * p.BR + t) * p.F_out + fr) * 32);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) resv[c] = __ldg(rr + c);
+      }
       mbar_wait(&tfull[a], pa);
       tc_fence_after();
       float v[32];
@@ -152,12 +158,9 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[a]);
-      if (p.res_plane >= 0) {
-        const float4* rr = reinterpret_cast<const float4*>(sIn + s * p.stage_bytes + p.plane[p.res_plane].offset) + i * 8;
+      if (has_res) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { const float4 x = rr[c ^ (i & 7)]; v[4 * c] += x.x; v[4 * c + 1] += x.y; v[4 * c + 2] += x.z; v[4 * c + 3] += x.w; }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        for (int c = 0; c < 8; ++c) { v[4 * c] += resv[c].x; v[4 * c + 1] += resv[c].y; v[4 * c + 2] += resv[c].z; v[4 * c + 3] += resv[c].w; }
       }
       const int row = min(tile * p.BR + t, p.rows - 1);
       const bool live = p.row_clip[row] >= 0;
@@ -258,14 +261,7 @@ void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const 
     p.tap[9] = Tap{np, 0};
     p.ntaps = 10; ++np;
   }
-  p.res_plane = -1;
-  CUtensorMap tmOut = make_map_out(out, rows, F_out, pitch, BR), tmRes = tmOut;
-  if (res) {
-    p.plane[np] = Plane{0, 0, 0, BR, plane_bytes(BR), off};
-    tmRes = make_map_out(res, rows, F_out, pitch, BR);
-    off += align1k(p.plane[np].bytes);
-    p.res_plane = np; ++np;
-  }
+  CUtensorMap tmOut = make_map_out(out, rows, F_out, pitch, BR);
   for (int q = np; q < 3; ++q) tm[q] = tm[0];
   p.nplanes = np;
   p.stage_bytes = off;
@@ -281,7 +277,7 @@ void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const 
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
   const int grid = p.ntiles < nsm ? p.ntiles : nsm;
   Scope scp(c->launches, st, tag, flops, 128.0 * rows * (F_in + F_out + (sc ? F_out : 0) + (res ? F_out : 0)));   // in + out (+ shortcut / residual)
-  tc::launch_pdl(fcm_conv_kernel, dim3(grid), dim3(320), smem, st, pdl, tm[0], tm[1], tm[2], tmW, tmOut, tmRes, p);
+  tc::launch_pdl(fcm_conv_kernel, dim3(grid), dim3(320), smem, st, pdl, tm[0], tm[1], tm[2], tmW, tmOut, p);
 }
 
 }  // namespace cbx

@@ -85,13 +85,13 @@ extern "C" int cbx_test_tgemm(cbx_ctx* c, const float* A, int64_t lda, const flo
     unsigned long long* p = reinterpret_cast<unsigned long long*>(C);
     CBX_CUDA_OK(c, cudaMemcpyToSymbol(tc::g_gemm_trace, &p, sizeof(p)));
   } else if (variant == 7) {    // the bottleneck layer's production epilogue (bias + ReLU + mask + segment sums, TMA-stored C)
-    static int32_t* row_seg = nullptr; static float* seg_sum = nullptr; static int cap = 0;
+    static int32_t* row_seg = nullptr; static unsigned long long* seg_sum = nullptr; static int cap = 0;
     if (cap < M) {
       cudaFree(row_seg); cudaFree(seg_sum);
       std::vector<int32_t> h(M);
       for (int i = 0; i < M; ++i) h[i] = (i % 501 == 500) ? -1 : (i / 501) * 5 + (i % 501) / 100;     // 500-frame clips, one guard row, 100-frame segments
       CBX_CUDA_OK(c, cudaMalloc((void**)&row_seg, sizeof(int32_t) * M));
-      CBX_CUDA_OK(c, cudaMalloc((void**)&seg_sum, sizeof(float) * 128 * (size_t)(M / 100 + 8)));
+      CBX_CUDA_OK(c, cudaMalloc((void**)&seg_sum, sizeof(unsigned long long) * 128 * (size_t)(M / 100 + 8)));
       CBX_CUDA_OK(c, cudaMemcpy(row_seg, h.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice));
       cap = M;
     }
@@ -101,6 +101,12 @@ extern "C" int cbx_test_tgemm(cbx_ctx* c, const float* A, int64_t lda, const flo
   } else if (variant == 4) {    // pre-activation GEMM (register producers), single CTA
     CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 128, true);
     tc::tgemm_bnrelu<128, 3>(c->launches, st, "test_tgemm_bnrelu", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K, epi);
+  } else if (variant == 9) {    // EXPERIMENT: two stages instead of three
+    CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 128, true);
+    tc::tgemm_bnrelu<128, 2>(c->launches, st, "test_tgemm_bnrelu_s2", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K, epi);
+  } else if (variant == 10) {   // EXPERIMENT: one stage
+    CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 128, true);
+    tc::tgemm_bnrelu<128, 1>(c->launches, st, "test_tgemm_bnrelu_s1", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K, epi);
   } else if (variant == 5) {    // the same as CTA pairs (cta_group::2)
     CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 64, true);
     tc::tgemm_bnrelu2<128, 4>(c->launches, st, "test_tgemm_bnrelu2", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K, epi);

@@ -251,8 +251,8 @@ __global__ void __launch_bounds__(128) cam_gate_kernel(const float* __restrict__
 constexpr int kMaxSegsSm = 8;      // segments per pass of the gate kernel
 // Gate from the segment sums the bottleneck epilogue accumulated (tensor-core mode), one CTA per clip; the sums are zeroed
 // after use so the next layer's epilogue can accumulate into the same buffer.
-__global__ void __launch_bounds__(256) cam_gate_clip_kernel(float* __restrict__ seg_sum, const ClipPlan* __restrict__ plan, DenseLayerW L,
-                                                            float* __restrict__ gate) {
+__global__ void __launch_bounds__(256) cam_gate_clip_kernel(unsigned long long* __restrict__ seg_sum, const ClipPlan* __restrict__ plan,
+                                                            DenseLayerW L, float* __restrict__ gate) {
   __shared__ float w1[kBnC * kCamHid];        // [128][64] transposed
   __shared__ float w2[kCamHid * kGrowth];     // [64][32] transposed
   __shared__ float ctx[kMaxSegsSm][kBnC];
@@ -266,10 +266,11 @@ __global__ void __launch_bounds__(256) cam_gate_clip_kernel(float* __restrict__ 
   for (int i = tid; i < kCamHid * kGrowth / 4; i += 256) reinterpret_cast<float4*>(w2)[i] = __ldg(reinterpret_cast<const float4*>(L.wc2T) + i);
   tc::pdl_trigger();            // short kernel: the local conv behind it may set up right away
   tc::pdl_wait();               // the segment sums come from the bottleneck GEMM in front (the weights above do not)
-  float* ss = seg_sum + (size_t)cp.seg0 * kBnC;
+  unsigned long long* ss = seg_sum + (size_t)cp.seg0 * kBnC;      // 40.24 fixed point (EpiBiasReluMaskSegsum)
+  auto seg_val = [&](int s, int ch) { return (float)((double)(long long)ss[(size_t)s * kBnC + ch] * (1.0 / (double)tc::kSegFix)); };
   if (tid < kBnC) {
     float t = 0.f;
-    for (int s = 0; s < S; ++s) t += ss[(size_t)s * kBnC + tid];
+    for (int s = 0; s < S; ++s) t += seg_val(s, tid);
     tot[tid] = t / (float)T;
   }
   __syncthreads();
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(256) cam_gate_clip_kernel(float* __restrict__ 
     for (int o = tid; o < ns * kBnC; o += 256) {
       const int s = o >> 7, ch = o & 127;
       const int len = min(kSegLen, T - (s0 + s) * kSegLen);
-      ctx[s][ch] = tot[ch] + ss[(size_t)(s0 + s) * kBnC + ch] / (float)len;
+      ctx[s][ch] = tot[ch] + seg_val(s0 + s, ch) / (float)len;
     }
     __syncthreads();
     for (int o = tid; o < ns * kCamHid; o += 256) {
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(256) cam_gate_clip_kernel(float* __restrict__ 
     }
     __syncthreads();
   }
-  for (int o = tid; o < S * kBnC; o += 256) ss[o] = 0.f;
+  for (int o = tid; o < S * kBnC; o += 256) ss[o] = 0ull;
 }
 
 struct LocalConvA {   // Conv1d(128->32, k3, dilation d, zero pad d): k = tap*128 + c
@@ -397,6 +398,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     // every sub-chunk buffer has one pad row in front (index -1 is readable)
     float* b0 = ch.b0 + 80 * kFcmC; float* b1 = ch.b1 + 40 * kFcmC; float* b2 = ch.b2 + 40 * kFcmC;
     float* b4 = ch.b4 + 20 * kFcmC; float* b5 = ch.b5 + 20 * kFcmC;
+    float* b3 = ch.b3 + 40 * kFcmC; float* b6 = ch.b6 + 20 * kFcmC;
     {
       const long long npos = (long long)rows * kKMels;
       if (c->mode == 1) { Scope sc(L, st, "fcm_conv1_kernel"); fcm_conv1_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ch.fbank, ch.cmn_sum, ch.fb_row_clip, W.conv1_w, W.conv1_b, b0, s.r0, rows, ch.fb_rows); }
@@ -419,14 +421,14 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     conv(W.res[0][0][0], W.tm_res[0][0][0], b0, 80, 40, 2, nullptr, 0, nullptr, b1);
     conv(W.res[0][0][1], W.tm_res[0][0][1], b1, 40, 40, 1, b0, 80, nullptr, b2);
     conv(W.res[0][1][0], W.tm_res[0][1][0], b2, 40, 40, 1, nullptr, 0, nullptr, b1);
-    conv(W.res[0][1][1], W.tm_res[0][1][1], b1, 40, 40, 1, nullptr, 0, b2, b2);
+    conv(W.res[0][1][1], W.tm_res[0][1][1], b1, 40, 40, 1, nullptr, 0, b2, b3);
     // layer2: 40 -> 20
-    conv(W.res[1][0][0], W.tm_res[1][0][0], b2, 40, 20, 2, nullptr, 0, nullptr, b4);
-    conv(W.res[1][0][1], W.tm_res[1][0][1], b4, 20, 20, 1, b2, 40, nullptr, b5);
+    conv(W.res[1][0][0], W.tm_res[1][0][0], b3, 40, 20, 2, nullptr, 0, nullptr, b4);
+    conv(W.res[1][0][1], W.tm_res[1][0][1], b4, 20, 20, 1, b3, 40, nullptr, b5);
     conv(W.res[1][1][0], W.tm_res[1][1][0], b5, 20, 20, 1, nullptr, 0, nullptr, b4);
-    conv(W.res[1][1][1], W.tm_res[1][1][1], b4, 20, 20, 1, nullptr, 0, b5, b5);
+    conv(W.res[1][1][1], W.tm_res[1][1][1], b4, 20, 20, 1, nullptr, 0, b5, b6);
     // head.conv2: 20 -> 10, written straight into the chunk-level [row][f*32+c] buffer
-    conv(W.head_conv2, W.tm_head2, b5, 20, 10, 2, nullptr, 0, nullptr, ch.fcm_out + (size_t)s.r0 * kFcmOut);
+    conv(W.head_conv2, W.tm_head2, b6, 20, 10, 2, nullptr, 0, nullptr, ch.fcm_out + (size_t)s.r0 * kFcmOut);
   }
 
   const int M = ch.td_rows;
@@ -445,7 +447,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     sgemm(L, st, "tdnn_gemm", M, kTdnnC, W.tdnn.K, TdnnA{ch.fcm_out, ch.fb_rows}, W.tdnn.w, W.tdnn.K, BiasReluMaskEpi{ch.cat1, 512, W.tdnn.bias, ch.td_row_clip});
   }
 
-  if (tcm && ch.segs > 0) cudaMemsetAsync(ch.seg_sum, 0, sizeof(float) * (size_t)ch.segs * kBnC, st);
+  if (tcm && ch.segs > 0) cudaMemsetAsync(ch.seg_sum, 0, sizeof(unsigned long long) * (size_t)ch.segs * kBnC, st);
   static const int kLayers[3] = {12, 24, 16};
   static const int kDil[3] = {1, 2, 2};
   float* cats[3] = {ch.cat1, ch.cat2, ch.cat3};
@@ -466,15 +468,15 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
       const DenseLayerW& D = W.dense[li];
       if (tcm && c->gemm_pair)
         tc::tgemm_bnrelu2<128, 4>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1h[li], ch.u, kBnC, M, kBnC, D.cin,
-                                  tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, ch.seg_sum, M});
+                                  tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M});
       else if (tcm)
         tc::tgemm_bnrelu<128, 3>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
-                                 tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, ch.seg_sum, M}, pdl);
+                                 tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
       else
         sgemm(L, st, "dense_bottleneck_gemm", M, kBnC, D.cin, BnReluA{cat, ld, D.a1, D.b1}, D.w1, D.cin, BiasReluMaskEpi{ch.u, kBnC, D.t2, ch.td_row_clip});
       if (ch.segs > 0 && tcm) {
         Scope sc(L, st, "cam_gate_kernel");
-        tc::launch_pdl(cam_gate_clip_kernel, dim3(ch.n_clips), dim3(256), 0, st, pdl, ch.seg_sum, ch.plan, D, ch.gate);
+        tc::launch_pdl(cam_gate_clip_kernel, dim3(ch.n_clips), dim3(256), 0, st, pdl, reinterpret_cast<unsigned long long*>(ch.seg_sum), ch.plan, D, ch.gate);
       } else if (ch.segs > 0) {
         { Scope sc(L, st, "seg_sum_kernel"); seg_sum_kernel<<<ch.segs, 128, 0, st>>>(ch.u, ch.plan, ch.seg_clip, ch.seg_sum); }
         { Scope sc(L, st, "cam_gate_kernel"); cam_gate_kernel<<<ch.segs, 128, 0, st>>>(ch.seg_sum, ch.plan, ch.seg_clip, D, ch.gate); }
