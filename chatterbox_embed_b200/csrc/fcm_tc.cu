@@ -141,16 +141,25 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
     const bool issuer = (warp == 2 || warp == 6) && lane == 0;
     pdl_wait();                     // the output buffer may still be an input of the kernel in front
     const int ng = p.ngroups;       // 2, or 1 when three input stages only fit beside ONE staging tile (group 1 then idles)
+    // residual of this thread's position, fetched one tile ahead (in flight during the previous tile's epilogue)
+    float4 resn[8];
+    const int fr = i - t * p.pitch;
+    auto res_valid = [&](int tile) { return p.res != nullptr && fr < p.F_out && t < p.BR && tile < p.ntiles && tile * p.BR + t < p.rows; };
+    auto res_fetch = [&](int tile) {
+      if (res_valid(tile)) {
+        const float4* rr = reinterpret_cast<const float4*>(p.res + ((size_t)(tile * p.BR + t) * p.F_out + fr) * 32);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) resn[c] = __ldg(rr + c);
+      }
+    };
+    if (grp < ng) res_fetch(blockIdx.x + grp * gridDim.x);
     for (int it = grp, tile = blockIdx.x + grp * gridDim.x; grp < ng && tile < p.ntiles; tile += ng * gridDim.x, it += ng) {
       const int a = it & 1, pa = (it >> 1) & 1;
       float4 resv[8];
-      const int fr = i - t * p.pitch;
-      const bool has_res = p.res != nullptr && fr < p.F_out && t < p.BR && tile * p.BR + t < p.rows;
-      if (has_res) {                                        // in flight while the tile's MMAs finish
-        const float4* rr = reinterpret_cast<const float4*>(p.res + ((size_t)(tile * p.BR + t) * p.F_out + fr) * 32);
+      const bool has_res = res_valid(tile);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) resv[c] = __ldg(rr + c);
-      }
+      for (int c = 0; c < 8; ++c) resv[c] = resn[c];
+      res_fetch(tile + ng * gridDim.x);
       mbar_wait(&tfull[a], pa);
       tc_fence_after();
       float v[32];

@@ -293,6 +293,19 @@ def test_mode1_ragged_config3(models, mode1):
         assert pl.xv_frames == 1 + (n - 400) // 160 and pl.xv_tdnn == (pl.xv_frames - 1) // 2 + 1
 
 
+def test_mode1_results_are_reproducible(models, mode1):
+    """Bit-identical embeddings from run to run, with the two encoder chains on two streams and programmatic dependent launch
+    on: no float atomics on the path (segment sums are 64-bit fixed-point reductions) and no racy staging.  An earlier build
+    read the FCM residual through a TMA plane and returned a different sample of errors every run (tools/determinism.py)."""
+    sdv, sdc, emb = _emb(models, "W1")
+    lens = [int(x) for x in synth.ragged_lengths(24)]
+    wavs = [synth.clip(i, n) for i, n in enumerate(lens)]
+    ve0, xv0 = emb.embed_wavs(wavs)
+    for _ in range(3):
+        ve, xv = emb.embed_wavs(wavs)
+        assert np.array_equal(ve, ve0) and np.array_equal(xv, xv0)
+
+
 def test_stream_api_equals_single_calls(models, mode1):
     """cbx_embed_host_submit / _wait with two batches in flight returns what the one-shot call returns, in order."""
     sdv, sdc, emb = _emb(models, "W1")
