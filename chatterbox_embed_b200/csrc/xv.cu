@@ -470,7 +470,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
         tc::tgemm_bnrelu2<128, 4>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1h[li], ch.u, kBnC, M, kBnC, D.cin,
                                   tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M});
       else if (tcm)
-        tc::tgemm_bnrelu<128, 3>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
+        tc::tgemm_bnrelu<128, 2>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
                                  tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
       else
         sgemm(L, st, "dense_bottleneck_gemm", M, kBnC, D.cin, BnReluA{cat, ld, D.a1, D.b1}, D.w1, D.cin, BiasReluMaskEpi{ch.u, kBnC, D.t2, ch.td_row_clip});
@@ -493,7 +493,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
       tc::tgemm_bnrelu2<128, 4>(L, st, "transit_gemm", cat, ld, T.a, T.b, W.tm_trh[b], out, ldo, M, T.cout, T.cin,
                                 tc::EpiMask{nullptr, ldo, ch.td_row_clip, M});
     else if (tcm)
-      tc::tgemm_bnrelu<128, 3>(L, st, "transit_gemm", cat, ld, T.a, T.b, W.tm_tr[b], out, ldo, M, T.cout, T.cin,
+      tc::tgemm_bnrelu<128, 2>(L, st, "transit_gemm", cat, ld, T.a, T.b, W.tm_tr[b], out, ldo, M, T.cout, T.cin,
                                tc::EpiMask{nullptr, ldo, ch.td_row_clip, M}, pdl);
     else
       sgemm(L, st, "transit_gemm", M, T.cout, T.cin, BnReluA{cat, ld, T.a, T.b}, T.w, T.cin, MaskEpi{out, ldo, ch.td_row_clip});
