@@ -8,8 +8,8 @@
 // of nine times.  The GEMM's M index therefore runs over (t, f') with f' in [0, F+2): the two extra positions per time row
 // are computed and dropped.  Frequency-stride-2 convs read two parity planes ({32, parity, F/2, rows} view of the tensor) so
 // the stride disappears into the TMA coordinates; a residual block's 1x1 stride-2 shortcut conv is a tenth tap on its own
-// plane.  An identity residual is read by the epilogue threads straight from global memory (one coalesced 128-byte row per
-// position, issued before the accumulator wait).  Weights ([32][taps*32], BN folded) stay resident in shared memory for the CTA's lifetime; the fp32 accumulator
+// plane.  An identity residual tile comes by its own tensor load into a buffer of the epilogue group, with its own mbarrier that
+// the epilogue threads themselves wait on.  Weights ([32][taps*32], BN folded) stay resident in shared memory for the CTA's lifetime; the fp32 accumulator
 // [128 x 32] is double-buffered in TMEM so the epilogue (bias, residual, ReLU, guard-row mask, 128-byte stores) of one tile
 // overlaps the MMAs of the next.  The epilogue is a latency-bound dependent chain (TMEM load, residual, bias, ReLU, staging,
 // barrier, TMA store: ~1 us per tile for one warp per SMSP), and it -- not HBM or the tensor pipe -- bounded this kernel, so
@@ -25,6 +25,7 @@ using namespace tc;
 constexpr int STAGES = 3;                         // at most; a conv whose stage is too large for three runs with two (Params::nstages)
 constexpr int MAX_TAPS = 10;
 constexpr int W_BYTES = MAX_TAPS * 32 * 128;       // 40 KB: [tap][32 out channels][32 in channels]
+constexpr int RES_BYTES = 128 * 128;               // one residual tile (BR rows x F_out positions x 128 B <= 16 KB)
 constexpr int OUT_BYTES = 2 * 128 * 128;           // 2 x 16 KB: one output staging tile per epilogue group
 
 struct Plane { int par, f0, dr, nrows; uint32_t bytes, offset; };   // TMA box {32, 1, pitch, nrows} at (0, par, f0, row + dr)
@@ -40,19 +41,22 @@ struct Params {
 
 __global__ void __launch_bounds__(320, 1)
 fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
-                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ Params p) {
+                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+                const __grid_constant__ Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sW = smem;
   uint8_t* sOut = smem + W_BYTES;                       // [2][128 positions][128 B] output staging (swizzled), one tile per group
   uint8_t* sIn = sOut + p.ngroups * (OUT_BYTES / 2);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + p.nstages * p.stage_bytes + 2048);
+  uint8_t* sRes = sIn + p.nstages * p.stage_bytes + 2048;       // [2 groups][2][16 KB] residual tiles (only when p.res)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRes + (p.res ? 4 * RES_BYTES : 0));
   uint64_t* full = bars;              // [STAGES]
   uint64_t* empty = bars + STAGES;    // [STAGES]
   uint64_t* tfull = empty + STAGES;   // [2] accumulator ready
   uint64_t* tempty = tfull + 2;       // [2] accumulator drained (4 warp arrivals)
   uint64_t* wfull = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  uint64_t* rfull = wfull + 1;        // [2 groups][2] residual tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -60,6 +64,7 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }     // a stage is free when its MMAs have completed
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     mbar_init(wfull, 1);
+    for (int r = 0; r < 4; ++r) mbar_init(&rfull[r], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 64);
@@ -128,7 +133,7 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
     // ===== epilogue: thread = output position i = (t, f') of the tile (f' >= F_out are the padding positions).  The output
     // tile leaves through a staging buffer and ONE tensor store whose box is clipped by the tensor's bounds (padding
     // positions / rows past the end).  (An earlier version brought the residual tile in as one more TMA plane of the input
-    // stage; its results were not reproducible from run to run -- tools/determinism.py -- and the direct loads are no slower.)
+    // stage, read after the accumulator barrier only; its results were not reproducible from run to run -- tools/determinism.py.)
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;                    // epilogue group = accumulator = parity of the CTA's tile counter
     const int i = q * 32 + lane;
@@ -141,25 +146,25 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
     const bool issuer = (warp == 2 || warp == 6) && lane == 0;
     pdl_wait();                     // the output buffer may still be an input of the kernel in front
     const int ng = p.ngroups;       // 2, or 1 when three input stages only fit beside ONE staging tile (group 1 then idles)
-    // residual of this thread's position, fetched one tile ahead (in flight during the previous tile's epilogue)
-    float4 resn[8];
+    // Identity residual: the group's issuer brings the tile's [BR][F_out][32] block in with ONE tensor load (128B swizzle,
+    // box clipped at the last row) into the group's own pair of buffers, one tile ahead, and every epilogue thread waits on
+    // that load's own mbarrier before it reads its 128-byte row.
     const int fr = i - t * p.pitch;
-    auto res_valid = [&](int tile) { return p.res != nullptr && fr < p.F_out && t < p.BR && tile < p.ntiles && tile * p.BR + t < p.rows; };
-    auto res_fetch = [&](int tile) {
-      if (res_valid(tile)) {
-        const float4* rr = reinterpret_cast<const float4*>(p.res + ((size_t)(tile * p.BR + t) * p.F_out + fr) * 32);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) resn[c] = __ldg(rr + c);
+    uint8_t* const res_buf = sRes + grp * (2 * RES_BYTES);
+    uint64_t* const res_bar = rfull + grp * 2;
+    auto res_issue = [&](int tile, int n) {              // n = ordinal of the tile within this group
+      if (p.res != nullptr && issuer && tile < p.ntiles) {
+        fence_proxy_async();                              // the buffer's previous readers are behind a named barrier
+        mbar_expect_tx(&res_bar[n & 1], (uint32_t)p.BR * (uint32_t)p.F_out * 128u);
+        tma_load_3d(res_buf + (n & 1) * RES_BYTES, &tmRes, &res_bar[n & 1], 0, 0, tile * p.BR);
       }
     };
-    if (grp < ng) res_fetch(blockIdx.x + grp * gridDim.x);
-    for (int it = grp, tile = blockIdx.x + grp * gridDim.x; grp < ng && tile < p.ntiles; tile += ng * gridDim.x, it += ng) {
+    if (grp < ng) res_issue(blockIdx.x + grp * gridDim.x, 0);
+    int nloc = 0;
+    for (int it = grp, tile = blockIdx.x + grp * gridDim.x; grp < ng && tile < p.ntiles; tile += ng * gridDim.x, it += ng, ++nloc) {
       const int a = it & 1, pa = (it >> 1) & 1;
-      float4 resv[8];
-      const bool has_res = res_valid(tile);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) resv[c] = resn[c];
-      res_fetch(tile + ng * gridDim.x);
+      const bool has_res = p.res != nullptr && fr < p.F_out && t < p.BR && tile * p.BR + t < p.rows;
+      res_issue(tile + ng * gridDim.x, nloc + 1);
       mbar_wait(&tfull[a], pa);
       tc_fence_after();
       float v[32];
@@ -167,9 +172,14 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[a]);
-      if (has_res) {
+      if (p.res != nullptr) {
+        mbar_wait(&res_bar[nloc & 1], (nloc >> 1) & 1);
+        if (has_res) {
+          const int pos = t * p.F_out + fr;               // row of the [BR * F_out][128 B] swizzled block
+          const float4* rr = reinterpret_cast<const float4*>(res_buf + (nloc & 1) * RES_BYTES) + pos * 8;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { v[4 * c] += resv[c].x; v[4 * c + 1] += resv[c].y; v[4 * c + 2] += resv[c].z; v[4 * c + 3] += resv[c].w; }
+          for (int c = 0; c < 8; ++c) { const float4 x = rr[c ^ (pos & 7)]; v[4 * c] += x.x; v[4 * c + 1] += x.y; v[4 * c + 2] += x.z; v[4 * c + 3] += x.w; }
+        }
       }
       const int row = min(tile * p.BR + t, p.rows - 1);
       const bool live = p.row_clip[row] >= 0;
@@ -271,12 +281,13 @@ void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const 
     p.ntaps = 10; ++np;
   }
   CUtensorMap tmOut = make_map_out(out, rows, F_out, pitch, BR);
+  CUtensorMap tmRes = res ? make_map_out(res, rows, F_out, F_out, BR) : tmOut;      // box {32, F_out, BR}: positions t * F_out + f
   for (int q = np; q < 3; ++q) tm[q] = tm[0];
   p.nplanes = np;
   p.stage_bytes = off;
   constexpr int kSmemMax = 227 * 1024;
   p.nstages = STAGES; p.ngroups = 2;
-  auto need = [&]() { return W_BYTES + p.ngroups * (OUT_BYTES / 2) + p.nstages * (int)off + 2048 + 1024 + 256; };
+  auto need = [&]() { return W_BYTES + p.ngroups * (OUT_BYTES / 2) + p.nstages * (int)off + 2048 + (res ? 4 * RES_BYTES : 0) + 1024 + 256; };
   if (need() > kSmemMax) p.ngroups = 1;             // the stride-2 convs of layer 1: two 26 KB parity planes per stage
   if (need() > kSmemMax) p.nstages = 2;
   const int smem = need();
@@ -286,7 +297,7 @@ void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const 
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
   const int grid = p.ntiles < nsm ? p.ntiles : nsm;
   Scope scp(c->launches, st, tag, flops, 128.0 * rows * (F_in + F_out + (sc ? F_out : 0) + (res ? F_out : 0)));   // in + out (+ shortcut / residual)
-  tc::launch_pdl(fcm_conv_kernel, dim3(grid), dim3(320), smem, st, pdl, tm[0], tm[1], tm[2], tmW, tmOut, p);
+  tc::launch_pdl(fcm_conv_kernel, dim3(grid), dim3(320), smem, st, pdl, tm[0], tm[1], tm[2], tmW, tmOut, tmRes, p);
 }
 
 }  // namespace cbx
