@@ -270,7 +270,6 @@ int cbx_set_option(cbx_ctx* c, const char* key, int64_t v) {
   else if (k == "mode" && (v == 0 || v == 1)) c->mode = v;
   else if (k == "overlap" && (v == 0 || v == 1)) c->overlap = v;
   else if (k == "lstm_dbg") c->lstm_dbg = v;
-  else if (k == "gemm_pair") c->gemm_pair = v;
   else if (k == "pdl") c->pdl = v;
   else if (k == "lstm_impl" && (v == 1 || v == 2)) c->lstm_impl = v;
   else if (k == "lstm_trace") c->lstm_trace = v;

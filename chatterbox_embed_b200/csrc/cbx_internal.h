@@ -112,7 +112,6 @@ struct XvWeights {
   const float *out_a, *out_b;                     // out_nonlinear BN
   const float *fin_w, *fin_b;                     // [192][1024] (BN folded), [192]
   CUtensorMap tm_tdnn, tm_w1[52], tm_wl[52], tm_tr[3];   // TMA maps of the GEMM B operands
-  CUtensorMap tm_w1h[52], tm_trh[3];                     // the same with 64-row boxes (CTA-pair GEMM: each CTA loads half a tile)
   CUtensorMap tm_res[2][2][2], tm_head2;
 };
 struct FrontendTables {
@@ -155,7 +154,6 @@ struct cbx_ctx {
   int64_t lstm_trace = 0;             // device pointer of the clock trace buffer
   int64_t lstm_impl = 2;              // 1: DSMEM-push recurrence, 2: L2 multicast-TMA recurrence
   int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)
-  int64_t gemm_pair = 0;              // 1: pre-activation GEMMs as CTA pairs (tcgen05 cta_group::2)
   int64_t pdl = 1;                    // programmatic dependent launch along the dense-layer chain
   // buffers owned by the library (cbx_embed_host / cbx_embed_host_submit): two slots so that the host<->device copies of
   // one batch overlap the kernels of the other; the workspace is shared (kernels of both slots run on one compute stream)

@@ -101,15 +101,6 @@ extern "C" int cbx_test_tgemm(cbx_ctx* c, const float* A, int64_t lda, const flo
   } else if (variant == 4) {    // pre-activation GEMM (register producers), single CTA
     CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 128, true);
     tc::tgemm_bnrelu<128, 3>(c->launches, st, "test_tgemm_bnrelu", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K, epi);
-  } else if (variant == 9) {    // EXPERIMENT: two stages instead of three
-    CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 128, true);
-    tc::tgemm_bnrelu<128, 2>(c->launches, st, "test_tgemm_bnrelu_s2", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K, epi);
-  } else if (variant == 10) {   // EXPERIMENT: one stage
-    CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 128, true);
-    tc::tgemm_bnrelu<128, 1>(c->launches, st, "test_tgemm_bnrelu_s1", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K, epi);
-  } else if (variant == 5) {    // the same as CTA pairs (cta_group::2)
-    CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 64, true);
-    tc::tgemm_bnrelu2<128, 4>(c->launches, st, "test_tgemm_bnrelu2", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K, epi);
   } else {
     c->err = "bad variant"; return CBX_ERR_ARG;
   }

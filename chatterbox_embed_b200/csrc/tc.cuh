@@ -140,60 +140,6 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
-// ---------------------------------------------------------------- CTA-pair (cta_group::2) wrappers
-// Two CTAs of a cluster on the two SMs of one TPC run ONE M = 256 MMA: each holds its own 128 rows of A and HALF of the B
-// tile; the leader (cluster rank 0) issues, both tensor cores execute, each writes its 128 accumulator rows to its own TMEM.
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope (remote arrivals)
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-// TMA load into THIS CTA's shared memory whose bytes are counted on the mbarrier at cluster address bar_cluster (the leader's)
-__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {   // one warp of EACH CTA of the pair
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives on the mbarrier at the same shared-memory offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-
 // 32 lanes x 32 columns: thread i of the warp gets columns [c, c+32) of TMEM lane (quadrant*32 + i)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -544,167 +490,6 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
   if (tr && threadIdx.x == 0) tr[7] = gtime();
 }
 
-// ---------------------------------------------------------------- CTA-pair version of the pre-activation GEMM
-// Same roles as tgemm_bnrelu_kernel, but two CTAs (cluster (2,1,1): two consecutive 128-row tiles, the two SMs of a TPC) share
-// every W tile: each CTA loads only BN/2 of its rows and the pair's tensor cores exchange the halves, so per CTA the B operand
-// costs half the TMA writes and half the shared-memory operand reads -- the unified L1 / shared-memory array is what bounds
-// this kernel.  The leader (rank 0) owns the full barriers: both CTAs' TMA bytes and all 256 producer arrivals
-// land there; its MMA warp issues tcgen05.mma.cta_group::2 (M = 256) and commits to the empty / accumulator barriers of both.
-static __device__ int g_tpc_lock[128];      // zero-initialised; one per TPC (per translation unit: all co-resident pair kernels live in xv.cu)
-
-template <int BN, int STAGES, class Epi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 2)
-tgemm_bnrelu2_kernel(const float* __restrict__ X, int lda, int M, const float* __restrict__ bn_a, const float* __restrict__ bn_b,
-                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, int nkb, Epi epi) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int A_BYTES = BM * BK * 4, B_BYTES = (BN / 2) * BK * 4;       // B: this CTA's half of the tile
-  constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* bfull = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
-  uint64_t* afull = bfull + STAGES;          // leader: 256 producer arrivals (128 local + 128 remote)
-  uint64_t* empty = afull + STAGES;          // pair-wide MMA commit
-  uint64_t* accum = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();                        // == blockIdx.x: the pair lies along x
-  const int m0 = (blockIdx.z * 2 + blockIdx.x) * BM, n0 = blockIdx.y * BN;   // n tiles next: the pairs that share X rows run together
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&afull[s], 256); mbar_init(&empty[s], 1); }
-    mbar_init(accum, 1);
-    fence_barrier_init();
-  }
-  // Two clusters share a TPC (2 CTAs per SM) and the pair-wide TMEM allocation is a rendezvous of the two SMs: if SM 2k served
-  // cluster A first and SM 2k+1 cluster B first, each would hold its SM's allocation permit while waiting for the other's peer.
-  // One lock per TPC (the pair always sits on SMs 2k / 2k+1, leader on 2k: tools/clustertest.cu) serialises the allocations.
-  int* lock = nullptr;
-  if (warp == 1 && rank == 0 && lane == 0) {
-    uint32_t smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    lock = g_tpc_lock + (smid >> 1);
-    while (atomicCAS(lock, 0, 1) != 0) __nanosleep(64);
-  }
-  cluster_sync_all();
-  if (warp == 1) tmem_alloc_pair(tmem_slot, TMEM_COLS);
-  tc_fence_before();
-  cluster_sync_all();
-  tc_fence_after();
-  if (lock) atomicExch(lock, 0);
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        if (rank == 0) mbar_expect_tx(&bfull[s], 2 * B_BYTES);
-        tma_load_2d_pair(sB + s * B_BYTES, &tmB, mapa_u32(smem_u32(&bfull[s]), 0), kb * BK, n0 + (int)rank * (BN / 2));
-      }
-    }
-  } else if (warp == 1) {
-    if (rank == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(2 * BM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-        mbar_wait_cluster(&afull[s], ph);
-        mbar_wait_cluster(&bfull[s], ph);
-        tc_fence_after();
-        const uint64_t ad = make_desc_sw128(smem_u32(sA + s * A_BYTES));
-        const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_tf32_pair(tmem_base, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (kb | k) != 0);
-          umma_commit_pair(&empty[s]);
-          if (kb == nkb - 1) umma_commit_pair(accum);
-        }
-        __syncwarp();
-      }
-    }
-  } else {
-    const int g = (warp - 2) >> 2;
-    const int t = (threadIdx.x - 64) & 127;
-    const int chunk = t & 7, r0 = t >> 3;
-    const float* xp = X + (size_t)(m0 + r0) * lda + chunk * 4;
-    const uint32_t afull0 = mapa_u32(smem_u32(afull), 0);          // the leader's afull[0]
-    float4 xa[BM / 16 + 2], xb[BM / 16 + 2];
-    auto load = [&](float4* dst, int kb) {
-      const int kcol = kb * BK;
-#pragma unroll
-      for (int i = 0; i < BM / 16; ++i)
-        dst[i] = (m0 + r0 + i * 16 < M) ? ldg_stream(reinterpret_cast<const float4*>(xp + (size_t)i * 16 * lda + kcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      dst[BM / 16] = __ldg(reinterpret_cast<const float4*>(bn_a + kcol + chunk * 4));
-      dst[BM / 16 + 1] = __ldg(reinterpret_cast<const float4*>(bn_b + kcol + chunk * 4));
-    };
-    auto produce = [&](const float4* x, int kb) {
-      const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-      const float4 sc = x[BM / 16], sh = x[BM / 16 + 1];
-      mbar_wait(&empty[s], ph ^ 1);
-      float4* base = reinterpret_cast<float4*>(sA + s * A_BYTES);
-#pragma unroll
-      for (int i = 0; i < BM / 16; ++i) {
-        const int r = r0 + i * 16;
-        float4 y;
-        y.x = to_tf32(fmaxf(fmaf(x[i].x, sc.x, sh.x), 0.f));
-        y.y = to_tf32(fmaxf(fmaf(x[i].y, sc.y, sh.y), 0.f));
-        y.z = to_tf32(fmaxf(fmaf(x[i].z, sc.z, sh.z), 0.f));
-        y.w = to_tf32(fmaxf(fmaf(x[i].w, sc.w, sh.w), 0.f));
-        base[r * 8 + (chunk ^ (r & 7))] = y;
-      }
-      fence_proxy_async();
-      mbar_arrive_cluster(afull0 + (uint32_t)s * 8u);
-    };
-    if (g < nkb) load(xa, g);
-    for (int kb = g; kb < nkb; kb += 2 * PG) {
-      if (kb + PG < nkb) load(xb, kb + PG);
-      produce(xa, kb);
-      if (kb + PG < nkb) {
-        if (kb + 2 * PG < nkb) load(xa, kb + 2 * PG);
-        produce(xb, kb + PG);
-      }
-    }
-    if (warp < 6) {
-      mbar_wait(accum, 0);
-      tc_fence_after();
-      const int q = warp & 3;
-      const int row = m0 + q * 32 + lane;
-      const int i = q * 32 + lane;
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-        epi(row, n0 + c, v);
-        const int buf = (c >> 5) % STAGES;
-        if (c >= 32 * STAGES) {
-          if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-        float4* so = reinterpret_cast<float4*>(sA + buf * A_BYTES) + i * 8;
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) so[jj ^ (i & 7)] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
-        fence_proxy_async();
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (warp == 2 && lane == 0) {
-          tma_store_2d(&tmC, sA + buf * A_BYTES, n0 + c, m0);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-      }
-      if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-      tc_fence_before();
-    }
-  }
-  tc_fence_before();
-  cluster_sync_all();          // neither CTA may retire (barriers, shared memory, TMEM) while its peer can still touch it
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc_pair(tmem_base, TMEM_COLS);
-  }
-}
-
 // ---------------------------------------------------------------- persistent GEMM
 //   C[m][n] = epi( sum_k pro(A[m][k]) * W[n][k] ),   one CTA per SM looping over 128 x BN output tiles (n fastest).
 // The shared-memory stage ring and the barriers' phases run on across tiles, and the fp32 accumulator is double-buffered
@@ -948,22 +733,6 @@ inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const fl
   Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
   CUtensorMap tmC = make_map_2d(C, M, N, ldc, BM, false);
   launch_pdl(kern, grid, dim3(320), SMEM, st, pdl, X, lda, M, bn_a, bn_b, tmB, tmC, (K + BK - 1) / BK, epi);
-}
-
-// CTA-pair launch: tmB must have a box of BN/2 rows; grid = (pair, n tiles, row-tile pairs) -- an odd last row tile gets a CTA with no rows
-template <int BN, int STAGES, class Epi>
-inline void tgemm_bnrelu2(Launches& L, cudaStream_t st, const char* tag, const float* X, int lda, const float* bn_a, const float* bn_b,
-                          const CUtensorMap& tmB_half, float* C, int ldc, int M, int N, int K, Epi epi) {
-  if (M <= 0 || N <= 0) return;
-  auto kern = tgemm_bnrelu2_kernel<BN, STAGES, Epi>;
-  constexpr int SMEM = smem_bytes(BN / 2, STAGES);
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
-  const int mt = (M + BM - 1) / BM;
-  dim3 grid(2, (N + BN - 1) / BN, (mt + 1) / 2);          // a launch with the pair along y is refused ("cluster misconfiguration")
-  Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
-  CUtensorMap tmC = make_map_2d(C, M, N, ldc, BM, false);
-  kern<<<grid, 320, SMEM, st>>>(X, lda, M, bn_a, bn_b, tmB_half, tmC, (K + BK - 1) / BK, epi);
 }
 
 }  // namespace tc

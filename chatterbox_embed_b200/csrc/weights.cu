@@ -281,16 +281,12 @@ int load_xv(cbx_ctx* c, const TensorMap& t) {
   for (int i = 0; i < 52; ++i) {
     W.tm_w1[i] = tc::make_map_2d(W.dense[i].w1, kBnC, W.dense[i].cin, W.dense[i].cin, 128, true);
     W.tm_wl[i] = tc::make_map_2d(W.dense[i].wl, kGrowth, 3 * kBnC, 3 * kBnC, 32, true);
-    W.tm_w1h[i] = tc::make_map_2d(W.dense[i].w1, kBnC, W.dense[i].cin, W.dense[i].cin, 64, true);
   }
   for (int l = 0; l < 2; ++l)
     for (int b = 0; b < 2; ++b)
       for (int k = 0; k < 2; ++k) W.tm_res[l][b][k] = tc::make_map_2d(W.res[l][b][k].w, kFcmC, W.res[l][b][k].K, W.res[l][b][k].K, 32, true);
   W.tm_head2 = tc::make_map_2d(W.head_conv2.w, kFcmC, 288, 288, 32, true);
-  for (int b = 0; b < 3; ++b) {
-    W.tm_tr[b] = tc::make_map_2d(W.transit[b].w, W.transit[b].cout, W.transit[b].cin, W.transit[b].cin, 128, true);
-    W.tm_trh[b] = tc::make_map_2d(W.transit[b].w, W.transit[b].cout, W.transit[b].cin, W.transit[b].cin, 64, true);
-  }
+  for (int b = 0; b < 3; ++b) W.tm_tr[b] = tc::make_map_2d(W.transit[b].w, W.transit[b].cout, W.transit[b].cin, W.transit[b].cin, 128, true);
   W.loaded = true;
   return CBX_OK;
 }

@@ -466,10 +466,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     }
     for (int i = 0; i < kLayers[b]; ++i, ++li) {
       const DenseLayerW& D = W.dense[li];
-      if (tcm && c->gemm_pair)
-        tc::tgemm_bnrelu2<128, 4>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1h[li], ch.u, kBnC, M, kBnC, D.cin,
-                                  tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M});
-      else if (tcm)
+      if (tcm)
         tc::tgemm_bnrelu<128, 2>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
                                  tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
       else
@@ -489,10 +486,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     const TransitW& T = W.transit[b];
     float* out = b == 0 ? ch.cat2 : (b == 1 ? ch.cat3 : ch.tr3);
     const int ldo = b == 2 ? kStatsC : 1024;
-    if (tcm && c->gemm_pair)
-      tc::tgemm_bnrelu2<128, 4>(L, st, "transit_gemm", cat, ld, T.a, T.b, W.tm_trh[b], out, ldo, M, T.cout, T.cin,
-                                tc::EpiMask{nullptr, ldo, ch.td_row_clip, M});
-    else if (tcm)
+    if (tcm)
       tc::tgemm_bnrelu<128, 2>(L, st, "transit_gemm", cat, ld, T.a, T.b, W.tm_tr[b], out, ldo, M, T.cout, T.cin,
                                tc::EpiMask{nullptr, ldo, ch.td_row_clip, M}, pdl);
     else
