@@ -227,11 +227,11 @@ def test_mode1_north_star_gate(models, mode1, kind):
     scale = max(1.0, float(np.abs(want_xv).max()))
     assert np.abs(xv - want_xv).max() <= 1e-3 * scale
     assert min(cos(a, b) for a, b in zip(xv, want_xv)) >= 0.9999
-    # batch composition must not matter beyond rounding noise.  Two things make the tensor-core mode position dependent
-    # in the last bits: the CAM segment sums are accumulated with atomics in the GEMM epilogue (summation order depends on
-    # where the clip's rows fall in the 128-row tiles), and the LSTM gate math shares one reciprocal between four
-    # neighbouring partials (1-2 ulp that depends on the neighbours).  The strict fp32 mode is position independent and
-    # holds this to 1e-6 / 1e-5 in test_ragged_batch_equals_per_clip_oracle.
+    # batch composition must not matter beyond rounding noise.  A run is bit-reproducible (test_mode1_results_are_reproducible),
+    # but the tensor-core mode is position dependent in the last bits: the CAM segment sums are fp32 partial sums over the
+    # 32-row groups of the GEMM epilogue before they enter the fixed-point reduction (the grouping depends on where the
+    # clip's rows fall in the 128-row tiles), and a last-bit difference flips TF32 operand roundings downstream.  The
+    # strict fp32 mode is position independent and holds this to 1e-6 / 1e-5 in test_ragged_batch_equals_per_clip_oracle.
     ve1, xv1 = emb.embed_wavs([wavs[3]])
     assert np.abs(ve1[0] - ve[3]).max() < 2e-5 and np.abs(xv1[0] - xv[3]).max() < 5e-4 * scale
 
