@@ -96,11 +96,11 @@ extern "C" int cbx_test_tgemm(cbx_ctx* c, const float* A, int64_t lda, const flo
       cap = M;
     }
     CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 128, true);
-    tc::tgemm_bnrelu<128, 3>(c->launches, st, "test_tgemm_bnrelu", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K,
+    tc::tgemm_bnrelu<128, 2>(c->launches, st, "test_tgemm_bnrelu", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K,
                              EpiSegsumProbe{{nullptr, (int)ldc, bias, row_seg, seg_sum, M}});
   } else if (variant == 4) {    // pre-activation GEMM (register producers), single CTA
     CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 128, true);
-    tc::tgemm_bnrelu<128, 3>(c->launches, st, "test_tgemm_bnrelu", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K, epi);
+    tc::tgemm_bnrelu<128, 2>(c->launches, st, "test_tgemm_bnrelu", A, (int)lda, pro_a, pro_b, tmB, C, (int)ldc, M, N, K, epi);
   } else {
     c->err = "bad variant"; return CBX_ERR_ARG;
   }
