@@ -48,8 +48,17 @@ struct EpiBiasReluMaskSegsum {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int seg = m < M ? row_seg[m] : -1;
+    // bias as eight 16-byte loads, unconditionally (one LSU request each instead of 32 predicated scalar ones: the LSU queue
+    // is shared with the other CTA's prefetch stream)
+    const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = seg >= 0 ? fmaxf(v[i] + __ldg(bias + n0 + i), 0.f) : 0.f;
+    for (int j = 0; j < 8; ++j) {
+      const float4 bb = __ldg(b4 + j);
+      v[4 * j] = seg >= 0 ? fmaxf(v[4 * j] + bb.x, 0.f) : 0.f;
+      v[4 * j + 1] = seg >= 0 ? fmaxf(v[4 * j + 1] + bb.y, 0.f) : 0.f;
+      v[4 * j + 2] = seg >= 0 ? fmaxf(v[4 * j + 2] + bb.z, 0.f) : 0.f;
+      v[4 * j + 3] = seg >= 0 ? fmaxf(v[4 * j + 3] + bb.w, 0.f) : 0.f;
+    }
     if (out && m < M) store32(out + (size_t)m * ld + n0, v);
     unsigned rem = __ballot_sync(full, seg >= 0);
     while (rem) {
