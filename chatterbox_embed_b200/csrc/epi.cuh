@@ -27,8 +27,15 @@ struct EpiBiasReluMask {         // out = row is a real frame ? relu(acc + bias)
   __device__ void operator()(int m, int n0, float* v) const {
     if (m >= M) return;
     const bool live = row_clip[m] >= 0;
+    const float4* b4 = reinterpret_cast<const float4*>(bias + n0);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = live ? fmaxf(v[i] + __ldg(bias + n0 + i), 0.f) : 0.f;
+    for (int j = 0; j < 8; ++j) {
+      const float4 bb = __ldg(b4 + j);
+      v[4 * j] = live ? fmaxf(v[4 * j] + bb.x, 0.f) : 0.f;
+      v[4 * j + 1] = live ? fmaxf(v[4 * j + 1] + bb.y, 0.f) : 0.f;
+      v[4 * j + 2] = live ? fmaxf(v[4 * j + 2] + bb.z, 0.f) : 0.f;
+      v[4 * j + 3] = live ? fmaxf(v[4 * j + 3] + bb.w, 0.f) : 0.f;
+    }
     store32(out + (size_t)m * ld + n0, v);
   }
 };

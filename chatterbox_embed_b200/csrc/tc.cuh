@@ -595,8 +595,11 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if constexpr (kTmaC) {
           const int i = q * 32 + lane;
           const int buf = (c >> 5) & 1;
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(epi.bias + n0 + c);      // eight LSU requests instead of 32
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(epi.bias + n0 + c + j);
+            for (int j = 0; j < 8; ++j) { const float4 bb = __ldg(b4 + j); v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
+          }
           if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used `buf` has read it
           asm volatile("bar.sync 1, 128;" ::: "memory");
           float4* so = reinterpret_cast<float4*>(sC + buf * (BM * 128)) + i * 8;
