@@ -341,9 +341,18 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
   uint64_t* empty = afull + STAGES;          // MMA commit: both the A and the B half of the stage are free
   uint64_t* accum = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  // BN scale / shift of all K columns, staged once (static data: loaded before the dependency wait): the producers then
+  // need no global loads besides X, whose requests already fill the SM's load queue
+  float* s_bn = reinterpret_cast<float*>(smem + STAGES * (A_BYTES + B_BYTES) + 256);      // [2][nkb * 32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;     // n fastest: the CTAs that share an X row tile run together (L2 reuse)
+  {
+    const int kq = nkb * (BK / 4);                          // float4s per vector
+    float4* d = reinterpret_cast<float4*>(s_bn);
+    for (int i = threadIdx.x; i < 2 * kq; i += 320)
+      d[i] = __ldg(reinterpret_cast<const float4*>(i < kq ? bn_a : bn_b) + (i < kq ? i : i - kq));
+  }
   unsigned long long* tr = g_gemm_trace ? g_gemm_trace + 16 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
   if (tr && threadIdx.x == 0) { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); tr[0] = smid; tr[1] = gtime(); }
 
@@ -398,18 +407,18 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
     const int t = (threadIdx.x - 64) & 127;
     const int chunk = t & 7, r0 = t >> 3;
     const float* xp = X + (size_t)(m0 + r0) * lda + chunk * 4;
-    float4 xa[BM / 16 + 2], xb[BM / 16 + 2];        // 8 rows of X plus the K block's BN scale / shift
+    float4 xa[BM / 16], xb[BM / 16];                // 8 rows of X each
+    const float4* sc4 = reinterpret_cast<const float4*>(s_bn) + chunk;
+    const float4* sh4 = sc4 + nkb * (BK / 4);
     auto load = [&](float4* dst, int kb) {
       const int kcol = kb * BK;
 #pragma unroll
       for (int i = 0; i < BM / 16; ++i)
         dst[i] = (m0 + r0 + i * 16 < M) ? ldg_stream(reinterpret_cast<const float4*>(xp + (size_t)i * 16 * lda + kcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      dst[BM / 16] = __ldg(reinterpret_cast<const float4*>(bn_a + kcol + chunk * 4));
-      dst[BM / 16 + 1] = __ldg(reinterpret_cast<const float4*>(bn_b + kcol + chunk * 4));
     };
     auto produce = [&](const float4* x, int kb) {
       const int s = kb % STAGES, ph = (kb / STAGES) & 1;
-      const float4 sc = x[BM / 16], sh = x[BM / 16 + 1];
+      const float4 sc = sc4[kb * (BK / 4)], sh = sh4[kb * (BK / 4)];
       mbar_wait(&empty[s], ph ^ 1);
       float4* base = reinterpret_cast<float4*>(sA + s * A_BYTES);
 #pragma unroll
@@ -729,7 +738,8 @@ inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const fl
                          const CUtensorMap& tmB, float* C, int ldc, int M, int N, int K, Epi epi, bool pdl = false) {
   if (M <= 0 || N <= 0) return;
   auto kern = tgemm_bnrelu_kernel<BN, STAGES, Epi>;
-  constexpr int SMEM = smem_bytes(BN, STAGES);
+  constexpr int SMEM = smem_bytes(BN, STAGES) + 2 * 1024 * 4;      // + BN scale / shift of up to 1024 columns
+  if (K > 1024) { fprintf(stderr, "libcbx: tgemm_bnrelu supports K <= 1024\n"); return; }
   static bool configured = false;
   if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
