@@ -362,6 +362,26 @@ def test_resample_matches_torchaudio(src, dst):
     assert np.abs(got[1].cpu().numpy() - frontend.resample_torchaudio(wavs[0][::-1].copy(), src, dst)).max() < 3e-5
 
 
+def test_resample_full_size_properties():
+    """256 clips x 10 s at 44.1 kHz (the tiled kernel: 160 phases x 475 taps) and 48 kHz (the per-sample kernel): length
+    formula, linearity, unit DC gain of every phase, and a sample of clips against torchaudio itself."""
+    from chatterbox_embed_b200 import Resample
+    g = torch.Generator(DEV).manual_seed(12)
+    for src in (44100, 48000):
+        n = src * 10
+        x = 0.1 * torch.randn(256, n, device=DEV, generator=g)
+        y = 0.1 * torch.randn(256, n, device=DEV, generator=g)
+        rs = Resample(src, 16000)
+        rx, ry = rs(x), rs(y)
+        assert tuple(rx.shape) == (256, 160000)
+        assert (rs(0.25 * x - 2.0 * y) - (0.25 * rx - 2.0 * ry)).abs().max() < 2e-6          # linear up to fp32 rounding
+        dc = rs(torch.ones(1, n, device=DEV))[0]
+        assert (dc[100:-100] - 1.0).abs().max() < 2e-3                                        # windowed-sinc phases sum to ~1
+        for i in (0, 255):
+            want = frontend.resample_torchaudio(x[i].cpu().numpy(), src, 16000)
+            assert np.abs(rx[i].cpu().numpy() - want).max() < 3e-5
+
+
 def test_save_voice_clone_resamples_like_the_reference(models, tmp_path):
     """S3Token2Mel.save_voice_clone (s3gen.py:107-119) on 24 kHz input: resample -> CAMPPlus -> .npy."""
     sdv, sdc, ve, cp = models["W1"]

@@ -123,3 +123,34 @@ def test_load_audio_like_librosa_load(tmp_path):
     y, sr = vp.load_audio(p)
     assert sr == 22050 and y.dtype == np.float32 and y.shape == (1000,)
     assert np.array_equal(y, (pcm.astype(np.float32) / 32768.0).mean(axis=1))         # soundfile scaling + librosa to_mono
+
+
+def test_s3_frontend_pad_matches_reference_fixture(golden_dir):
+    """S3Tokenizer.pad (s3tokenizer.py:52-74) is host arithmetic: lengths from the verbatim reference."""
+    import torch
+    from chatterbox_embed_b200.s3tokenizer import S3TokenizerFrontend
+    g = np.load(os.path.join(golden_dir, "ref_s3_log_mel.npz"))
+    fe = S3TokenizerFrontend("cpu")                      # pad / _prepare_audio never touch the device
+    got = [fe.pad([np.zeros(int(n), np.float32)], 16000)[0].shape[1] for n in g["pad_in"]]
+    assert got == g["pad_out"].tolist()
+    out = fe.pad([torch.ones(2, 700)], 16000)[0]         # (B, L) tensors are padded on the right with zeros
+    assert tuple(out.shape) == (2, 1280) and float(out[:, 700:].abs().max()) == 0.0
+    assert [tuple(w.shape) for w in fe._prepare_audio([np.zeros(5, np.float32), torch.zeros(1, 7)])] == [(1, 5), (1, 7)]
+
+
+def test_next_row_wrappers_refuse_what_they_do_not_build():
+    """No silent fallbacks: non-default mel settings, a tokenizer forward without a quantizer, CPU tensors."""
+    import torch
+    from chatterbox_embed_b200 import _lib, mel_spectrogram, Resample
+    from chatterbox_embed_b200.s3tokenizer import S3TokenizerFrontend
+    with pytest.raises(NotImplementedError):
+        mel_spectrogram(torch.zeros(1, 24000), n_fft=1024)
+    with pytest.raises(NotImplementedError):
+        S3TokenizerFrontend("cpu").forward([np.zeros(16000, np.float32)])
+    with pytest.raises(Exception, match="integer"):
+        Resample(44100.5, 16000)
+    assert Resample(16000, 16000)(torch.ones(3)) is not None         # identity needs no device
+    assert _lib.prompt_mel_frames(240000) == 500 and _lib.s3_log_mel_frames(160000) == 1000 and _lib.resample_out_len(44100, 16000, 441000) == 160000
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.CbxError):
+            mel_spectrogram(torch.zeros(1, 24000))                    # needs a B200: no CPU path
