@@ -258,14 +258,15 @@ __global__ void __launch_bounds__(256) cam_gate_clip_kernel(unsigned long long* 
   __shared__ float ctx[kMaxSegsSm][kBnC];
   __shared__ float hid[kMaxSegsSm][kCamHid];
   __shared__ float tot[kBnC];
-  const ClipPlan cp = plan[blockIdx.x];
   const int tid = threadIdx.x;
-  const int T = cp.xv_tdnn, S = cp.xv_segs;
   // weights -> shared memory (coalesced 16-byte loads, all in flight at once)
   for (int i = tid; i < kBnC * kCamHid / 4; i += 256) reinterpret_cast<float4*>(w1)[i] = __ldg(reinterpret_cast<const float4*>(L.wc1T) + i);
   for (int i = tid; i < kCamHid * kGrowth / 4; i += 256) reinterpret_cast<float4*>(w2)[i] = __ldg(reinterpret_cast<const float4*>(L.wc2T) + i);
   tc::pdl_trigger();            // short kernel: the local conv behind it may set up right away
-  tc::pdl_wait();               // the segment sums come from the bottleneck GEMM in front (the weights above do not)
+  tc::pdl_wait();               // only the layer's weights (static since load time) are read before this point: everything written
+                                // during this call -- the plan table included -- is visible only from here on
+  const ClipPlan cp = plan[blockIdx.x];
+  const int T = cp.xv_tdnn, S = cp.xv_segs;
   unsigned long long* ss = seg_sum + (size_t)cp.seg0 * kBnC;      // 40.24 fixed point (EpiBiasReluMaskSegsum)
   auto seg_val = [&](int s, int ch) { return (float)((double)(long long)ss[(size_t)s * kBnC + ch] * (1.0 / (double)tc::kSegFix)); };
   if (tid < kBnC) {

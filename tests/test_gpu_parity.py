@@ -306,6 +306,24 @@ def test_mode1_results_are_reproducible(models, mode1):
         assert np.array_equal(ve, ve0) and np.array_equal(xv, xv0)
 
 
+def test_launch_options_do_not_change_results(models, mode1):
+    """Programmatic dependent launch (kernels start while their predecessor drains and prefetch what is already final) and
+    the two-stream overlap are scheduling only: bit-identical embeddings with either switched off."""
+    sdv, sdc, emb = _emb(models, "W1")
+    lens = [int(x) for x in synth.ragged_lengths(24)]
+    wavs = [synth.clip(i, n) for i, n in enumerate(lens)]
+    ctx = _lib.context(0)
+    ref = emb.embed_wavs(wavs)
+    try:
+        for key in ("pdl", "overlap"):
+            ctx.set_option(key, 0)
+            got = emb.embed_wavs(wavs)
+            ctx.set_option(key, 1)
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), key
+    finally:
+        ctx.set_option("pdl", 1); ctx.set_option("overlap", 1)
+
+
 def test_stream_api_equals_single_calls(models, mode1):
     """cbx_embed_host_submit / _wait with two batches in flight returns what the one-shot call returns, in order."""
     sdv, sdc, emb = _emb(models, "W1")
