@@ -79,10 +79,13 @@ void cbx_destroy(cbx_ctx* ctx);
 const char* cbx_last_error(const cbx_ctx* ctx);   /* ctx may be NULL: last error of cbx_create */
 const char* cbx_version(void);
 
-/* Tuning: key in {"xv_chunk_rows","fcm_chunk_rows","lstm_chunk_partials","mode","overlap"}.  mode: 1 (default) = tensor-core
- * (tcgen05, TF32 / 3xTF32) kernels, 0 = strict fp32 SIMT kernels everywhere (the on-device fp32 yardstick).  overlap: 1 = with both encoders
- * requested, CAMPPlus runs on an internal second stream beside the VoiceEncoder chain (forked from / joined into the
- * caller's stream). */
+/* Tuning: key in {"xv_chunk_rows","fcm_chunk_rows","lstm_chunk_partials","mode","overlap","pdl"}.  mode: 1 (default) =
+ * tensor-core (tcgen05, TF32 / 3xTF32) kernels, 0 = strict fp32 SIMT kernels everywhere (the on-device fp32 yardstick).
+ * overlap: 1 (default) = with both encoders requested, CAMPPlus runs on an internal second stream beside the
+ * VoiceEncoder chain (forked from / joined into the caller's stream).  pdl: 1 (default) = the CAMPPlus convolution and
+ * dense-layer chains use programmatic dependent launch (a kernel sets up while its predecessor drains).  overlap and pdl
+ * are scheduling only: results are bit-identical with either off.  ("lstm_impl", "lstm_dbg", "lstm_trace" select / probe
+ * the recurrence kernel and are for the tools under tools/.) */
 int cbx_set_option(cbx_ctx* ctx, const char* key, int64_t value);
 int64_t cbx_get_option(const cbx_ctx* ctx, const char* key);
 
