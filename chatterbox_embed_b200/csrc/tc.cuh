@@ -319,7 +319,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // Here producer warps do the staging themselves: coalesced 16-byte global loads of X (many in flight), BN + ReLU + tf32
 // rounding in registers, one store into the 128B-swizzled K-major stage.  Two producer groups of 4 warps alternate K blocks,
 // so one group's load latency hides behind the other's arithmetic.  W tiles come by TMA; MMA / epilogue as in tgemm_kernel.
-// Warps: 0 = TMA (W), 1 = MMA issuer, 2..5 = epilogue, 6..9 = producer group 0, 10..13 = producer group 1.
+// Warps: 0 = TMA (W), 1 = MMA issuer, 2..5 = producer group 0, 6..9 = producer group 1; all eight run the epilogue.
 constexpr int PG = 2;     // producer groups
 
 // timeline probe (tools/gemm_trace.py): when set, every CTA records {smid, t_entry, t_setup, t_first_full, t_accum, t_end}
@@ -500,20 +500,18 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
 }
 
 // ---------------------------------------------------------------- persistent GEMM
-//   C[m][n] = epi( sum_k pro(A[m][k]) * W[n][k] ),   one CTA per SM looping over 128 x BN output tiles (n fastest).
+//   C[m][n] = sum_k A[m][k] * W[n][k] + bias[n],   one CTA per SM looping over 128 x BN output tiles (n fastest).
 // The shared-memory stage ring and the barriers' phases run on across tiles, and the fp32 accumulator is double-buffered
-// in TMEM (2 x BN columns), so the epilogue of tile i (TMEM -> registers -> global) overlaps the K loop of tile i+1 and
-// the per-CTA set-up (barrier init, TMEM allocation, descriptor prefetch) is paid once per SM instead of once per tile.
-// kPro = false: A tiles come by TMA (tf32 rounding in the tensor map); warps 0 = TMA, 1 = MMA, 2..5 = epilogue.
-// kPro = true:  A is produced by warps 6..13 (two groups alternating K blocks): coalesced 16-byte loads of X, BatchNorm +
-//               ReLU + tf32 rounding in registers, one store into the swizzled stage (pre-activation D-TDNN layers).
-// kTmaC = true: the epilogue is "+ bias" and the C tile leaves through two 16 KB staging buffers and TMA tensor stores
-// (one 128 x 32 box per accumulator chunk) instead of per-thread 16-byte stores scattered over 32 rows.
-template <int BN, int STAGES, bool kPro, bool kTmaC, class Epi>
-__global__ void __launch_bounds__(kPro ? 448 : 192, 1)
+// in TMEM (2 x BN columns), so the epilogue of tile i overlaps the K loop of tile i+1 and the per-CTA set-up (barrier init,
+// TMEM allocation, descriptor prefetch) is paid once per SM instead of once per tile.  A and W tiles come by TMA (tf32
+// rounding of A in the tensor map); warps 0 = TMA, 1 = MMA, 2..5 = epilogue.  The C tile leaves through two 16 KB staging
+// buffers and TMA tensor stores (one 128 x 32 box per accumulator chunk) instead of per-thread 16-byte stores scattered over
+// 32 rows.  (A second epilogue group, as in the convolution kernels, made this one slower: it is bound by its 4 KB per row
+// of C writes, and the extra staging buffers cost a pipeline stage.)
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
 pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-             const float* __restrict__ X, int lda,
-             const float* __restrict__ bn_a, const float* __restrict__ bn_b, int M, int n_tiles_n, int n_tiles, int nkb, Epi epi) {
+             const float* __restrict__ bias, int n_tiles_n, int n_tiles, int nkb) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
@@ -521,20 +519,17 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   constexpr int TMEM_COLS = 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* bfull = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));   // TMA bytes (B, and A when !kPro)
-  uint64_t* afull = bfull + STAGES;          // 128 producer arrivals (kPro)
-  uint64_t* empty = afull + STAGES;          // MMA commit
+  uint64_t* bfull = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));   // TMA bytes (A and B)
+  uint64_t* empty = bfull + STAGES;          // MMA commit
   uint64_t* tfull = empty + STAGES;          // [2] accumulator ready
   uint64_t* tempty = tfull + 2;              // [2] accumulator drained (4 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint8_t* sC = smem + STAGES * (A_BYTES + B_BYTES) + 1024;    // [2][128 rows x 128 B] C staging (kTmaC)
+  uint8_t* sC = smem + STAGES * (A_BYTES + B_BYTES) + 1024;    // [2][128 rows x 128 B] C staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    if (!kPro) tma_prefetch_desc(&tmA);
-    if (kTmaC) tma_prefetch_desc(&tmC);
-    tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&afull[s], 128); mbar_init(&empty[s], 1); }
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bfull[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     fence_barrier_init();
   }
@@ -552,8 +547,8 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&bfull[s], kPro ? B_BYTES : A_BYTES + B_BYTES);
-          if (!kPro) tma_load_2d(sA + s * A_BYTES, &tmA, &bfull[s], kb * BK, m0);
+          mbar_expect_tx(&bfull[s], A_BYTES + B_BYTES);
+          tma_load_2d(sA + s * A_BYTES, &tmA, &bfull[s], kb * BK, m0);
           tma_load_2d(sB + s * B_BYTES, &tmB, &bfull[s], kb * BK, n0);
         }
       }
@@ -568,7 +563,6 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t d = tmem_base + a * BN;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
-        if (kPro) mbar_wait(&afull[s], ph);
         mbar_wait(&bfull[s], ph);
         tc_fence_after();
         const uint64_t ad = make_desc_sw128(smem_u32(sA + s * A_BYTES));
@@ -583,15 +577,15 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
       }
     }
-  } else if (warp < 6) {
+  } else {
     const int q = warp & 3;
+    const int i = q * 32 + lane;
     int ti = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
       const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
       const int a = ti & 1, pa = (ti >> 1) & 1;
       mbar_wait(&tfull[a], pa);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         float v[32];
@@ -601,65 +595,26 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[a]);
         }
-        if constexpr (kTmaC) {
-          const int i = q * 32 + lane;
-          const int buf = (c >> 5) & 1;
-          {
-            const float4* b4 = reinterpret_cast<const float4*>(epi.bias + n0 + c);      // eight LSU requests instead of 32
+        const int buf = (c >> 5) & 1;
+        {
+          const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c);      // eight LSU requests instead of 32
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { const float4 bb = __ldg(b4 + j); v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
-          }
-          if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used `buf` has read it
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          float4* so = reinterpret_cast<float4*>(sC + buf * (BM * 128)) + i * 8;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) so[j ^ (i & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          fence_proxy_async();
-          asm volatile("bar.sync 2, 128;" ::: "memory");
-          if (warp == 2 && lane == 0) {
-            tma_store_2d(&tmC, sC + buf * (BM * 128), n0 + c, m0);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-        } else {
-          epi(row, n0 + c, v);
+          for (int j = 0; j < 8; ++j) { const float4 bb = __ldg(b4 + j); v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
         }
-      }
-    }
-    if (kTmaC && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  } else if (kPro) {
-    const int g = (warp - 6) >> 2;
-    const int t = (threadIdx.x - 192) & 127;
-    const int chunk = t & 7, r0 = t >> 3;
-    int it0 = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it0 += nkb) {
-      const int m0 = (tile / n_tiles_n) * BM;
-      const float* xp = X + (size_t)(m0 + r0) * lda + chunk * 4;
-      for (int kb = g; kb < nkb; kb += PG) {
-        const int it = it0 + kb;
-        const int s = it % STAGES, ph = (it / STAGES) & 1;
-        const int kcol = kb * BK;
-        float4 x[BM / 16];
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used `buf` has read it
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        float4* so = reinterpret_cast<float4*>(sC + buf * (BM * 128)) + i * 8;
 #pragma unroll
-        for (int i = 0; i < BM / 16; ++i)
-          x[i] = (m0 + r0 + i * 16 < M) ? __ldg(reinterpret_cast<const float4*>(xp + (size_t)i * 16 * lda + kcol)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(bn_a + kcol + chunk * 4));
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(bn_b + kcol + chunk * 4));
-        mbar_wait(&empty[s], ph ^ 1);
-        float4* base = reinterpret_cast<float4*>(sA + s * A_BYTES);
-#pragma unroll
-        for (int i = 0; i < BM / 16; ++i) {
-          const int r = r0 + i * 16;
-          float4 y;
-          y.x = to_tf32(fmaxf(fmaf(x[i].x, sc.x, sh.x), 0.f));
-          y.y = to_tf32(fmaxf(fmaf(x[i].y, sc.y, sh.y), 0.f));
-          y.z = to_tf32(fmaxf(fmaf(x[i].z, sc.z, sh.z), 0.f));
-          y.w = to_tf32(fmaxf(fmaf(x[i].w, sc.w, sh.w), 0.f));
-          base[r * 8 + (chunk ^ (r & 7))] = y;
-        }
+        for (int j = 0; j < 8; ++j) so[j ^ (i & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         fence_proxy_async();
-        mbar_arrive(&afull[s]);
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+          tma_store_2d(&tmC, sC + buf * (BM * 128), n0 + c, m0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
     }
+    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
@@ -691,46 +646,20 @@ inline void tgemm(Launches& L, cudaStream_t st, const char* tag, const CUtensorM
   kern<<<grid, Pro::kOn ? 320 : 192, SMEM, st>>>(tmA, tmB, nkb, tap, pro, epi);
 }
 
-struct EpiBiasPtr { const float* bias; __device__ void operator()(int, int, float*) const {} };
-
-// persistent GEMM launchers: plain (A by TMA) and pre-activation (A = relu(bn(X)) produced by warps)
+// persistent GEMM launcher: C[M][N] (row-major, leading dimension ldc) = A . W^T + bias, C written with TMA tensor stores
 int sm_count();
-template <int BN, int STAGES, class Epi>
-inline void pgemm(Launches& L, cudaStream_t st, const char* tag, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, Epi epi) {
-  if (M <= 0 || N <= 0) return;
-  auto kern = pgemm_kernel<BN, STAGES, false, false, Epi>;
-  constexpr int SMEM = smem_bytes(BN, STAGES);
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
-  const int tn = (N + BN - 1) / BN, tiles = ((M + BM - 1) / BM) * tn;
-  Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
-  kern<<<tiles < sm_count() ? tiles : sm_count(), 192, SMEM, st>>>(tmA, tmB, tmB, nullptr, 0, nullptr, nullptr, M, tn, tiles, (K + BK - 1) / BK, epi);
-}
-// C[M][N] (row-major, leading dimension ldc) = A . W^T + bias, C written with TMA tensor stores
 template <int BN, int STAGES>
 inline void pgemm_bias_tma(Launches& L, cudaStream_t st, const char* tag, const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int ldc,
                            const float* bias, int M, int N, int K) {
   if (M <= 0 || N <= 0) return;
-  auto kern = pgemm_kernel<BN, STAGES, false, true, EpiBiasPtr>;
+  auto kern = pgemm_kernel<BN, STAGES>;
   constexpr int SMEM = smem_bytes(BN, STAGES) + 1024 + 2 * BM * 128;
   static bool configured = false;
   if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
   const int tn = (N + BN - 1) / BN, tiles = ((M + BM - 1) / BM) * tn;
   CUtensorMap tmC = make_map_2d(C, M, N, ldc, BM, false);
   Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
-  kern<<<tiles < sm_count() ? tiles : sm_count(), 192, SMEM, st>>>(tmA, tmB, tmC, nullptr, 0, nullptr, nullptr, M, tn, tiles, (K + BK - 1) / BK, EpiBiasPtr{bias});
-}
-template <int BN, int STAGES, class Epi>
-inline void pgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const float* X, int lda, const float* bn_a, const float* bn_b,
-                         const CUtensorMap& tmB, int M, int N, int K, Epi epi) {
-  if (M <= 0 || N <= 0) return;
-  auto kern = pgemm_kernel<BN, STAGES, true, false, Epi>;
-  constexpr int SMEM = smem_bytes(BN, STAGES);
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
-  const int tn = (N + BN - 1) / BN, tiles = ((M + BM - 1) / BM) * tn;
-  Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
-  kern<<<tiles < sm_count() ? tiles : sm_count(), 448, SMEM, st>>>(tmB, tmB, tmB, X, lda, bn_a, bn_b, M, tn, tiles, (K + BK - 1) / BK, epi);
+  kern<<<tiles < sm_count() ? tiles : sm_count(), 192, SMEM, st>>>(tmA, tmB, tmC, bias, tn, tiles, (K + BK - 1) / BK);
 }
 
 template <int BN, int STAGES, class Epi>
