@@ -11,6 +11,10 @@ computes on this path:
 * ``frontend.py``  -- librosa 0.11 semantics used by ``melspec.py:9-64`` and
   ``voice_encoder.py:267`` (stft / filters.mel / effects.trim), and the Kaldi
   fbank of ``xvector.py:45-58`` (torchaudio.compliance.kaldi).
+  Also the callers one step out: the torchaudio sinc resampler behind ``get_resampler``
+  (``s3gen.py:41-44``), the 24 kHz prompt mel (``s3gen/utils/mel.py:33-81``) and the S3Tokenizer log-mel
+  (``s3tokenizer/s3tokenizer.py:128-168``), each as a float64 numpy restatement plus a torch version that repeats the
+  reference's own ops.
 * ``nets.py``      -- ``VoiceEncoder.forward/inference`` (``voice_encoder.py:139-199``)
   and ``CAMPPlus.forward`` (``xvector.py:61-423``) written against a plain
   ``state_dict`` with the reference's key names.
@@ -28,4 +32,8 @@ librosa boundary**: librosa 0.11.0 is neither vendored in the reference nor
 installed/installable here, and the reference holds no golden vectors for it.
 It is cross-checked against ``torch.stft`` and
 ``torchaudio.functional.melscale_fbanks`` instead (tests/test_oracle.py).
+The next-row restatements are pinned: the resampler against torchaudio itself (installed; filter bank bit-identical),
+the prompt mel and the S3Tokenizer log-mel against fixtures produced by the verbatim reference files
+(``tests/golden/ref_prompt_mel.npz``, ``ref_s3_log_mel.npz``; ``python -m oracle.make_golden --prompt-mel | --s3``;
+for ``s3tokenizer.py`` the third-party base class ``s3tokenizer.S3TokenizerV2`` is stubbed, ``refload.py``).
 """
