@@ -232,8 +232,9 @@ def test_mode1_north_star_gate(models, mode1, kind):
     # 32-row groups of the GEMM epilogue before they enter the fixed-point reduction (the grouping depends on where the
     # clip's rows fall in the 128-row tiles), and a last-bit difference flips TF32 operand roundings downstream.  The
     # strict fp32 mode is position independent and holds this to 1e-6 / 1e-5 in test_ragged_batch_equals_per_clip_oracle.
+    # (the VoiceEncoder path has no such grouping: bit-identical alone and in the batch, tools/batch_invariance.py)
     ve1, xv1 = emb.embed_wavs([wavs[3]])
-    assert np.abs(ve1[0] - ve[3]).max() < 2e-5 and np.abs(xv1[0] - xv[3]).max() < 5e-4 * scale
+    assert np.array_equal(ve1[0], ve[3]) and np.abs(xv1[0] - xv[3]).max() < 5e-4 * scale
 
 
 def test_mode1_sensitised_weights(models, mode1):
