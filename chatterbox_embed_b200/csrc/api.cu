@@ -271,6 +271,7 @@ int cbx_set_option(cbx_ctx* c, const char* key, int64_t v) {
   else if (k == "overlap" && (v == 0 || v == 1)) c->overlap = v;
   else if (k == "lstm_dbg") c->lstm_dbg = v;
   else if (k == "pdl") c->pdl = v;
+  else if (k == "batch_invariant") c->batch_invariant = v;
   else if (k == "lstm_impl" && (v == 1 || v == 2)) c->lstm_impl = v;
   else if (k == "lstm_trace") c->lstm_trace = v;
   else { c->err = "bad option " + k; return CBX_ERR_ARG; }
@@ -285,6 +286,8 @@ int64_t cbx_get_option(const cbx_ctx* c, const char* key) {
   if (k == "lstm_chunk_partials") return c->lstm_chunk_slots;
   if (k == "mode") return c->mode;
   if (k == "overlap") return c->overlap;
+  if (k == "pdl") return c->pdl;
+  if (k == "batch_invariant") return c->batch_invariant;
   return -1;
 }
 

@@ -49,7 +49,13 @@ struct EpiBiasReluMask {         // out = row is a real frame ? relu(acc + bias)
 // run to run (with float atomics every run drew a different sample of the TF32 rounding noise: the max-abs error of the
 // ragged W1 batch wandered between 5e-4 and 2.3e-3).  Resolution 6e-8, range +-5e11 per column and segment.
 constexpr float kSegFix = 16777216.f;                 // 2^24
-struct EpiBiasReluMaskSegsum {
+// kExact (option "batch_invariant"): the warp's partial sums are exact too -- every value is split into its integer part and a
+// 24-bit fraction and each part is added across the warp with redux.sync (32-bit integer adds) -- so the sum of a segment's rows
+// does not depend on which rows share a warp and a clip's x-vector is bit-identical alone, in any batch and at any chunking
+// (the VoiceEncoder embedding already is).  64 redux.sync per segment and chunk cost ~0.5 ms per step (a 64-bit shuffle butterfly
+// spills and costs 1.1 ms), so the default is the fp32 butterfly: reproducible run to run, position dependent within 1.2e-4.
+template <bool kExact>
+struct EpiBiasReluMaskSegsumT {
   float* out; int ld; const float* bias; const int32_t* row_seg; unsigned long long* seg_sum; int M;     // out == nullptr: the kernel stores (TMA)
   __device__ void operator()(int m, int n0, float* v) const {
     const unsigned full = 0xffffffffu;
@@ -72,6 +78,20 @@ struct EpiBiasReluMaskSegsum {
       const int s = __shfl_sync(full, seg, __ffs(rem) - 1);
       rem &= ~__ballot_sync(full, seg == s);
       const bool mine = seg == s;
+      if constexpr (kExact) {
+        int keep_hi = 0; unsigned keep_lo = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = mine ? fminf(v[i], 1.0e9f) : 0.f;                  // activations are >= 0 and far below 2^31
+          const int hi = __float2int_rd(x);
+          const unsigned lo = __float2uint_rn((x - (float)hi) * kSegFix);    // exact: < 2^24, or 2^24 after rounding (still exact in the sum)
+          const int sh = __reduce_add_sync(full, hi);
+          const unsigned sl = __reduce_add_sync(full, lo);
+          if (lane == i) { keep_hi = sh; keep_lo = sl; }
+        }
+        atomicAdd(seg_sum + (size_t)s * kBnC + n0 + lane, (unsigned long long)(((long long)keep_hi << 24) + (long long)keep_lo));
+        continue;
+      }
       float a[16], b[8], c[4], d[2];
       {
         const bool up = lane & 16;
@@ -103,6 +123,9 @@ struct EpiBiasReluMaskSegsum {
     }
   }
 };
+
+using EpiBiasReluMaskSegsum = EpiBiasReluMaskSegsumT<false>;
+using EpiBiasReluMaskSegsumExact = EpiBiasReluMaskSegsumT<true>;
 
 struct EpiMask {                 // out = row is a real frame ? acc : 0                (transit layers)
   float* out; int ld; const int32_t* row_clip; int M;           // out == nullptr: the kernel stores (TMA)

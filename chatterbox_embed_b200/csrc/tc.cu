@@ -55,7 +55,7 @@ using namespace cbx;
 
 // same functor under a type of this translation unit: the kernel template is then instantiated HERE (next to the trace pointer
 // this file sets) instead of being merged with xv.cu's instantiation
-namespace { struct EpiSegsumProbe : tc::EpiBiasReluMaskSegsum {}; }
+namespace { struct EpiSegsumProbe : tc::EpiBiasReluMaskSegsum { }; }
 
 extern "C" int cbx_test_tgemm(cbx_ctx* c, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc,
                               int M, int N, int K, const float* bias, const float* pro_a, const float* pro_b, int variant,

@@ -467,7 +467,10 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     }
     for (int i = 0; i < kLayers[b]; ++i, ++li) {
       const DenseLayerW& D = W.dense[li];
-      if (tcm)
+      if (tcm && c->batch_invariant)
+        tc::tgemm_bnrelu<128, 2>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
+                                 tc::EpiBiasReluMaskSegsumExact{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
+      else if (tcm)
         tc::tgemm_bnrelu<128, 2>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
                                  tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
       else

@@ -84,7 +84,10 @@ const char* cbx_version(void);
  * overlap: 1 (default) = with both encoders requested, CAMPPlus runs on an internal second stream beside the
  * VoiceEncoder chain (forked from / joined into the caller's stream).  pdl: 1 (default) = the CAMPPlus convolution and
  * dense-layer chains use programmatic dependent launch (a kernel sets up while its predecessor drains).  overlap and pdl
- * are scheduling only: results are bit-identical with either off.  ("lstm_impl", "lstm_dbg", "lstm_trace" select / probe
+ * are scheduling only: results are bit-identical with either off.  batch_invariant: 1 = the x-vector of a clip is
+ * bit-identical whatever else is in the batch and however the call is chunked (exact warp-level segment sums, ~3 %
+ * slower); 0 (default) = reproducible from run to run, position dependent within ~1e-4 (the VoiceEncoder embedding is
+ * batch invariant either way).  ("lstm_impl", "lstm_dbg", "lstm_trace" select / probe
  * the recurrence kernel and are for the tools under tools/.) */
 int cbx_set_option(cbx_ctx* ctx, const char* key, int64_t value);
 int64_t cbx_get_option(const cbx_ctx* ctx, const char* key);

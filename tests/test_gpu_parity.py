@@ -307,6 +307,34 @@ def test_mode1_results_are_reproducible(models, mode1):
         assert np.array_equal(ve, ve0) and np.array_equal(xv, xv0)
 
 
+def test_batch_invariant_option(models, mode1):
+    """With batch_invariant = 1 a clip's embeddings are bit-identical alone, inside a batch, in the reversed batch and under a
+    different chunking (exact segment sums); the default keeps the x-vector within 5e-4 * scale of that."""
+    sdv, sdc, emb = _emb(models, "W1")
+    lens = [int(x) for x in synth.ragged_lengths(10)] + [16000, 25599]
+    wavs = [synth.clip(i, n) for i, n in enumerate(lens)]
+    ctx = _lib.context(0)
+    fast = emb.embed_wavs(wavs)
+    old = {k: ctx.get_option(k) for k in ("xv_chunk_rows", "fcm_chunk_rows", "lstm_chunk_partials")}
+    try:
+        ctx.set_option("batch_invariant", 1)
+        ve, xv = emb.embed_wavs(wavs)
+        rve, rxv = emb.embed_wavs(wavs[::-1])
+        assert np.array_equal(rve[::-1], ve) and np.array_equal(rxv[::-1], xv)
+        for i in (0, 5, 11):
+            v1, x1 = emb.embed_wavs([wavs[i]])
+            assert np.array_equal(v1[0], ve[i]) and np.array_equal(x1[0], xv[i])
+        ctx.set_option("xv_chunk_rows", 900); ctx.set_option("fcm_chunk_rows", 400); ctx.set_option("lstm_chunk_partials", 7)
+        cve, cxv = emb.embed_wavs(wavs)
+        assert np.array_equal(cve, ve) and np.array_equal(cxv, xv)
+    finally:
+        ctx.set_option("batch_invariant", 0)
+        for k, v in old.items():
+            ctx.set_option(k, v)
+    scale = max(1.0, float(np.abs(xv).max()))
+    assert np.array_equal(fast[0], ve) and np.abs(fast[1] - xv).max() < 5e-4 * scale
+
+
 def test_launch_options_do_not_change_results(models, mode1):
     """Programmatic dependent launch (kernels start while their predecessor drains and prefetch what is already final) and
     the two-stream overlap are scheduling only: bit-identical embeddings with either switched off."""
