@@ -195,6 +195,11 @@ int load_ve(cbx_ctx* c, const std::map<std::string, std::pair<const float*, int6
 int load_xv(cbx_ctx* c, const std::map<std::string, std::pair<const float*, int64_t>>& t);
 int build_frontend_tables(cbx_ctx* c);
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: set it once per (kernel, device), so that several
+// contexts on several GPUs of one process all get it (tc.cu)
+void ensure_max_smem(const void* kernel, int bytes);
+template <class K> inline void ensure_max_smem(K kernel, int bytes) { ensure_max_smem(reinterpret_cast<const void*>(kernel), bytes); }
+
 // ---- workspace carving ------------------------------------------------------------------------
 struct Carver {
   char* base; int64_t off = 0; int64_t cap;

@@ -291,8 +291,7 @@ void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const 
   if (need() > kSmemMax) p.ngroups = 1;             // the stride-2 convs of layer 1: two 26 KB parity planes per stage
   if (need() > kSmemMax) p.nstages = 2;
   const int smem = need();
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(fcm_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax); configured = true; }
+  ensure_max_smem(fcm_conv_kernel, kSmemMax);
   int nsm = 148;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
   const int grid = p.ntiles < nsm ? p.ntiles : nsm;

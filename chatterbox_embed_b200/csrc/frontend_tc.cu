@@ -275,8 +275,7 @@ void launch(cbx_ctx* c, cudaStream_t st, const char* tag, const CUtensorMap& hi0
             const CUtensorMap& lo1, const float* pcm, Rows rf, const float* bintab, float* out, int rows) {
   if (rows <= 0) return;
   auto kern = dftmel_kernel<Rows, NB1, NMEL, LOG>;
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); configured = true; }
+  ensure_max_smem(kern, SMEM_BYTES);
   Scope sc(c->launches, st, tag, 3.0 * 2.0 * rows * (256 + NB1) * KTOT, 4.0 * rows * (160 + NMEL));   // one hop of PCM in, one feature row out
   kern<<<(rows + BM - 1) / BM, 192, SMEM_BYTES, st>>>(hi0, lo0, hi1, lo1, pcm, rf, reinterpret_cast<const float4*>(bintab), out, rows);
 }

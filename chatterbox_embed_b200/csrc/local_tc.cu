@@ -158,8 +158,7 @@ void run_local_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmU, cons
                        int col0, const float* gate, const int32_t* row_seg, bool pdl) {
   using namespace lconv;
   if (M <= 0) return;
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(local_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); configured = true; }
+  ensure_max_smem(local_conv_kernel, SMEM_BYTES);
   Params p{M, dil, col0, (M + 127) / 128, gate, row_seg};
   const int grid = p.ntiles < tc::sm_count() ? p.ntiles : tc::sm_count();
   Scope sc(c->launches, st, "dense_local_gemm", 2.0 * M * kGrowth * 3 * kBnC, 4.0 * M * (kBnC + kGrowth));

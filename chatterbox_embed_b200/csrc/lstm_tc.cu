@@ -610,11 +610,7 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
 void run_lstm_rec_tc(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
                      int n_slots, cudaStream_t st) {
   if (n_slots <= 0) return;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(lstm::lstm_rec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::SMEM_BYTES);
-    configured = true;
-  }
+  ensure_max_smem(lstm::lstm_rec_tc_kernel, lstm::SMEM_BYTES);
   lstm::Params p{xw, slot_row, whh_perm, hseq, hlast, n_slots, (long long*)c->lstm_trace, (int)c->lstm_dbg};
   const int tiles = (n_slots + lstm::TILE - 1) / lstm::TILE;
   Scope sc(c->launches, st, "lstm_rec_tc_kernel", 2.0 * n_slots * kVePartial * kVeHidden * kVeGates, 4.0 * n_slots * kVePartial * (kVeGates + kVeHidden));
@@ -648,12 +644,8 @@ int lstm_padded_slots(int n_slots) { return (n_slots + lstm::TILE - 1) / lstm::T
 void run_lstm_rec_tc2(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
                       int n_slots, cudaStream_t st) {
   if (n_slots <= 0) return;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(lstm::lstm_rec_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::SMEM_BYTES);
-    cudaFuncSetAttribute(lstm::lstm_rec_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::SMEM_BYTES);
-    configured = true;
-  }
+  ensure_max_smem(lstm::lstm_rec_tc2_kernel<true>, lstm::SMEM_BYTES);
+  ensure_max_smem(lstm::lstm_rec_tc2_kernel<false>, lstm::SMEM_BYTES);
   const int tiles = (n_slots + lstm::TILE - 1) / lstm::TILE;
   const int64_t rows = (int64_t)tiles * lstm::TILE * kVePartial;
   CUtensorMap tmH = tc::make_map_2d(hseq, rows, kVeHidden, kVeHidden, lstm::NSUB, false);

@@ -76,8 +76,7 @@ extern "C" int cbx_project(cbx_ctx* c, const float* x_dev, int64_t n, int in_dim
   cudaSetDevice(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = (size_t)proj::ROWS * (in_dim + 1) * sizeof(float);
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(proj::project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, proj::ROWS * (proj::MAX_K + 1) * 4); configured = true; }
+  ensure_max_smem(proj::project_kernel, proj::ROWS * (proj::MAX_K + 1) * 4);
   const long long blocks = (n + proj::ROWS - 1) / proj::ROWS;
   if (blocks > 0x7fffffffLL) { c->err = "cbx_project: too many rows"; return CBX_ERR_ARG; }
   // few rows: spread the output features over more blocks so a single profile still fills the SMs

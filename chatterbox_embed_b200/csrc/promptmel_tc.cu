@@ -285,7 +285,7 @@ static int build_tables(cbx_ctx* c) {
   T.hi = T.blob; T.lo = T.blob + nmat; T.bins = T.blob + 2 * nmat;
   T.tm_hi = tc::make_map_2d(T.hi, NCOLS, NFFT, NFFT, 256, false);
   T.tm_lo = tc::make_map_2d(T.lo, NCOLS, NFFT, NFFT, 256, false);
-  CBX_CUDA_OK(c, cudaFuncSetAttribute(promptmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  ensure_max_smem(promptmel_kernel, SMEM_BYTES);
   T.ready = true;
   return CBX_OK;
 }

@@ -145,8 +145,7 @@ int cbx_resample(cbx_ctx* c, const float* x_dev, const int64_t* in_offsets_host,
   const size_t tiled_smem = ((size_t)(kRsFrames - 1) * orig + taps) * sizeof(float);
   const bool tiled = nnew >= 32 && tiled_smem <= 200 * 1024;
   if (tiled) {
-    static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(resample_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); configured = true; }
+    ensure_max_smem(resample_tiled_kernel, 200 * 1024);
   }
   for (int z0 = 0; z0 < n_clips; z0 += 65535) {          // grid.y limit
     const int nz = std::min(65535, n_clips - z0);

@@ -7,9 +7,21 @@
 
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 
 namespace cbx {
+
+void ensure_max_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;          // (kernel, device) -> bytes granted
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  int& have = done[{kernel, dev}];
+  if (have < bytes) { cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); have = bytes; }
+}
+
 namespace tc {
 
 EncodeTiledFn encode_fn() {

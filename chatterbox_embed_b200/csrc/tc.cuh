@@ -638,8 +638,7 @@ inline void tgemm(Launches& L, cudaStream_t st, const char* tag, const CUtensorM
   if (M <= 0 || N <= 0) return;
   auto kern = tgemm_kernel<BN, STAGES, Pro, Epi>;
   constexpr int SMEM = smem_bytes(BN, STAGES);
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
+  ensure_max_smem(kern, SMEM);
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
   const int nkb = tap.cpb * ntaps;
   Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * (K / ntaps) + (double)M * N));   // algorithmic bytes: A once + C
@@ -654,8 +653,7 @@ inline void pgemm_bias_tma(Launches& L, cudaStream_t st, const char* tag, const 
   if (M <= 0 || N <= 0) return;
   auto kern = pgemm_kernel<BN, STAGES>;
   constexpr int SMEM = smem_bytes(BN, STAGES) + 1024 + 2 * BM * 128;
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
+  ensure_max_smem(kern, SMEM);
   const int tn = (N + BN - 1) / BN, tiles = ((M + BM - 1) / BM) * tn;
   CUtensorMap tmC = make_map_2d(C, M, N, ldc, BM, false);
   Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
@@ -669,8 +667,7 @@ inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const fl
   auto kern = tgemm_bnrelu_kernel<BN, STAGES, Epi>;
   constexpr int SMEM = smem_bytes(BN, STAGES) + 2 * 1024 * 4;      // + BN scale / shift of up to 1024 columns
   if (K > 1024) { fprintf(stderr, "libcbx: tgemm_bnrelu supports K <= 1024\n"); return; }
-  static bool configured = false;
-  if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM); configured = true; }
+  ensure_max_smem(kern, SMEM);
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
   CUtensorMap tmC = make_map_2d(C, M, N, ldc, BM, false);
