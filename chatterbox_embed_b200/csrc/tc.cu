@@ -93,7 +93,7 @@ extern "C" int cbx_test_tgemm(cbx_ctx* c, const float* A, int64_t lda, const flo
   } else if (variant == 2) {
     CUtensorMap tmB = tc::make_map_2d(W, N, K, ldw, 32, true);
     tc::tgemm<32, 4>(c->launches, st, "test_tgemm_n32", tmA, tmB, M, N, K, tap, 1, tc::NoPrologue{}, epi);
-  } else if (variant == 6) {    // set / clear the timeline probe of the pre-activation GEMM: C = trace buffer (8 x u64 per CTA) or NULL
+  } else if (variant == 6) {    // set / clear the timeline probe of the pre-activation GEMM: C = trace buffer (16 x u64 per CTA) or NULL
     unsigned long long* p = reinterpret_cast<unsigned long long*>(C);
     CBX_CUDA_OK(c, cudaMemcpyToSymbol(tc::g_gemm_trace, &p, sizeof(p)));
   } else if (variant == 7) {    // the bottleneck layer's production epilogue (bias + ReLU + mask + segment sums, TMA-stored C)
