@@ -50,3 +50,38 @@ def raise_for_status(status: np.ndarray, flags: int) -> None:
         if bad.size:
             raise AssertionError(f"choose a window size 400 that is [2, len]: clips {bad.tolist()[:8]} are shorter than one "
                                  "Kaldi frame (torchaudio kaldi.py:142-144)")
+
+
+class WeightSync:
+    """Mixin for the drop-in modules: push the module's tensors into the libcbx context when they change, without walking the
+    module tree on every call (``state_dict()`` of CAMPPlus is ~940 tensors: 2-3 ms of Python per call, more than the GPU
+    work of a single clip).  The tensor list is cached and dropped whenever the module is moved / cast (``_apply``) or loaded
+    (``load_state_dict``); in-place edits are seen through the tensors' version counters."""
+
+    def _cbx_tensors(self):
+        cache = self.__dict__.get("_cbx_cache")
+        if cache is None:
+            cache = [(k, v) for k, v in self.state_dict().items() if self._cbx_wants(k)]
+            self.__dict__["_cbx_cache"] = cache
+        return cache
+
+    def _cbx_fingerprint(self, dev):
+        ts = self._cbx_tensors()
+        return (dev, id(self), len(ts), sum(v._version for _, v in ts), ts[0][1].data_ptr(), ts[-1][1].data_ptr())
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_cbx_cache", None)
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.__dict__.pop("_cbx_cache", None)
+        return super().load_state_dict(*args, **kwargs)
+
+    def _cbx_sync(self, which: int, slot: str):
+        dev = device_index(self.device)
+        ctx = _lib.context(dev)
+        key = self._cbx_fingerprint(dev)
+        if ctx.__dict__.get(slot) != key:
+            ctx.load_weights(which, {k: v.detach().float().cpu().numpy() for k, v in self._cbx_tensors()})
+            ctx.__dict__[slot] = key
+        return ctx

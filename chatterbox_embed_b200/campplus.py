@@ -92,7 +92,7 @@ def _init(shape, kind):
     return torch.tensor(0, dtype=torch.long)
 
 
-class CAMPPlus(nn.Module):
+class CAMPPlus(_host.WeightSync, nn.Module):
     def __init__(self, feat_dim=80, embedding_size=192, growth_rate=32, bn_size=4, init_channels=128,
                  config_str="batchnorm-relu", memory_efficient=True, output_level="segment", **kwargs):
         super().__init__()
@@ -126,15 +126,12 @@ class CAMPPlus(nn.Module):
     def device(self):
         return next(self.parameters()).device
 
+    @staticmethod
+    def _cbx_wants(key: str) -> bool:
+        return not key.endswith("num_batches_tracked")
+
     def _ctx(self) -> _lib.Context:
-        dev = _host.device_index(self.device)
-        ctx = _lib.context(dev)
-        sd = {k: v for k, v in self.state_dict().items() if not k.endswith("num_batches_tracked")}
-        key = (dev, id(self), tuple((k, v.data_ptr(), v._version) for k, v in sd.items()))
-        if ctx.__dict__.get("_xv_key") != key:
-            ctx.load_weights(1, {k: v.detach().float().cpu().numpy() for k, v in sd.items()})
-            ctx.__dict__["_xv_key"] = key
-        return ctx
+        return self._cbx_sync(1, "_xv_key")
 
     def _clips(self, audio_list) -> List[torch.Tensor]:
         if torch.is_tensor(audio_list):

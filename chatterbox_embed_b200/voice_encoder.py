@@ -23,7 +23,7 @@ def get_num_wins(n_frames: int, step: int, min_coverage: float, hp: VoiceEncConf
     return _lib.num_wins(n_frames, step, min_coverage)
 
 
-class VoiceEncoder(nn.Module):
+class VoiceEncoder(_host.WeightSync, nn.Module):
     def __init__(self, hp=VoiceEncConfig()):
         super().__init__()
         check_baked(hp)
@@ -41,15 +41,12 @@ class VoiceEncoder(nn.Module):
         return next(self.parameters()).device
 
     # -- weights -> libcbx --------------------------------------------------------------------------------------
+    @staticmethod
+    def _cbx_wants(key: str) -> bool:
+        return key.startswith(("lstm.", "proj."))
+
     def _ctx(self) -> _lib.Context:
-        dev = _host.device_index(self.device)
-        ctx = _lib.context(dev)
-        params = {k: v for k, v in self.state_dict().items() if k.startswith(("lstm.", "proj."))}
-        key = (dev, id(self), tuple((k, v.data_ptr(), v._version) for k, v in params.items()))
-        if ctx.__dict__.get("_ve_key") != key:
-            ctx.load_weights(0, {k: v.detach().float().cpu().numpy() for k, v in params.items()})
-            ctx.__dict__["_ve_key"] = key
-        return ctx
+        return self._cbx_sync(0, "_ve_key")
 
     # -- reference API ---------------------------------------------------------------------------------------------
     def forward(self, mels: torch.FloatTensor):

@@ -335,6 +335,27 @@ def test_batch_invariant_option(models, mode1):
     assert np.array_equal(fast[0], ve) and np.abs(fast[1] - xv).max() < 5e-4 * scale
 
 
+def test_weight_updates_are_picked_up(mode1):
+    """The modules push their tensors to libcbx lazily and cache the tensor list: in-place edits (version counters), a new
+    load_state_dict and a fresh module must all be seen."""
+    sdv, sdc = weights.ve_state_dict("W1"), weights.campplus_state_dict("W1")
+    ve = VoiceEncoder(); ve.load_state_dict(sdv); ve = ve.to(DEV).eval()
+    cp = CAMPPlus(); cp.load_state_dict(sdc); cp = cp.to(DEV).eval()
+    w = synth.clip(3, 32000)
+    wt = torch.from_numpy(w).to(DEV)[None]
+    v0, x0 = ve.embeds_from_wavs([w], 16000), cp.inference(wt).cpu().numpy()
+    with torch.no_grad():
+        ve.proj.weight.mul_(-1.0)                                          # in-place edit
+        cp.state_dict()["xvector.dense.linear.weight"].mul_(2.0)
+    v1, x1 = ve.embeds_from_wavs([w], 16000), cp.inference(wt).cpu().numpy()
+    assert not np.allclose(np.nan_to_num(v1), v0) and not np.allclose(x1, x0)
+    ve.load_state_dict(sdv); cp.load_state_dict(sdc)                       # back to the original weights
+    assert np.array_equal(ve.embeds_from_wavs([w], 16000), v0) and np.array_equal(cp.inference(wt).cpu().numpy(), x0)
+    ve2 = VoiceEncoder(); ve2.load_state_dict(weights.ve_state_dict("W2")); ve2 = ve2.to(DEV).eval()      # another module (W2: different LSTM weights) takes over the context
+    assert not np.array_equal(ve2.embeds_from_wavs([w], 16000), v0)
+    assert np.array_equal(ve.embeds_from_wavs([w], 16000), v0)
+
+
 def test_launch_options_do_not_change_results(models, mode1):
     """Programmatic dependent launch (kernels start while their predecessor drains and prefetch what is already final) and
     the two-stream overlap are scheduling only: bit-identical embeddings with either switched off."""

@@ -20,3 +20,23 @@ print(f"both encoders, one call (SpeakerEmbedder)         {t(lambda: emb.embed_w
 for n in (8, 32):
     ws = [synth.clip(i, 160000) for i in range(n)]
     print(f"both encoders, {n:2d} x 10 s clips in one call         {t(lambda: emb.embed_wavs(ws), 10):.2f} ms")
+
+# where does a single-clip call spend its time: host enqueue (cbx_embed returns) vs GPU completion
+from chatterbox_embed_b200 import _lib
+ctx = _lib.context(0)
+lens = [160000]; off = np.array([0, 160000], np.int64)
+pcm = torch.from_numpy(w).to(dev)
+flags = _lib.DO_VE | _lib.DO_XV
+ws = torch.empty(ctx.workspace_bytes(lens, 77, 0.8, flags), dtype=torch.uint8, device=dev)
+veo = torch.empty(1, 256, device=dev); xvo = torch.empty(1, 192, device=dev); st_ = torch.zeros(1, dtype=torch.int32, device=dev)
+stream = torch.cuda.Stream()
+for key, val in (("overlap", 1), ("overlap", 0)):
+    ctx.set_option(key, val)
+    enq, tot = [], []
+    for _ in range(25):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        ctx.embed(pcm.data_ptr(), off, 20.0, 77, 0.8, veo.data_ptr(), xvo.data_ptr(), st_.data_ptr(), ws.data_ptr(), ws.numel(), stream.cuda_stream, flags)
+        t1 = time.perf_counter(); torch.cuda.synchronize(); t2 = time.perf_counter()
+        enq.append((t1 - t0) * 1e3); tot.append((t2 - t0) * 1e3)
+    print(f"cbx_embed, one clip, {key}={val}: host enqueue {np.median(enq[5:]):.2f} ms, until done {np.median(tot[5:]):.2f} ms")
+ctx.set_option("overlap", 1)
