@@ -44,28 +44,26 @@ class S3TokenizerFrontend:
         self.n_fft = 400
         self.quantizer = quantizer
 
+    @staticmethod
+    def _as_batch(wav) -> torch.Tensor:
+        """numpy or tensor, (L,) or (B, L) -> tensor (B, L)."""
+        t = torch.from_numpy(wav) if isinstance(wav, np.ndarray) else wav
+        return t.unsqueeze(0) if t.dim() == 1 else t
+
     def pad(self, wavs, sr) -> List[torch.Tensor]:
-        """s3tokenizer.py:52-74: zero-pad every wav to a multiple of 40 ms."""
-        processed_wavs = []
+        """s3tokenizer.py:52-74: every wav zero-padded on the right to a whole number of 40 ms tokens (25 tokens/s), with the
+        reference's float arithmetic (ceil of length / sr * 25, then int of tokens * (sr / 25))."""
+        out = []
         for wav in wavs:
-            if isinstance(wav, np.ndarray):
-                wav = torch.from_numpy(wav)
-            if wav.dim() == 1:
-                wav = wav.unsqueeze(0)
-            n_tokens = np.ceil((wav.shape[1] / sr) * S3_TOKEN_RATE)
-            intended_wav_len = int(n_tokens * (sr / S3_TOKEN_RATE))
-            processed_wavs.append(torch.nn.functional.pad(wav, (0, intended_wav_len - wav.shape[-1]), mode="constant", value=0))
-        return processed_wavs
+            t = self._as_batch(wav)
+            tokens = np.ceil((t.shape[1] / sr) * S3_TOKEN_RATE)
+            want = int(tokens * (sr / S3_TOKEN_RATE))
+            out.append(torch.nn.functional.pad(t, (0, want - t.shape[-1]), mode="constant", value=0))
+        return out
 
     def _prepare_audio(self, wavs):
-        processed_wavs = []
-        for wav in wavs:
-            if isinstance(wav, np.ndarray):
-                wav = torch.from_numpy(wav)
-            if wav.dim() == 1:
-                wav = wav.unsqueeze(0)
-            processed_wavs.append(wav)
-        return processed_wavs
+        """s3tokenizer.py:76-87: a list of (1, L) tensors."""
+        return [self._as_batch(w) for w in wavs]
 
     @torch.no_grad()
     def log_mel_spectrogram(self, audio: torch.Tensor, padding: int = 0) -> torch.Tensor:

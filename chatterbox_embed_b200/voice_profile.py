@@ -40,14 +40,12 @@ class VoiceProfile:
 
     @classmethod
     def load(cls, path: str, device: str = "cpu") -> "VoiceProfile":
+        """s3gen.py:447-456: the pickled dict back into a profile (optional keys stay None)."""
         data = np.load(path, allow_pickle=True).item()
-        return cls(
-            embedding=torch.tensor(data["embedding"]).to(device),
-            prompt_feat=torch.tensor(data["prompt_feat"]).to(device) if "prompt_feat" in data else None,
-            prompt_feat_len=data.get("prompt_feat_len"),
-            prompt_token=torch.tensor(data["prompt_token"]).to(device) if "prompt_token" in data else None,
-            prompt_token_len=torch.tensor(data["prompt_token_len"]).to(device) if "prompt_token_len" in data else None,
-        )
+        def tensor(key):
+            return torch.tensor(data[key]).to(device) if key in data else None
+        return cls(embedding=tensor("embedding"), prompt_feat=tensor("prompt_feat"), prompt_feat_len=data.get("prompt_feat_len"),
+                   prompt_token=tensor("prompt_token"), prompt_token_len=tensor("prompt_token_len"))
 
     def save(self, path: str):
         np.save(path, profile_dict(self))
@@ -70,16 +68,13 @@ def profile_dict(profile: VoiceProfile, ve_embedding: Optional[torch.Tensor] = N
 
 
 def load_voice_profile(path: str, device="cpu") -> VoiceProfile:
-    """tts.py:555-586 / vc.py:676-708."""
+    """tts.py:555-586 / vc.py:676-708: like VoiceProfile.load, plus the ``ve_embedding`` attribute (None for old files)."""
     data = np.load(path, allow_pickle=True).item()
-    profile = VoiceProfile(
-        embedding=torch.from_numpy(data["embedding"]).to(device),
-        prompt_feat=torch.from_numpy(data["prompt_feat"]).to(device) if "prompt_feat" in data else None,
-        prompt_feat_len=data.get("prompt_feat_len"),
-        prompt_token=torch.from_numpy(data["prompt_token"]).to(device) if "prompt_token" in data else None,
-        prompt_token_len=torch.from_numpy(data["prompt_token_len"]).to(device) if "prompt_token_len" in data else None,
-    )
-    profile.ve_embedding = torch.from_numpy(data["ve_embedding"]).to(device) if "ve_embedding" in data else None
+    def tensor(key):
+        return torch.from_numpy(data[key]).to(device) if key in data else None
+    profile = VoiceProfile(embedding=tensor("embedding"), prompt_feat=tensor("prompt_feat"), prompt_feat_len=data.get("prompt_feat_len"),
+                           prompt_token=tensor("prompt_token"), prompt_token_len=tensor("prompt_token_len"))
+    profile.ve_embedding = tensor("ve_embedding")
     return profile
 
 
