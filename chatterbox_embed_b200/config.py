@@ -1,30 +1,19 @@
-"""Hyper-parameters of the VoiceEncoder path (mirror of voice_encoder/config.py:1-18).  The CUDA kernels are
-compiled for exactly these values; constructing a VoiceEncoder with other values raises."""
+"""Hyper-parameters of the VoiceEncoder path: the same attribute names and values as the reference's ``VoiceEncConfig``
+(voice_encoder/config.py:1-18).  The sm_100a kernels are compiled for exactly the values in ``_BAKED``; constructing a
+VoiceEncoder with other values raises."""
 
+# What the kernels are built for, grouped by the stage that consumes it.
+_BAKED = dict(
+    # front end (ve.cu / frontend_tc.cu): 16 kHz, periodic Hann 400, hop 160, 40 Slaney mels over 0..8000 Hz, power spectrum
+    sample_rate=16000, n_fft=400, win_size=400, hop_size=160, num_mels=40, fmin=0, fmax=8000,
+    preemphasis=0., mel_power=2.0, mel_type="amp", normalized_mels=False,
+    # recurrence (lstm_tc.cu) and projection (project.cu): 160-frame partials, 3 x 256 LSTM, 256-d embedding behind a ReLU
+    ve_partial_frames=160, ve_hidden_size=256, speaker_embed_size=256, ve_final_relu=True)
 
-class VoiceEncConfig:
-    num_mels = 40
-    sample_rate = 16000
-    speaker_embed_size = 256
-    ve_hidden_size = 256
-    flatten_lstm_params = False
-    n_fft = 400
-    hop_size = 160
-    win_size = 400
-    fmax = 8000
-    fmin = 0
-    preemphasis = 0.
-    mel_power = 2.0
-    mel_type = "amp"
-    normalized_mels = False
-    ve_partial_frames = 160
-    ve_final_relu = True
-    stft_magnitude_min = 1e-4
+# Attributes the reference class also carries and this path never reads (a torch LSTM detail; the floor of the dB mel type).
+_UNUSED = dict(flatten_lstm_params=False, stft_magnitude_min=1e-4)
 
-
-_BAKED = dict(num_mels=40, sample_rate=16000, speaker_embed_size=256, ve_hidden_size=256, n_fft=400, hop_size=160,
-              win_size=400, fmax=8000, fmin=0, preemphasis=0., mel_power=2.0, mel_type="amp", normalized_mels=False,
-              ve_partial_frames=160, ve_final_relu=True)
+VoiceEncConfig = type("VoiceEncConfig", (), {**_BAKED, **_UNUSED, "__doc__": "Class attributes as in voice_encoder/config.py:1-18."})
 
 
 def check_baked(hp) -> None:

@@ -133,7 +133,7 @@ fcm_conv_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__
     // ===== epilogue: thread = output position i = (t, f') of the tile (f' >= F_out are the padding positions).  The output
     // tile leaves through a staging buffer and ONE tensor store whose box is clipped by the tensor's bounds (padding
     // positions / rows past the end).  (An earlier version brought the residual tile in as one more TMA plane of the input
-    // stage, read after the accumulator barrier only; its results were not reproducible from run to run -- tools/determinism.py.)
+    // stage, read after the accumulator barrier only; its results were not reproducible from run to run -- tests/tools/determinism.py.)
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;                    // epilogue group = accumulator = parity of the CTA's tile counter
     const int i = q * 32 + lane;

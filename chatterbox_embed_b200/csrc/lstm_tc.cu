@@ -336,7 +336,7 @@ struct Params2 {
   float* hseq;                // tiled time-major [tiles*160*224][256] (tf32-rounded h), also the exchange medium
   float* hlast;               // [n_slots][256] or nullptr
   int n_slots;
-  long long* trace;           // [160][2][8] clock64 stamps of CTA 0 when non-null (tools/lstm_trace.py)
+  long long* trace;           // [160][2][8] clock64 stamps of CTA 0 when non-null (tests/tools/lstm_trace.py)
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {

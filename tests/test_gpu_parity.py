@@ -232,7 +232,7 @@ def test_mode1_north_star_gate(models, mode1, kind):
     # 32-row groups of the GEMM epilogue before they enter the fixed-point reduction (the grouping depends on where the
     # clip's rows fall in the 128-row tiles), and a last-bit difference flips TF32 operand roundings downstream.  The
     # strict fp32 mode is position independent and holds this to 1e-6 / 1e-5 in test_ragged_batch_equals_per_clip_oracle.
-    # (the VoiceEncoder path has no such grouping: bit-identical alone and in the batch, tools/batch_invariance.py)
+    # (the VoiceEncoder path has no such grouping: bit-identical alone and in the batch, tests/tools/batch_invariance.py)
     ve1, xv1 = emb.embed_wavs([wavs[3]])
     assert np.array_equal(ve1[0], ve[3]) and np.abs(xv1[0] - xv[3]).max() < 5e-4 * scale
 
@@ -297,7 +297,7 @@ def test_mode1_ragged_config3(models, mode1):
 def test_mode1_results_are_reproducible(models, mode1):
     """Bit-identical embeddings from run to run, with the two encoder chains on two streams and programmatic dependent launch
     on: no float atomics on the path (segment sums are 64-bit fixed-point reductions) and no racy staging.  An earlier build
-    read the FCM residual through a TMA plane and returned a different sample of errors every run (tools/determinism.py)."""
+    read the FCM residual through a TMA plane and returned a different sample of errors every run (tests/tools/determinism.py)."""
     sdv, sdc, emb = _emb(models, "W1")
     lens = [int(x) for x in synth.ragged_lengths(24)]
     wavs = [synth.clip(i, n) for i, n in enumerate(lens)]

@@ -1,6 +1,6 @@
 """Does a clip's embedding depend on what else is in the batch?  (mode 1)"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from chatterbox_embed_b200 import CAMPPlus, VoiceEncoder, _lib, scheduler, synth
 from oracle import weights

@@ -1,7 +1,7 @@
 """Run the device path twice on the same ragged batch and report, stage by stage, whether the intermediate buffers are
-bit-identical.  python tools/determinism.py [mode] [overlap] [pdl]"""
+bit-identical.  python tests/tools/determinism.py [mode] [overlap] [pdl]"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from chatterbox_embed_b200 import CAMPPlus, VoiceEncoder, _lib, synth
 from oracle import weights

@@ -1,6 +1,6 @@
-"""GPU-box check of the tensor-core front-ends against the oracle (stage level) + timing.  python tools/fe_check.py"""
+"""GPU-box check of the tensor-core front-ends against the oracle (stage level) + timing.  python tests/tools/fe_check.py"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from chatterbox_embed_b200 import CAMPPlus, VoiceEncoder, _lib, synth
 from oracle import frontend, weights

@@ -1,8 +1,8 @@
 """Stage-wise parity report of the CUDA path against the oracle (run on the GPU box).
-    python tools/gpu_check.py [W0|W1|W2] [mode]
+    python tests/tools/gpu_check.py [W0|W1|W2] [mode]
 """
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from chatterbox_embed_b200 import CAMPPlus, VoiceEncoder, _lib, synth
 from oracle import frontend, nets, weights

@@ -1,6 +1,6 @@
-"""GPU-box check of the tensor-core LSTM recurrence against the oracle, with timing.  python tools/lstm_check.py"""
+"""GPU-box check of the tensor-core LSTM recurrence against the oracle, with timing.  python tests/tools/lstm_check.py"""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from chatterbox_embed_b200 import VoiceEncoder, _lib
 from oracle import nets, weights

@@ -1,6 +1,6 @@
 """Timing experiments on the tensor-core LSTM recurrence (GPU box)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from chatterbox_embed_b200 import VoiceEncoder, _lib
 from oracle import weights

@@ -1,6 +1,6 @@
 """Clock trace of one CTA of the tensor-core LSTM recurrence v2 (GPU box): where does a step go?"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from chatterbox_embed_b200 import VoiceEncoder, _lib
 from oracle import weights

@@ -1,6 +1,6 @@
 """Stage buffers with programmatic dependent launch on vs off on a SMALL batch (tiny kernels overlap deepest)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from chatterbox_embed_b200 import CAMPPlus, VoiceEncoder, _lib, synth
 from oracle import weights, make_golden

@@ -1,7 +1,7 @@
 """Stress: many batches of varied size through the HOST path (two streams, programmatic dependent launch) must give the same
-bits as the fully serialised configuration (pdl = 0, overlap = 0).  python tools/pdl_stress.py [rounds]"""
+bits as the fully serialised configuration (pdl = 0, overlap = 0).  python tests/tools/pdl_stress.py [rounds]"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from chatterbox_embed_b200 import CAMPPlus, VoiceEncoder, _lib, scheduler, synth
 from oracle import weights

@@ -1,6 +1,6 @@
-"""Repeatability of the mode-1 x-vector error on the ragged config-3 sample (run-to-run, per build).  python tools/ragged_check.py [reps]"""
+"""Repeatability of the mode-1 x-vector error on the ragged config-3 sample (run-to-run, per build).  python tests/tools/ragged_check.py [reps]"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from chatterbox_embed_b200 import CAMPPlus, VoiceEncoder, _lib, scheduler, synth
 from oracle import nets, weights
