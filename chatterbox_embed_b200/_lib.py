@@ -33,6 +33,7 @@ _SIGS = {
     "cbx_plan_clip": (C.c_int, [C.c_int64, C.c_int, C.c_double, _P(ClipPlan)]),
     "cbx_trim_num_frames": (C.c_int64, [C.c_int64]),
     "cbx_clip_cost": (C.c_double, [C.c_int64]),
+    "cbx_partition": (C.c_int, [_P(C.c_int64), C.c_int64, C.c_int, _P(C.c_int32), _P(C.c_int64), _P(C.c_double)]),
     "cbx_create": (C.c_int, [C.c_int, _P(C.c_void_p)]),
     "cbx_destroy": (None, [C.c_void_p]),
     "cbx_last_error": (C.c_char_p, [C.c_void_p]),
@@ -118,6 +119,17 @@ def s3_log_mel_frames(n_samples: int) -> int:
 
 def clip_cost(n_samples: int) -> float:
     return lib().cbx_clip_cost(int(n_samples))
+
+
+def partition(lengths: Sequence[int], world: int):
+    """cbx_partition: (rank_of int32 [n], row_of int64 [n], rank_cost float64 [world])."""
+    lens = np.ascontiguousarray(lengths, dtype=np.int64)
+    rank_of, row_of, cost = np.empty(len(lens), np.int32), np.empty(len(lens), np.int64), np.empty(world, np.float64)
+    rc = lib().cbx_partition(lens.ctypes.data_as(_P(C.c_int64)), len(lens), int(world), rank_of.ctypes.data_as(_P(C.c_int32)),
+                             row_of.ctypes.data_as(_P(C.c_int64)), cost.ctypes.data_as(_P(C.c_double)))
+    if rc:
+        raise CbxError("cbx_partition: bad argument (negative length or world <= 0)")
+    return rank_of, row_of, cost
 
 
 class Context:

@@ -1,7 +1,10 @@
 // Integer host logic of the path: partial/window arithmetic and per-clip frame counts.
 // Follows voice_encoder.py:54-81 (get_num_wins / get_frame_step), melspec.py:50 (T_ve),
 // torchaudio kaldi.py:63-67 (snip_edges frame count) and xvector.py:221-231, 364-372.
+#include <algorithm>
 #include <cmath>
+#include <numeric>
+#include <vector>
 
 #include "cbx_internal.h"
 
@@ -54,6 +57,32 @@ double cbx_clip_cost(int64_t n) {
   if (cbx_plan_clip(n, 77, 0.8, &p) != CBX_OK) return 0.0;
   // LSTM per partial-step, FCM per frame, TDNN stack per T' frame
   return 2703360.0 * 160.0 * (double)p.ve_partials + 4776960.0 * (double)p.xv_frames + 12959744.0 * (double)p.xv_tdnn;
+}
+
+int cbx_partition(const int64_t* n_samples, int64_t n, int world, int32_t* rank_of, int64_t* row_of, double* rank_cost) {
+  if (n < 0 || world <= 0 || (n > 0 && (!n_samples || !rank_of))) return CBX_ERR_ARG;
+  std::vector<double> cost((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    if (n_samples[i] < 0) return CBX_ERR_ARG;
+    cost[(size_t)i] = cbx_clip_cost(n_samples[i]);
+  }
+  // most expensive first (ties keep clip order), dealt out and back again over the ranks: rank k receives positions
+  // k, 2R-1-k, 2R+k, ... of the sorted list, so counts differ by at most one and every pair of rounds evens the cost out
+  std::vector<int64_t> order((size_t)n);
+  std::iota(order.begin(), order.end(), (int64_t)0);
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cost[(size_t)a] > cost[(size_t)b]; });
+  if (rank_cost) std::fill(rank_cost, rank_cost + world, 0.0);
+  for (int64_t pos = 0; pos < n; ++pos) {
+    const int64_t round = pos / world, k = pos % world;
+    const int r = (int)((round & 1) ? world - 1 - k : k);
+    rank_of[order[(size_t)pos]] = r;
+    if (rank_cost) rank_cost[r] += cost[(size_t)order[(size_t)pos]];
+  }
+  if (row_of) {   // a rank keeps its clips in ascending clip order
+    std::vector<int64_t> count((size_t)world, 0);
+    for (int64_t i = 0; i < n; ++i) row_of[i] = count[(size_t)rank_of[i]]++;
+  }
+  return CBX_OK;
 }
 
 const char* cbx_version(void) { return "cbx 0.1 (sm_100a)"; }

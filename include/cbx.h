@@ -72,6 +72,13 @@ int cbx_plan_clip(int64_t n_samples, int step, double min_coverage, cbx_clip_pla
 int64_t cbx_trim_num_frames(int64_t n_samples);
 /* Cost model for rank balancing, in FLOP. */
 double cbx_clip_cost(int64_t n_samples);
+/* Ragged-batch scheduler (north_star (d)): deals n clips of n_samples[i] samples to `world` ranks
+ * so that clip counts differ by at most one and the summed cbx_clip_cost is near equal (clips sorted by cost, most
+ * expensive first, dealt out and back over the ranks).  rank_of[n] receives every clip's rank; row_of[n] (may be NULL)
+ * its row inside that rank's shard, a shard keeping its clips in ascending clip order; rank_cost[world] (may be NULL)
+ * the summed cost per rank.  The reference has no counterpart: its worker embeds one clip per message
+ * (worker_redis.py:162). */
+int cbx_partition(const int64_t* n_samples, int64_t n, int world, int32_t* rank_of, int64_t* row_of, double* rank_cost);
 
 /* ---- context --------------------------------------------------------------------------- */
 int cbx_create(int device, cbx_ctx** out);

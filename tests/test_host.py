@@ -84,6 +84,17 @@ def test_scheduler_partition_balances_and_inverts():
         inv = scheduler.inverse_permutation(shards, len(lens))
         gathered = np.concatenate([np.pad(s, (0, max(sizes) - len(s)), constant_values=-1) for s in shards])
         assert (gathered[inv] == np.arange(len(lens))).all()
+        # the C entry point itself: rank, row inside the rank's shard and summed cost per rank
+        rank_of, row_of, rank_cost = _lib.partition(lens, world)
+        assert (inv == rank_of.astype(np.int64) * max(sizes) + row_of).all()
+        np.testing.assert_allclose(rank_cost, costs, rtol=1e-12)
+    for n in (0, 1, 3):                                   # fewer clips than ranks: empty shards, nothing lost
+        shards = scheduler.partition(lens[:n], 4)
+        assert sorted(np.concatenate(shards).tolist()) == list(range(n)) and max(len(s) for s in shards) <= 1
+    with pytest.raises(_lib.CbxError):
+        _lib.partition([16000, -1], 2)
+    with pytest.raises(_lib.CbxError):
+        _lib.partition([16000], 0)
 
 
 def test_voice_profile_container_round_trip(tmp_path):
