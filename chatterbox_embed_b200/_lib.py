@@ -121,6 +121,12 @@ def clip_cost(n_samples: int) -> float:
     return lib().cbx_clip_cost(int(n_samples))
 
 
+def _i64(values):
+    """Sequence / array of integers -> (keep-alive int64 array, const int64_t* for the C call); no per-element Python."""
+    arr = np.ascontiguousarray(values, dtype=np.int64)
+    return arr, arr.ctypes.data_as(_P(C.c_int64))
+
+
 def partition(lengths: Sequence[int], world: int):
     """cbx_partition: (rank_of int32 [n], row_of int64 [n], rank_cost float64 [world])."""
     lens = np.ascontiguousarray(lengths, dtype=np.int64)
@@ -175,13 +181,13 @@ class Context:
         self._check(lib().cbx_load_weights(self._h, which, n, c_names, c_ptrs, c_num), "cbx_load_weights")
 
     def workspace_bytes(self, lengths: Sequence[int], step: int, min_cov: float, flags: int) -> int:
-        arr = (C.c_int64 * len(lengths))(*[int(x) for x in lengths])
-        return self._check(lib().cbx_workspace_bytes(self._h, len(lengths), arr, step, min_cov, flags), "cbx_workspace_bytes")
+        keep, arr = _i64(lengths)
+        return self._check(lib().cbx_workspace_bytes(self._h, len(keep), arr, step, min_cov, flags), "cbx_workspace_bytes")
 
     def embed(self, pcm_ptr: int, offsets: Sequence[int], trim_top_db: float, step: int, min_cov: float,
               ve_ptr: int, xv_ptr: int, status_ptr: int, ws_ptr: int, ws_bytes: int, stream: int, flags: int):
         n = len(offsets) - 1
-        off = (C.c_int64 * (n + 1))(*[int(x) for x in offsets])
+        keep, off = _i64(offsets)
         self._check(lib().cbx_embed(self._h, pcm_ptr, off, n, float(trim_top_db), step, min_cov,
                                     ve_ptr, xv_ptr, status_ptr, ws_ptr, ws_bytes, stream, flags), "cbx_embed")
 
@@ -220,18 +226,18 @@ class Context:
 
     def resample(self, x_ptr: int, in_offsets: Sequence[int], src_sr: int, dst_sr: int, y_ptr: int, out_offsets: Sequence[int], stream: int):
         n = len(in_offsets) - 1
-        a = (C.c_int64 * (n + 1))(*[int(v) for v in in_offsets])
-        b = (C.c_int64 * (n + 1))(*[int(v) for v in out_offsets])
+        keep_a, a = _i64(in_offsets)
+        keep_b, b = _i64(out_offsets)
         self._check(lib().cbx_resample(self._h, x_ptr, a, n, int(src_sr), int(dst_sr), y_ptr, b, stream), "cbx_resample")
 
     def prompt_mel(self, pcm_ptr: int, offsets: Sequence[int], out_ptr: int, stream: int):
         n = len(offsets) - 1
-        a = (C.c_int64 * (n + 1))(*[int(v) for v in offsets])
+        keep, a = _i64(offsets)
         self._check(lib().cbx_prompt_mel(self._h, pcm_ptr, a, n, out_ptr, stream), "cbx_prompt_mel")
 
     def s3_log_mel(self, pcm_ptr: int, offsets: Sequence[int], out_ptr: int, stream: int):
         n = len(offsets) - 1
-        a = (C.c_int64 * (n + 1))(*[int(v) for v in offsets])
+        keep, a = _i64(offsets)
         self._check(lib().cbx_s3_log_mel(self._h, pcm_ptr, a, n, out_ptr, stream), "cbx_s3_log_mel")
 
     def project(self, x_ptr: int, n: int, in_dim: int, w_ptr: int, b_ptr: Optional[int], out_dim: int, normalize: bool, y_ptr: int, stream: int):

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from chatterbox_embed_b200 import CAMPPlus, VoiceEncoder, VoiceEncConfig, _lib, scheduler, synth
-from oracle import nets, weights
+from oracle import frontend, nets, weights
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -40,6 +40,29 @@ def test_num_wins_and_step_match_oracle(golden_dir):
 def test_plan_clip(n, want):
     p = _lib.plan_clip(n)
     assert (p.ve_frames, p.ve_partials, p.ve_target, p.xv_frames, p.xv_tdnn, p.xv_segments) == want
+
+
+def test_plan_arithmetic_matches_oracle_on_random_inputs():
+    """cbx_ve_num_wins / cbx_plan_clip against the oracle's restatement of get_num_wins (voice_encoder.py:54-66) and of the
+    Kaldi frame count (kaldi.py:63-67) over random frame counts, steps, coverages and clip lengths (bit-exact integers)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.integers(1, 200000), st.integers(1, 160), st.floats(0.0, 1.0))
+    def wins(n_frames, step, cov):
+        assert _lib.num_wins(n_frames, step, cov) == tuple(int(v) for v in nets.num_wins(n_frames, step, cov))
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.integers(0, 16000 * 600), st.sampled_from([77, 80, 160, 1]))
+    def plan(n, step):
+        p = _lib.plan_clip(n, step, 0.8)
+        w, t = nets.num_wins(1 + n // 160, step, 0.8)
+        tk = frontend.kaldi_num_frames(n) if n >= 400 else 0
+        td = (tk - 1) // 2 + 1 if tk > 0 else 0
+        assert (p.ve_frames, p.ve_partials, p.ve_target, p.xv_frames, p.xv_tdnn, p.xv_segments) == (1 + n // 160, int(w), int(t), tk, td, -(-td // 100))
+
+    wins()
+    plan()
 
 
 def test_no_cpu_fallback():
