@@ -270,6 +270,7 @@ int cbx_set_option(cbx_ctx* c, const char* key, int64_t v) {
   else if (k == "mode" && (v == 0 || v == 1)) c->mode = v;
   else if (k == "overlap" && (v == 0 || v == 1)) c->overlap = v;
   else if (k == "lstm_dbg") c->lstm_dbg = v;
+  else if (k == "probe") c->probe = v;
   else if (k == "pdl") c->pdl = v;
   else if (k == "batch_invariant") c->batch_invariant = v;
   else if (k == "lstm_impl" && (v == 1 || v == 2)) c->lstm_impl = v;
@@ -288,6 +289,7 @@ int64_t cbx_get_option(const cbx_ctx* c, const char* key) {
   if (k == "overlap") return c->overlap;
   if (k == "pdl") return c->pdl;
   if (k == "batch_invariant") return c->batch_invariant;
+  if (k == "probe") return c->probe;
   return -1;
 }
 

@@ -154,6 +154,7 @@ struct cbx_ctx {
   int64_t lstm_trace = 0;             // device pointer of the clock trace buffer
   int64_t lstm_impl = 2;              // 1: DSMEM-push recurrence, 2: L2 multicast-TMA recurrence
   int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)
+  int64_t probe = 0;                  // timing experiments, results are WRONG while set: bit 0 = no CAM gate kernel (tools/probe_bounds.py)
   int64_t batch_invariant = 0;        // 1: exact warp-level segment sums: x-vectors bit-identical whatever the batch (about 0.5 ms per step)
   int64_t pdl = 1;                    // programmatic dependent launch along the dense-layer chain
   // buffers owned by the library (cbx_embed_host / cbx_embed_host_submit): two slots so that the host<->device copies of

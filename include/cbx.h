@@ -95,7 +95,8 @@ const char* cbx_version(void);
  * bit-identical whatever else is in the batch and however the call is chunked (exact warp-level segment sums, ~3 %
  * slower); 0 (default) = reproducible from run to run, position dependent within ~1e-4 (the VoiceEncoder embedding is
  * batch invariant either way).  ("lstm_impl", "lstm_dbg", "lstm_trace" select / probe
- * the recurrence kernel and are for the tools under tools/.) */
+ * the recurrence kernel and are for the tools under tools/; "probe" != 0 removes kernels from the chain to time what is left
+ * -- results are WRONG while it is set -- bit 0: the CAM gate kernel, tools/probe_bounds.py.) */
 int cbx_set_option(cbx_ctx* ctx, const char* key, int64_t value);
 int64_t cbx_get_option(const cbx_ctx* ctx, const char* key);
 
