@@ -88,7 +88,7 @@ XvLayout plan_xv(const Batch& b, int c0, int c1, int64_t fcm_chunk_rows) {
   return L;
 }
 
-XvChunk carve_xv(Carver& cv, const XvLayout& L, cbx_ctx* c) {
+XvChunk carve_xv(Carver& cv, const XvLayout& L, cbx_ctx* c, bool cat_bf16) {
   XvChunk ch{};
   ch.n_clips = (int)L.plan.size(); ch.fb_rows = L.fb_rows; ch.td_rows = L.td_rows; ch.segs = L.segs; ch.fcm_rows = L.fcm_rows;
   ch.plan = cv.take<ClipPlan>(ch.n_clips);
@@ -111,6 +111,9 @@ XvChunk carve_xv(Carver& cv, const XvLayout& L, cbx_ctx* c) {
   ch.cat1 = cv.take<float>((int64_t)L.td_rows * 512);
   ch.cat2 = cv.take<float>((int64_t)L.td_rows * 1024);
   ch.cat3 = cv.take<float>((int64_t)L.td_rows * 1024);
+  ch.cat1h = cat_bf16 ? cv.take<uint16_t>((int64_t)L.td_rows * 512) : nullptr;
+  ch.cat2h = cat_bf16 ? cv.take<uint16_t>((int64_t)L.td_rows * 1024) : nullptr;
+  ch.cat3h = cat_bf16 ? cv.take<uint16_t>((int64_t)L.td_rows * 1024) : nullptr;
   ch.u = cv.take<float>((int64_t)L.td_rows * kBnC);
   ch.tr3 = cv.take<float>((int64_t)L.td_rows * kStatsC);
   ch.seg_sum = cv.take<float>((int64_t)std::max(L.segs, 1) * kBnC * 2);      // fp32 in the strict mode, 64-bit fixed point in the tensor-core mode
@@ -181,7 +184,7 @@ int64_t workspace_bytes_for(cbx_ctx* c, const Batch& b, int flags) {
   ChunkSets s = make_chunks(c, b, flags);
   int64_t ve_max = 0, xv_max = 0;
   for (auto& r : s.ve) { Carver cv(nullptr, 0); carve_ve(cv, plan_ve(b, r.first, r.second), nullptr); ve_max = std::max(ve_max, cv.off); }
-  for (auto& r : s.xv) { Carver cv(nullptr, 0); carve_xv(cv, plan_xv(b, r.first, r.second, c->fcm_chunk_rows), nullptr); xv_max = std::max(xv_max, cv.off); }
+  for (auto& r : s.xv) { Carver cv(nullptr, 0); carve_xv(cv, plan_xv(b, r.first, r.second, c->fcm_chunk_rows), nullptr, c->cat_bf16 != 0); xv_max = std::max(xv_max, cv.off); }
   return ((ve_max + 255) & ~int64_t(255)) + ((xv_max + 255) & ~int64_t(255)) + 1024;
 }
 
@@ -271,6 +274,7 @@ int cbx_set_option(cbx_ctx* c, const char* key, int64_t v) {
   else if (k == "overlap" && (v == 0 || v == 1)) c->overlap = v;
   else if (k == "lstm_dbg") c->lstm_dbg = v;
   else if (k == "probe") c->probe = v;
+  else if (k == "cat_bf16" && (v == 0 || v == 1)) c->cat_bf16 = v;
   else if (k == "pdl") c->pdl = v;
   else if (k == "batch_invariant") c->batch_invariant = v;
   else if (k == "lstm_impl" && (v == 1 || v == 2)) c->lstm_impl = v;
@@ -290,6 +294,7 @@ int64_t cbx_get_option(const cbx_ctx* c, const char* key) {
   if (k == "pdl") return c->pdl;
   if (k == "batch_invariant") return c->batch_invariant;
   if (k == "probe") return c->probe;
+  if (k == "cat_bf16") return c->cat_bf16;
   return -1;
 }
 
@@ -358,7 +363,7 @@ int cbx_embed(cbx_ctx* c, const float* pcm, const int64_t* off, int n, float tri
     XvLayout L = plan_xv(b, r.first, r.second, c->fcm_chunk_rows);
     // taps are byte offsets from the start of the caller's workspace
     Carver cv_abs(ws, ws_bytes); cv_abs.off = ve_region;
-    XvChunk ch = carve_xv(cv_abs, L, c);
+    XvChunk ch = carve_xv(cv_abs, L, c, c->cat_bf16 != 0);
     ch.hplan = L.plan.data();
     CBX_CUDA_OK(c, cudaMemcpyAsync(ch.plan, L.plan.data(), sizeof(ClipPlan) * L.plan.size(), cudaMemcpyHostToDevice, sx));
     run_xv_chunk(c, pcm, ch, xv_out, status, sx);

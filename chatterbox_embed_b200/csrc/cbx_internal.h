@@ -154,6 +154,7 @@ struct cbx_ctx {
   int64_t lstm_trace = 0;             // device pointer of the clock trace buffer
   int64_t lstm_impl = 2;              // 1: DSMEM-push recurrence, 2: L2 multicast-TMA recurrence
   int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)
+  int64_t cat_bf16 = 0;               // 1 = the D-TDNN GEMMs read a bf16 copy of the concatenation buffers (looser tolerance)
   int64_t probe = 0;                  // timing experiments, results are WRONG while set: bit 0 = no CAM gate kernel (tools/probe_bounds.py)
   int64_t batch_invariant = 0;        // 1: exact warp-level segment sums: x-vectors bit-identical whatever the batch (about 0.5 ms per step)
   int64_t pdl = 1;                    // programmatic dependent launch along the dense-layer chain
@@ -243,6 +244,7 @@ struct XvChunk {
   float *b0, *b1, *b2, *b3, *b4, *b5, *b6;   // FCM activations of one sub-chunk
   float* fcm_out;           // [fb_rows][320]
   float *cat1, *cat2, *cat3;   // [td_rows][512|1024|1024]
+  uint16_t *cat1h, *cat2h, *cat3h;   // bf16 copies of the same (option cat_bf16; null otherwise)
   float* u;                 // [td_rows][128]
   float* tr3;               // [td_rows][512]
   float* seg_sum;           // [segs][128] fp32 (strict mode) or 64-bit fixed point (tensor-core mode: 2 floats per entry)
@@ -259,7 +261,7 @@ void run_ve_forward_partials(cbx_ctx* c, const float* mels, int n, float* out, v
 void run_ve_mel_tc(cbx_ctx* c, const float* pcm, const VeChunk& ch, cudaStream_t st);
 void run_kaldi_fbank_tc(cbx_ctx* c, const float* pcm, const XvChunk& ch, cudaStream_t st);
 void run_local_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmU, const CUtensorMap& tmW, const CUtensorMap& tmOut, int M, int dil,
-                       int col0, const float* gate, const int32_t* row_seg, bool pdl = false);   // local_tc.cu
+                       int col0, const float* gate, const int32_t* row_seg, bool pdl = false, uint16_t* shadow = nullptr, int ldh = 0);   // local_tc.cu
 int lstm_padded_slots(int n_slots);     // slots rounded up to whole 224-partial cluster tiles (lstm_tc.cu)
 void run_lstm_rec_tc2(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
                       int n_slots, cudaStream_t st);

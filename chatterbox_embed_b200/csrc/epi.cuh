@@ -12,6 +12,20 @@ __device__ __forceinline__ void store32(float* dst, const float* v) {
   for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
+// 32 values -> 32 bf16 (round to nearest even), 64 contiguous bytes: the bf16 copy of the concatenation buffer (option cat_bf16)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));      // upper half <- first source, lower half <- second
+  return r;
+}
+__device__ __forceinline__ void store32_bf16(uint16_t* dst, const float* v) {
+  uint4* o = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                      pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+}
+
 struct EpiBias {                 // out = acc + bias                                  (LSTM input projections)
   float* out; int ld; const float* bias; int M;
   __device__ void operator()(int m, int n0, float* v) const {
@@ -24,6 +38,7 @@ struct EpiBias {                 // out = acc + bias                            
 
 struct EpiBiasReluMask {         // out = row is a real frame ? relu(acc + bias) : 0   (TDNN, dense-layer bottleneck)
   float* out; int ld; const float* bias; const int32_t* row_clip; int M;
+  uint16_t* shadow = nullptr; int ldh = 0;                     // bf16 copy of the same tile (option cat_bf16)
   __device__ void operator()(int m, int n0, float* v) const {
     if (m >= M) return;
     const bool live = row_clip[m] >= 0;
@@ -37,6 +52,7 @@ struct EpiBiasReluMask {         // out = row is a real frame ? relu(acc + bias)
       v[4 * j + 3] = live ? fmaxf(v[4 * j + 3] + bb.w, 0.f) : 0.f;
     }
     store32(out + (size_t)m * ld + n0, v);
+    if (shadow) store32_bf16(shadow + (size_t)m * ldh + n0, v);
   }
 };
 
@@ -129,11 +145,13 @@ using EpiBiasReluMaskSegsumExact = EpiBiasReluMaskSegsumT<true>;
 
 struct EpiMask {                 // out = row is a real frame ? acc : 0                (transit layers)
   float* out; int ld; const int32_t* row_clip; int M;           // out == nullptr: the kernel stores (TMA)
+  uint16_t* shadow = nullptr; int ldh = 0;                     // bf16 copy of the same tile (option cat_bf16)
   __device__ void operator()(int m, int n0, float* v) const {
     const bool live = m < M && row_clip[m] >= 0;
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = live ? v[i] : 0.f;
     if (out && m < M) store32(out + (size_t)m * ld + n0, v);
+    if (shadow && m < M) store32_bf16(shadow + (size_t)m * ldh + n0, v);
   }
 };
 

@@ -9,6 +9,7 @@
 // into columns [cin, cin + 32) of the concat buffer.
 #include "cbx_internal.h"
 #include "tc.cuh"
+#include "epi.cuh"
 
 namespace cbx {
 namespace lconv {
@@ -25,6 +26,7 @@ constexpr int SMEM_BYTES = W_BYTES + OUT_BYTES + STAGES * STAGE_BYTES + 1024 + 2
 struct Params {
   int M, dil, col0, ntiles;
   const float* gate; const int32_t* row_seg;
+  uint16_t* shadow; int ldh;            // bf16 copy of the concatenation buffer (option cat_bf16), or null
 };
 
 __global__ void __launch_bounds__(320, 1)
@@ -131,6 +133,7 @@ local_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
         v[4 * c + 2] = seg >= 0 ? v[4 * c + 2] * gg.z : 0.f;
         v[4 * c + 3] = seg >= 0 ? v[4 * c + 3] * gg.w : 0.f;
       }
+      if (p.shadow && m < p.M) tc::store32_bf16(p.shadow + (size_t)m * p.ldh + p.col0, v);
       // the group's previous store has read the staging tile
       if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 3, 128;" ::: "memory");
 #pragma unroll
@@ -155,11 +158,11 @@ local_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
 // u [M][128] -> cat[:, col0 : col0 + 32] = conv_k3_dil(u) * gate[segment]; tmU: {128 cols, M rows} box {32, 128 + 2 dil} (tf32),
 // tmOut: {ld cols, M rows} box {32, 128} (fp32) over the concat buffer
 void run_local_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmU, const CUtensorMap& tmW, const CUtensorMap& tmOut, int M, int dil,
-                       int col0, const float* gate, const int32_t* row_seg, bool pdl) {
+                       int col0, const float* gate, const int32_t* row_seg, bool pdl, uint16_t* shadow, int ldh) {
   using namespace lconv;
   if (M <= 0) return;
   ensure_max_smem(local_conv_kernel, SMEM_BYTES);
-  Params p{M, dil, col0, (M + 127) / 128, gate, row_seg};
+  Params p{M, dil, col0, (M + 127) / 128, gate, row_seg, shadow, ldh};
   const int grid = p.ntiles < tc::sm_count() ? p.ntiles : tc::sm_count();
   Scope sc(c->launches, st, "dense_local_gemm", 2.0 * M * kGrowth * 3 * kBnC, 4.0 * M * (kBnC + kGrowth));
   tc::launch_pdl(local_conv_kernel, dim3(grid), dim3(320), SMEM_BYTES, st, pdl, tmU, tmW, tmOut, p);

@@ -59,6 +59,11 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 // one lane of a fully converged warp (the warp-uniform tcgen05 / TMA instructions are issued from inside `if (elect_one())`
 // with the whole warp running the surrounding loop: that keeps the issue path free of divergence bookkeeping)
 __device__ __forceinline__ bool elect_one() {
@@ -326,9 +331,11 @@ constexpr int PG = 2;     // producer groups
 static __device__ unsigned long long* g_gemm_trace = nullptr;
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
-template <int BN, int STAGES, class Epi>
+// XH: X is the bf16 copy of the buffer (option cat_bf16): half the bytes and half the load instructions per K block; BN, ReLU
+// and the tf32 stage are unchanged (the MMA stays kind::tf32, the weights are not rounded any further).
+template <int BN, int STAGES, class Epi, bool XH>
 __global__ void __launch_bounds__(320, 2)
-tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __restrict__ bn_a, const float* __restrict__ bn_b,
+tgemm_bnrelu_kernel(const void* __restrict__ Xv, int lda, int M, const float* __restrict__ bn_a, const float* __restrict__ bn_b,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, int nkb, Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -405,6 +412,55 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
     // Warps 2..5 run the epilogue once their K blocks are done.
     const int g = (warp - 2) >> 2;
     const int t = (threadIdx.x - 64) & 127;
+    if constexpr (XH) {
+      // bf16 X: a K block is 64 bytes of a row = four 16-byte chunks of 8 channels; thread = (chunk, row r0 + 32 i)
+      const int chunk = t & 3, r0 = t >> 2;
+      const uint16_t* xp = reinterpret_cast<const uint16_t*>(Xv) + (size_t)(m0 + r0) * lda + chunk * 8;
+      uint4 xa[BM / 32], xb[BM / 32];
+      const float4* sc4 = reinterpret_cast<const float4*>(s_bn) + 2 * chunk;
+      const float4* sh4 = sc4 + nkb * (BK / 4);
+      auto load = [&](uint4* dst, int kb) {
+        const int kcol = kb * BK;
+#pragma unroll
+        for (int i = 0; i < BM / 32; ++i)
+          dst[i] = (m0 + r0 + i * 32 < M) ? ldg_stream(reinterpret_cast<const uint4*>(xp + (size_t)i * 32 * lda + kcol)) : make_uint4(0u, 0u, 0u, 0u);
+      };
+      auto produce = [&](const uint4* x, int kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        const float4 sc0 = sc4[kb * (BK / 4)], sc1 = sc4[kb * (BK / 4) + 1], sh0 = sh4[kb * (BK / 4)], sh1 = sh4[kb * (BK / 4) + 1];
+        mbar_wait(&empty[s], ph ^ 1);
+        float4* base = reinterpret_cast<float4*>(sA + s * A_BYTES);
+#pragma unroll
+        for (int i = 0; i < BM / 32; ++i) {
+          const int r = r0 + i * 32;
+          const uint4 q = x[i];                 // element 2j in the low half of word j, 2j + 1 in the high half
+          float4 y0, y1;
+          y0.x = to_tf32(fmaxf(fmaf(__uint_as_float(q.x << 16), sc0.x, sh0.x), 0.f));
+          y0.y = to_tf32(fmaxf(fmaf(__uint_as_float(q.x & 0xffff0000u), sc0.y, sh0.y), 0.f));
+          y0.z = to_tf32(fmaxf(fmaf(__uint_as_float(q.y << 16), sc0.z, sh0.z), 0.f));
+          y0.w = to_tf32(fmaxf(fmaf(__uint_as_float(q.y & 0xffff0000u), sc0.w, sh0.w), 0.f));
+          y1.x = to_tf32(fmaxf(fmaf(__uint_as_float(q.z << 16), sc1.x, sh1.x), 0.f));
+          y1.y = to_tf32(fmaxf(fmaf(__uint_as_float(q.z & 0xffff0000u), sc1.y, sh1.y), 0.f));
+          y1.z = to_tf32(fmaxf(fmaf(__uint_as_float(q.w << 16), sc1.z, sh1.z), 0.f));
+          y1.w = to_tf32(fmaxf(fmaf(__uint_as_float(q.w & 0xffff0000u), sc1.w, sh1.w), 0.f));
+          base[r * 8 + ((2 * chunk) ^ (r & 7))] = y0;
+          base[r * 8 + ((2 * chunk + 1) ^ (r & 7))] = y1;
+        }
+        fence_proxy_async();
+        mbar_arrive(&afull[s]);
+      };
+      pdl_wait();
+      if (g < nkb) load(xa, g);
+      for (int kb = g; kb < nkb; kb += 2 * PG) {
+        if (kb + PG < nkb) load(xb, kb + PG);
+        produce(xa, kb);
+        if (kb + PG < nkb) {
+          if (kb + 2 * PG < nkb) load(xa, kb + 2 * PG);
+          produce(xb, kb + PG);
+        }
+      }
+    } else {
+    const float* X = reinterpret_cast<const float*>(Xv);
     const int chunk = t & 7, r0 = t >> 3;
     const float* xp = X + (size_t)(m0 + r0) * lda + chunk * 4;
     float4 xa[BM / 16], xb[BM / 16];                // 8 rows of X each
@@ -443,6 +499,7 @@ tgemm_bnrelu_kernel(const float* __restrict__ X, int lda, int M, const float* __
         if (kb + 2 * PG < nkb) load(xa, kb + 2 * PG);
         produce(xb, kb + PG);
       }
+    }
     }
     pdl_trigger();              // every CTA has its loads behind it: the next kernel may start setting up
     {
@@ -660,16 +717,16 @@ inline void pgemm_bias_tma(Launches& L, cudaStream_t st, const char* tag, const 
   kern<<<tiles < sm_count() ? tiles : sm_count(), 192, SMEM, st>>>(tmA, tmB, tmC, bias, tn, tiles, (K + BK - 1) / BK);
 }
 
-template <int BN, int STAGES, class Epi>
-inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const float* X, int lda, const float* bn_a, const float* bn_b,
+template <int BN, int STAGES, class Epi, bool XH = false>
+inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const void* X, int lda, const float* bn_a, const float* bn_b,
                          const CUtensorMap& tmB, float* C, int ldc, int M, int N, int K, Epi epi, bool pdl = false) {
   if (M <= 0 || N <= 0) return;
-  auto kern = tgemm_bnrelu_kernel<BN, STAGES, Epi>;
+  auto kern = tgemm_bnrelu_kernel<BN, STAGES, Epi, XH>;
   constexpr int SMEM = smem_bytes(BN, STAGES) + 2 * 1024 * 4;      // + BN scale / shift of up to 1024 columns
   if (K > 1024) { fprintf(stderr, "libcbx: tgemm_bnrelu supports K <= 1024\n"); return; }
   ensure_max_smem(kern, SMEM);
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
+  Scope sc(L, st, tag, 2.0 * M * N * K, (XH ? 2.0 : 4.0) * (double)M * K + 4.0 * (double)M * N);
   CUtensorMap tmC = make_map_2d(C, M, N, ldc, BM, false);
   launch_pdl(kern, grid, dim3(320), SMEM, st, pdl, X, lda, M, bn_a, bn_b, tmB, tmC, (K + BK - 1) / BK, epi);
 }

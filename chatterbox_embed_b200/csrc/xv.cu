@@ -443,7 +443,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     const int sh[5] = {-1, -1, 0, 0, 1}, c0[5] = {0, kFcmOut, 0, kFcmOut, 0};
     for (int i = 0; i < 5; ++i) { tap.shift[i] = sh[i]; tap.col0[i] = c0[i]; }
     tc::tgemm<128, 3>(L, st, "tdnn_gemm", tmA, W.tm_tdnn, M, kTdnnC, W.tdnn.K, tap, 5, tc::NoPrologue{},
-                      tc::EpiBiasReluMask{ch.cat1, 512, W.tdnn.bias, ch.td_row_clip, M});
+                      tc::EpiBiasReluMask{ch.cat1, 512, W.tdnn.bias, ch.td_row_clip, M, ch.cat1h, 512});
   } else {
     sgemm(L, st, "tdnn_gemm", M, kTdnnC, W.tdnn.K, TdnnA{ch.fcm_out, ch.fb_rows}, W.tdnn.w, W.tdnn.K, BiasReluMaskEpi{ch.cat1, 512, W.tdnn.bias, ch.td_row_clip});
   }
@@ -452,6 +452,8 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
   static const int kLayers[3] = {12, 24, 16};
   static const int kDil[3] = {1, 2, 2};
   float* cats[3] = {ch.cat1, ch.cat2, ch.cat3};
+  uint16_t* cath[3] = {ch.cat1h, ch.cat2h, ch.cat3h};      // bf16 copies (option cat_bf16, tensor-core mode): what the GEMMs then read
+  const bool bf = tcm && ch.cat1h != nullptr;
   const int lds[3] = {512, 1024, 1024};
   int li = 0;
   for (int b = 0; b < 3; ++b) {
@@ -470,6 +472,9 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
       if (tcm && c->batch_invariant)
         tc::tgemm_bnrelu<128, 2>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
                                  tc::EpiBiasReluMaskSegsumExact{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
+      else if (bf)
+        tc::tgemm_bnrelu<128, 2, tc::EpiBiasReluMaskSegsum, true>(L, st, "dense_bottleneck_gemm", cath[b], ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
+                                 tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
       else if (tcm)
         tc::tgemm_bnrelu<128, 2>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
                                  tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
@@ -485,14 +490,17 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
         { Scope sc(L, st, "cam_gate_kernel"); cam_gate_kernel<<<ch.segs, 128, 0, st>>>(ch.seg_sum, ch.plan, ch.seg_clip, D, ch.gate); }
       }
       if (tcm)
-        run_local_conv_tc(c, st, tm_u, W.tm_wl[li], tm_cat, M, kDil[b], D.cin, ch.gate, ch.td_row_seg, pdl);
+        run_local_conv_tc(c, st, tm_u, W.tm_wl[li], tm_cat, M, kDil[b], D.cin, ch.gate, ch.td_row_seg, pdl, bf ? cath[b] : nullptr, ld);
       else
         sgemm(L, st, "dense_local_gemm", M, kGrowth, 3 * kBnC, LocalConvA{ch.u, kDil[b], M}, D.wl, 3 * kBnC, GateEpi{cat, ld, D.cin, ch.gate, ch.td_row_seg});
     }
     const TransitW& T = W.transit[b];
     float* out = b == 0 ? ch.cat2 : (b == 1 ? ch.cat3 : ch.tr3);
     const int ldo = b == 2 ? kStatsC : 1024;
-    if (tcm)
+    if (bf)
+      tc::tgemm_bnrelu<128, 2, tc::EpiMask, true>(L, st, "transit_gemm", cath[b], ld, T.a, T.b, W.tm_tr[b], out, ldo, M, T.cout, T.cin,
+                               tc::EpiMask{nullptr, ldo, ch.td_row_clip, M, b < 2 ? cath[b + 1] : nullptr, ldo}, pdl);
+    else if (tcm)
       tc::tgemm_bnrelu<128, 2>(L, st, "transit_gemm", cat, ld, T.a, T.b, W.tm_tr[b], out, ldo, M, T.cout, T.cin,
                                tc::EpiMask{nullptr, ldo, ch.td_row_clip, M}, pdl);
     else

@@ -86,7 +86,7 @@ void cbx_destroy(cbx_ctx* ctx);
 const char* cbx_last_error(const cbx_ctx* ctx);   /* ctx may be NULL: last error of cbx_create */
 const char* cbx_version(void);
 
-/* Tuning: key in {"xv_chunk_rows","fcm_chunk_rows","lstm_chunk_partials","mode","overlap","pdl"}.  mode: 1 (default) =
+/* Tuning: key in {"xv_chunk_rows","fcm_chunk_rows","lstm_chunk_partials","mode","overlap","pdl","batch_invariant","cat_bf16"}.  mode: 1 (default) =
  * tensor-core (tcgen05, TF32 / 3xTF32) kernels, 0 = strict fp32 SIMT kernels everywhere (the on-device fp32 yardstick).
  * overlap: 1 (default) = with both encoders requested, CAMPPlus runs on an internal second stream beside the
  * VoiceEncoder chain (forked from / joined into the caller's stream).  pdl: 1 (default) = the CAMPPlus convolution and
@@ -94,7 +94,10 @@ const char* cbx_version(void);
  * are scheduling only: results are bit-identical with either off.  batch_invariant: 1 = the x-vector of a clip is
  * bit-identical whatever else is in the batch and however the call is chunked (exact warp-level segment sums, ~3 %
  * slower); 0 (default) = reproducible from run to run, position dependent within ~1e-4 (the VoiceEncoder embedding is
- * batch invariant either way).  ("lstm_impl", "lstm_dbg", "lstm_trace" select / probe
+ * batch invariant either way).  cat_bf16: 1 = the D-TDNN bottleneck / transit GEMMs read a bf16 copy of the concatenation
+ * buffers that the producing epilogues write beside the fp32 one (activations rounded once to bf16; weights, MMAs and every
+ * other tensor unchanged): 3 % faster, x-vector error 1.1-1.4x the TF32 mode's; 0 (default) = fp32 storage.
+ * ("lstm_impl", "lstm_dbg", "lstm_trace" select / probe
  * the recurrence kernel and are for the tools under tools/; "probe" != 0 removes kernels from the chain to time what is left
  * -- results are WRONG while it is set -- bit 0: the CAM gate kernel, tools/probe_bounds.py.) */
 int cbx_set_option(cbx_ctx* ctx, const char* key, int64_t value);

@@ -335,6 +335,39 @@ def test_batch_invariant_option(models, mode1):
     assert np.array_equal(fast[0], ve) and np.abs(fast[1] - xv).max() < 5e-4 * scale
 
 
+@pytest.mark.parametrize("kind,tol,min_cos", [("W0", 1e-3, 0.9999), ("W1", 2e-3, 0.9999), ("W2", 5e-2, 0.999)])
+def test_cat_bf16_option(models, mode1, kind, tol, min_cos):
+    """Option cat_bf16 (first piece of the bf16 mode, BASELINE config 5): the D-TDNN bottleneck / transit GEMMs read a bf16
+    copy of the concatenation buffers -- activations rounded to bf16 once, weights and MMAs stay TF32.  Its own, looser
+    tolerance (measured, DESIGN.md 7.3: W0 4.9e-5, W1 6.1e-4, W2 8.7e-2 at |x| <= 9.8 / cos 0.99968 against 7.6e-2 / 0.99992 without it): the
+    north_star gate still holds with the default-init weights; the VoiceEncoder
+    embedding is untouched (bit-identical); chunking stays invisible up to rounding."""
+    sdv, sdc, emb = _emb(models, kind)
+    lens = [int(x) for x in synth.ragged_lengths(6)] + [720, 25599]
+    wavs = [synth.mixed(i, n) for i, n in enumerate(lens)]
+    want = nets.campplus_embed_wavs(sdc, wavs)
+    ve0, xv0 = emb.embed_wavs(wavs)
+    old = mode1.get_option("xv_chunk_rows")
+    try:
+        mode1.set_option("cat_bf16", 1)
+        ve1, xv1 = emb.embed_wavs(wavs)
+        mode1.set_option("xv_chunk_rows", 900)
+        ve2, xv2 = emb.embed_wavs(wavs)
+    finally:
+        mode1.set_option("cat_bf16", 0)
+        mode1.set_option("xv_chunk_rows", old)
+    scale = max(1.0, float(np.abs(want).max()))
+    assert np.array_equal(ve0, ve1) and np.array_equal(ve0, ve2)
+    assert not np.array_equal(xv0, xv1)                                  # the option is really on
+    for xv in (xv1, xv2):
+        assert np.isfinite(xv[:-2]).all()
+        assert np.abs(xv[:-2] - want[:-2]).max() <= tol * scale
+        assert min(cos(a, b) for a, b in zip(xv[:-2], want[:-2])) >= min_cos
+    # and off again: the default path is back, bit for bit
+    ve3, xv3 = emb.embed_wavs(wavs)
+    assert np.array_equal(ve3, ve0) and np.array_equal(xv3, xv0)
+
+
 def test_weight_updates_are_picked_up(mode1):
     """The modules push their tensors to libcbx lazily and cache the tensor list: in-place edits (version counters), a new
     load_state_dict and a fresh module must all be seen."""
