@@ -274,7 +274,7 @@ int cbx_set_option(cbx_ctx* c, const char* key, int64_t v) {
   else if (k == "overlap" && (v == 0 || v == 1)) c->overlap = v;
   else if (k == "lstm_dbg") c->lstm_dbg = v;
   else if (k == "probe") c->probe = v;
-  else if (k == "cat_bf16" && (v == 0 || v == 1)) c->cat_bf16 = v;
+  else if (k == "cat_bf16" && v >= 0 && v <= 2) c->cat_bf16 = v;
   else if (k == "pdl") c->pdl = v;
   else if (k == "batch_invariant") c->batch_invariant = v;
   else if (k == "lstm_impl" && (v == 1 || v == 2)) c->lstm_impl = v;

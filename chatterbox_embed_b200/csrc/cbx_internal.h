@@ -84,12 +84,13 @@ struct DenseLayerW {
   int cin;
   const float *a1, *b1;      // BN1 scale/shift on the layer input (prologue)
   const float *w1, *t2;      // [128][cin] with BN2 scale folded, BN2 shift
+  const float *w1h;          // the same as bf16 [128][cin] (option cat_bf16 = 2)
   const float *wl;           // [32][3*128] local conv, k = tap*128 + c
   const float *wc1, *bc1;    // [64][128], [64]
   const float *wc2, *bc2;    // [32][64], [32]
   const float *wc1T, *wc2T;  // [128][64], [64][32] transposed copies
 };
-struct TransitW { int cin, cout; const float *a, *b, *w; };
+struct TransitW { int cin, cout; const float *a, *b, *w, *wh; };   // wh: w as bf16 (option cat_bf16 = 2)
 
 struct VeWeights {
   bool loaded = false;
@@ -112,6 +113,7 @@ struct XvWeights {
   const float *out_a, *out_b;                     // out_nonlinear BN
   const float *fin_w, *fin_b;                     // [192][1024] (BN folded), [192]
   CUtensorMap tm_tdnn, tm_w1[52], tm_wl[52], tm_tr[3];   // TMA maps of the GEMM B operands
+  CUtensorMap tm_w1h[52], tm_trh[3];                     // bf16 copies: box {64 channels, 128 rows}
   CUtensorMap tm_res[2][2][2], tm_head2;
 };
 struct FrontendTables {
@@ -154,7 +156,7 @@ struct cbx_ctx {
   int64_t lstm_trace = 0;             // device pointer of the clock trace buffer
   int64_t lstm_impl = 2;              // 1: DSMEM-push recurrence, 2: L2 multicast-TMA recurrence
   int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)
-  int64_t cat_bf16 = 0;               // 1 = the D-TDNN GEMMs read a bf16 copy of the concatenation buffers (looser tolerance)
+  int64_t cat_bf16 = 0;               // 1 = the D-TDNN GEMMs read a bf16 copy of the concatenation buffers, 2 = and run on bf16 operands (kind::f16)
   int64_t probe = 0;                  // timing experiments, results are WRONG while set: bit 0 = no CAM gate kernel (tools/probe_bounds.py)
   int64_t batch_invariant = 0;        // 1: exact warp-level segment sums: x-vectors bit-identical whatever the batch (about 0.5 ms per step)
   int64_t pdl = 1;                    // programmatic dependent launch along the dense-layer chain

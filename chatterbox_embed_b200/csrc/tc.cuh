@@ -121,6 +121,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with bf16 operands (kind::f16, fp32 accumulation): 16 K elements = 32 bytes per instruction
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrives on the mbarrier when all MMAs issued so far by this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -180,6 +189,11 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
 // kind::tf32 instruction descriptor: D=f32, A=B=tf32, both K-major, M x N
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- K-block -> A tile coordinates
@@ -331,12 +345,17 @@ constexpr int PG = 2;     // producer groups
 static __device__ unsigned long long* g_gemm_trace = nullptr;
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
-// XH: X is the bf16 copy of the buffer (option cat_bf16): half the bytes and half the load instructions per K block; BN, ReLU
-// and the tf32 stage are unchanged (the MMA stays kind::tf32, the weights are not rounded any further).
-template <int BN, int STAGES, class Epi, bool XH>
+// XM = 1: X is the bf16 copy of the buffer (option cat_bf16 = 1): half the bytes and half the load instructions per K block; BN,
+// ReLU and the tf32 stage are unchanged (the MMA stays kind::tf32, the weights are not rounded any further).
+// XM = 2 (cat_bf16 = 2): bf16 OPERANDS as well -- a K block is 64 channels per 128-byte row, the stage holds bf16, W comes
+// from its bf16 copy (tmB: box {64, BN}), kind::f16 MMAs: half the stage stores and half the operand bytes per channel.
+// K need not be a multiple of 64: the tail block's missing channels are zeros on both sides (TMA fill / masked loads).
+template <int BN, int STAGES, class Epi, int XM>
 __global__ void __launch_bounds__(320, 2)
-tgemm_bnrelu_kernel(const void* __restrict__ Xv, int lda, int M, const float* __restrict__ bn_a, const float* __restrict__ bn_b,
+tgemm_bnrelu_kernel(const void* __restrict__ Xv, int lda, int M, int K, const float* __restrict__ bn_a, const float* __restrict__ bn_b,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, int nkb, Epi epi) {
+  constexpr bool XH = XM == 1;
+  constexpr int KB = XM == 2 ? 64 : BK;          // channels per K block
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
@@ -355,10 +374,12 @@ tgemm_bnrelu_kernel(const void* __restrict__ Xv, int lda, int M, const float* __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;     // n fastest: the CTAs that share an X row tile run together (L2 reuse)
   {
-    const int kq = nkb * (BK / 4);                          // float4s per vector
+    const int kq = nkb * (KB / 4);                          // float4s per vector (the tail block's missing channels: zeros)
     float4* d = reinterpret_cast<float4*>(s_bn);
-    for (int i = threadIdx.x; i < 2 * kq; i += 320)
-      d[i] = __ldg(reinterpret_cast<const float4*>(i < kq ? bn_a : bn_b) + (i < kq ? i : i - kq));
+    for (int i = threadIdx.x; i < 2 * kq; i += 320) {
+      const int j = i < kq ? i : i - kq;
+      d[i] = 4 * j < K ? __ldg(reinterpret_cast<const float4*>(i < kq ? bn_a : bn_b) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   unsigned long long* tr = g_gemm_trace ? g_gemm_trace + 16 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
   if (tr && threadIdx.x == 0) { uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); tr[0] = smid; tr[1] = gtime(); }
@@ -382,11 +403,11 @@ tgemm_bnrelu_kernel(const void* __restrict__ Xv, int lda, int M, const float* __
         const int s = kb % STAGES, ph = (kb / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&bfull[s], B_BYTES);
-        tma_load_2d(sB + s * B_BYTES, &tmB, &bfull[s], kb * BK, n0);
+        tma_load_2d(sB + s * B_BYTES, &tmB, &bfull[s], kb * KB, n0);
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+    constexpr uint32_t idesc = XM == 2 ? make_idesc_bf16(BM, BN) : make_idesc_tf32(BM, BN);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % STAGES, ph = (kb / STAGES) & 1;
       mbar_wait(&afull[s], ph);
@@ -397,8 +418,10 @@ tgemm_bnrelu_kernel(const void* __restrict__ Xv, int lda, int M, const float* __
       const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k)
-          umma_tf32(tmem_base, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (kb | k) != 0);
+        for (int k = 0; k < BK / UMMA_K; ++k) {            // four instructions of 32 K bytes either way
+          if constexpr (XM == 2) umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          else umma_tf32(tmem_base, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (kb | k) != 0);
+        }
         umma_commit(&empty[s]);
         if (kb == nkb - 1) umma_commit(accum);
       }
@@ -412,7 +435,52 @@ tgemm_bnrelu_kernel(const void* __restrict__ Xv, int lda, int M, const float* __
     // Warps 2..5 run the epilogue once their K blocks are done.
     const int g = (warp - 2) >> 2;
     const int t = (threadIdx.x - 64) & 127;
-    if constexpr (XH) {
+    if constexpr (XM == 2) {
+      // bf16 X, bf16 stage: a K block is 128 bytes of a row = eight 16-byte chunks of 8 channels; thread = (chunk, row r0 + 16 i)
+      const int chunk = t & 7, r0 = t >> 3;
+      const uint16_t* xp = reinterpret_cast<const uint16_t*>(Xv) + (size_t)(m0 + r0) * lda + chunk * 8;
+      uint4 xa[BM / 16], xb[BM / 16];
+      const float4* sc4 = reinterpret_cast<const float4*>(s_bn) + 2 * chunk;
+      const float4* sh4 = sc4 + nkb * (KB / 4);
+      auto load = [&](uint4* dst, int kb) {
+        const int kcol = kb * KB;
+        const bool in_k = kcol + chunk * 8 < K;
+#pragma unroll
+        for (int i = 0; i < BM / 16; ++i)
+          dst[i] = (in_k && m0 + r0 + i * 16 < M) ? ldg_stream(reinterpret_cast<const uint4*>(xp + (size_t)i * 16 * lda + kcol)) : make_uint4(0u, 0u, 0u, 0u);
+      };
+      auto bnrelu2 = [](uint32_t w, float s0, float h0, float s1, float h1) {
+        const float a = fmaxf(fmaf(__uint_as_float(w << 16), s0, h0), 0.f), b = fmaxf(fmaf(__uint_as_float(w & 0xffff0000u), s1, h1), 0.f);
+        uint32_t r;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+        return r;
+      };
+      auto produce = [&](const uint4* x, int kb) {
+        const int s = kb % STAGES, ph = (kb / STAGES) & 1;
+        const float4 sc0 = sc4[kb * (KB / 4)], sc1 = sc4[kb * (KB / 4) + 1], sh0 = sh4[kb * (KB / 4)], sh1 = sh4[kb * (KB / 4) + 1];
+        mbar_wait(&empty[s], ph ^ 1);
+        uint4* base = reinterpret_cast<uint4*>(sA + s * A_BYTES);
+#pragma unroll
+        for (int i = 0; i < BM / 16; ++i) {
+          const int r = r0 + i * 16;
+          const uint4 q = x[i];
+          base[r * 8 + (chunk ^ (r & 7))] = make_uint4(bnrelu2(q.x, sc0.x, sh0.x, sc0.y, sh0.y), bnrelu2(q.y, sc0.z, sh0.z, sc0.w, sh0.w),
+                                                       bnrelu2(q.z, sc1.x, sh1.x, sc1.y, sh1.y), bnrelu2(q.w, sc1.z, sh1.z, sc1.w, sh1.w));
+        }
+        fence_proxy_async();
+        mbar_arrive(&afull[s]);
+      };
+      pdl_wait();
+      if (g < nkb) load(xa, g);
+      for (int kb = g; kb < nkb; kb += 2 * PG) {
+        if (kb + PG < nkb) load(xb, kb + PG);
+        produce(xa, kb);
+        if (kb + PG < nkb) {
+          if (kb + 2 * PG < nkb) load(xa, kb + 2 * PG);
+          produce(xb, kb + PG);
+        }
+      }
+    } else if constexpr (XH) {
       // bf16 X: a K block is 64 bytes of a row = four 16-byte chunks of 8 channels; thread = (chunk, row r0 + 32 i)
       const int chunk = t & 3, r0 = t >> 2;
       const uint16_t* xp = reinterpret_cast<const uint16_t*>(Xv) + (size_t)(m0 + r0) * lda + chunk * 8;
@@ -688,6 +756,7 @@ EncodeTiledFn encode_fn();
 
 // 2-D fp32 row-major [rows][cols] with leading dimension ld (floats); box = 32 columns x box_rows rows, 128B swizzle
 CUtensorMap make_map_2d(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool round_tf32);
+CUtensorMap make_map_2d_bf16(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
 template <int BN, int STAGES, class Pro, class Epi>
 inline void tgemm(Launches& L, cudaStream_t st, const char* tag, const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K,
@@ -717,18 +786,19 @@ inline void pgemm_bias_tma(Launches& L, cudaStream_t st, const char* tag, const 
   kern<<<tiles < sm_count() ? tiles : sm_count(), 192, SMEM, st>>>(tmA, tmB, tmC, bias, tn, tiles, (K + BK - 1) / BK);
 }
 
-template <int BN, int STAGES, class Epi, bool XH = false>
+template <int BN, int STAGES, class Epi, int XM = 0>
 inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const void* X, int lda, const float* bn_a, const float* bn_b,
                          const CUtensorMap& tmB, float* C, int ldc, int M, int N, int K, Epi epi, bool pdl = false) {
   if (M <= 0 || N <= 0) return;
-  auto kern = tgemm_bnrelu_kernel<BN, STAGES, Epi, XH>;
+  auto kern = tgemm_bnrelu_kernel<BN, STAGES, Epi, XM>;
   constexpr int SMEM = smem_bytes(BN, STAGES) + 2 * 1024 * 4;      // + BN scale / shift of up to 1024 columns
   if (K > 1024) { fprintf(stderr, "libcbx: tgemm_bnrelu supports K <= 1024\n"); return; }
   ensure_max_smem(kern, SMEM);
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
-  Scope sc(L, st, tag, 2.0 * M * N * K, (XH ? 2.0 : 4.0) * (double)M * K + 4.0 * (double)M * N);
+  Scope sc(L, st, tag, 2.0 * M * N * K, (XM ? 2.0 : 4.0) * (double)M * K + 4.0 * (double)M * N);
   CUtensorMap tmC = make_map_2d(C, M, N, ldc, BM, false);
-  launch_pdl(kern, grid, dim3(320), SMEM, st, pdl, X, lda, M, bn_a, bn_b, tmB, tmC, (K + BK - 1) / BK, epi);
+  constexpr int KB = XM == 2 ? 64 : BK;
+  launch_pdl(kern, grid, dim3(320), SMEM, st, pdl, X, lda, M, K, bn_a, bn_b, tmB, tmC, (K + KB - 1) / KB, epi);
 }
 
 }  // namespace tc

@@ -31,6 +31,18 @@ struct Packer {
   }
 };
 
+// fp32 -> bf16 (round to nearest even), two per float slot of the blob
+static std::vector<float> to_bf16_words(const float* w, size_t n) {
+  std::vector<float> out((n + 1) / 2, 0.f);
+  uint16_t* h = reinterpret_cast<uint16_t*>(out.data());
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t u; std::memcpy(&u, w + i, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    h[i] = (uint16_t)(u >> 16);
+  }
+  return out;
+}
+
 struct Getter {
   const TensorMap& t; cbx_ctx* c; bool ok = true;
   const float* get(const std::string& name, int64_t numel) {
@@ -232,6 +244,7 @@ int load_xv(cbx_ctx* c, const TensorMap& t) {
       for (int n = 0; n < kBnC; ++n)
         for (int k = 0; k < cin; ++k) o1[(size_t)n * cin + k] = w1[(size_t)n * cin + k] * bn2.scale[n];
       pk.add(&L.w1, o1);
+      pk.add(&L.w1h, to_bf16_words(o1.data(), o1.size()));
       pk.add(&L.t2, bn2.shift);
       std::vector<float> ol((size_t)kGrowth * 3 * kBnC);
       for (int n = 0; n < kGrowth; ++n)
@@ -260,6 +273,7 @@ int load_xv(cbx_ctx* c, const TensorMap& t) {
     pk.add(&T.a, bn.scale);
     pk.add(&T.b, bn.shift);
     pk.add(&T.w, std::vector<float>(w, w + (size_t)(ch / 2) * ch));
+    pk.add(&T.wh, to_bf16_words(w, (size_t)(ch / 2) * ch));
     ch /= 2;
   }
   {
@@ -280,6 +294,7 @@ int load_xv(cbx_ctx* c, const TensorMap& t) {
   W.tm_tdnn = tc::make_map_2d(W.tdnn.w, kTdnnC, W.tdnn.K, W.tdnn.K, 128, true);
   for (int i = 0; i < 52; ++i) {
     W.tm_w1[i] = tc::make_map_2d(W.dense[i].w1, kBnC, W.dense[i].cin, W.dense[i].cin, 128, true);
+    W.tm_w1h[i] = tc::make_map_2d_bf16(W.dense[i].w1h, kBnC, W.dense[i].cin, W.dense[i].cin, 128);
     W.tm_wl[i] = tc::make_map_2d(W.dense[i].wl, kGrowth, 3 * kBnC, 3 * kBnC, 32, true);
   }
   for (int l = 0; l < 2; ++l)
@@ -287,6 +302,7 @@ int load_xv(cbx_ctx* c, const TensorMap& t) {
       for (int k = 0; k < 2; ++k) W.tm_res[l][b][k] = tc::make_map_2d(W.res[l][b][k].w, kFcmC, W.res[l][b][k].K, W.res[l][b][k].K, 32, true);
   W.tm_head2 = tc::make_map_2d(W.head_conv2.w, kFcmC, 288, 288, 32, true);
   for (int b = 0; b < 3; ++b) W.tm_tr[b] = tc::make_map_2d(W.transit[b].w, W.transit[b].cout, W.transit[b].cin, W.transit[b].cin, 128, true);
+  for (int b = 0; b < 3; ++b) W.tm_trh[b] = tc::make_map_2d_bf16(W.transit[b].wh, W.transit[b].cout, W.transit[b].cin, W.transit[b].cin, 128);
   W.loaded = true;
   return CBX_OK;
 }

@@ -472,8 +472,11 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
       if (tcm && c->batch_invariant)
         tc::tgemm_bnrelu<128, 2>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
                                  tc::EpiBiasReluMaskSegsumExact{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
+      else if (bf && c->cat_bf16 == 2)
+        tc::tgemm_bnrelu<128, 2, tc::EpiBiasReluMaskSegsum, 2>(L, st, "dense_bottleneck_gemm", cath[b], ld, D.a1, D.b1, W.tm_w1h[li], ch.u, kBnC, M, kBnC, D.cin,
+                                 tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
       else if (bf)
-        tc::tgemm_bnrelu<128, 2, tc::EpiBiasReluMaskSegsum, true>(L, st, "dense_bottleneck_gemm", cath[b], ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
+        tc::tgemm_bnrelu<128, 2, tc::EpiBiasReluMaskSegsum, 1>(L, st, "dense_bottleneck_gemm", cath[b], ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
                                  tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
       else if (tcm)
         tc::tgemm_bnrelu<128, 2>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
@@ -497,8 +500,11 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     const TransitW& T = W.transit[b];
     float* out = b == 0 ? ch.cat2 : (b == 1 ? ch.cat3 : ch.tr3);
     const int ldo = b == 2 ? kStatsC : 1024;
-    if (bf)
-      tc::tgemm_bnrelu<128, 2, tc::EpiMask, true>(L, st, "transit_gemm", cath[b], ld, T.a, T.b, W.tm_tr[b], out, ldo, M, T.cout, T.cin,
+    if (bf && c->cat_bf16 == 2)
+      tc::tgemm_bnrelu<128, 2, tc::EpiMask, 2>(L, st, "transit_gemm", cath[b], ld, T.a, T.b, W.tm_trh[b], out, ldo, M, T.cout, T.cin,
+                               tc::EpiMask{nullptr, ldo, ch.td_row_clip, M, b < 2 ? cath[b + 1] : nullptr, ldo}, pdl);
+    else if (bf)
+      tc::tgemm_bnrelu<128, 2, tc::EpiMask, 1>(L, st, "transit_gemm", cath[b], ld, T.a, T.b, W.tm_tr[b], out, ldo, M, T.cout, T.cin,
                                tc::EpiMask{nullptr, ldo, ch.td_row_clip, M, b < 2 ? cath[b + 1] : nullptr, ldo}, pdl);
     else if (tcm)
       tc::tgemm_bnrelu<128, 2>(L, st, "transit_gemm", cat, ld, T.a, T.b, W.tm_tr[b], out, ldo, M, T.cout, T.cin,

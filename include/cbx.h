@@ -94,9 +94,11 @@ const char* cbx_version(void);
  * are scheduling only: results are bit-identical with either off.  batch_invariant: 1 = the x-vector of a clip is
  * bit-identical whatever else is in the batch and however the call is chunked (exact warp-level segment sums, ~3 %
  * slower); 0 (default) = reproducible from run to run, position dependent within ~1e-4 (the VoiceEncoder embedding is
- * batch invariant either way).  cat_bf16: 1 = the D-TDNN bottleneck / transit GEMMs read a bf16 copy of the concatenation
- * buffers that the producing epilogues write beside the fp32 one (activations rounded once to bf16; weights, MMAs and every
- * other tensor unchanged): 3 % faster, x-vector error 1.1-1.4x the TF32 mode's; 0 (default) = fp32 storage.
+ * batch invariant either way).  cat_bf16 (first pieces of a bf16 mode; looser tolerances): 1 = the D-TDNN
+ * bottleneck / transit GEMMs read a bf16 copy of the concatenation buffers that the producing epilogues write beside the
+ * fp32 one (activations rounded once to bf16; weights and MMAs stay TF32): 3 % faster, x-vector error 1.1-1.4x the TF32
+ * mode's; 2 = those GEMMs also run on bf16 operands (kind::f16 MMAs, bf16 weight copies, fp32 accumulation): 10 % faster,
+ * error 2-6x the TF32 mode's (still inside cos >= 0.9999 / 1e-3 with default-init weights); 0 (default) = fp32 storage.
  * ("lstm_impl", "lstm_dbg", "lstm_trace" select / probe
  * the recurrence kernel and are for the tools under tools/; "probe" != 0 removes kernels from the chain to time what is left
  * -- results are WRONG while it is set -- bit 0: the CAM gate kernel, tools/probe_bounds.py.) */

@@ -1,7 +1,9 @@
 """Option cat_bf16 (the D-TDNN GEMMs read a bf16 copy of the concatenation buffers): accuracy against the fp32 oracle for the
 three weight sets, and what it buys (256 x 10 s clips, CAMPPlus alone and both encoders).
 
-    python tests/tools/cat_bf16_check.py
+    python tests/tools/cat_bf16_check.py [settings, default: 0 1 2]
+
+cat_bf16 = 1: bf16 copy of the concatenation buffers, tf32 operands; 2: bf16 operands as well (kind::f16, bf16 weights).
 """
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -10,13 +12,14 @@ from chatterbox_embed_b200 import CAMPPlus, VoiceEncoder, _lib, scheduler, synth
 from oracle import nets, weights
 
 dev = torch.device("cuda:0")
+OPTS = [int(a) for a in sys.argv[1:]] or [0, 1, 2]
 wavs = [synth.mixed(i, n) for i, n in enumerate((48000, 25600, 64000, 16000 * 7 + 123))]
 for kind in ("W0", "W1", "W2"):
     sdc = weights.campplus_state_dict(kind)
     want = nets.campplus_embed_wavs(sdc, wavs)
     cp = CAMPPlus(); cp.load_state_dict(sdc); cp = cp.to(dev).eval()
     ctx = cp._ctx()
-    for opt in (0, 1):
+    for opt in OPTS:
         ctx.set_option("cat_bf16", opt)
         got = cp.inference([torch.from_numpy(w) for w in wavs]).cpu().numpy()
         err = float(np.abs(got - want).max())
@@ -49,7 +52,7 @@ def run(flags):
 
 
 ref = None
-for opt in (0, 1):
+for opt in OPTS:
     ctx.set_option("cat_bf16", opt)
     ms_x, xv = run(_lib.DO_XV)
     ms_b, _ = run(_lib.DO_VE | _lib.DO_XV)
