@@ -8,6 +8,8 @@ accumulates in fp32 (torch CPU); everything else stays fp32.  TF32 rounding (10-
 today) is reported beside it as the yardstick.
 
     python tests/tools/bf16_study.py [n_clips] [clip_seconds]
+    python tests/tools/bf16_study.py settings      # the two built settings of the cat_bf16 option, emulated on the clips of
+                                                   # cat_bf16_check.py (prediction beside the GPU measurement)
 
 Output: per weight set (W0 default init, W1 randomised BN, W2 sensitised / calibrated) and per family set, the max-abs
 error and minimum cosine of the 192-d x-vector and of the 256-d VoiceEncoder embedding against the fp32 oracle.
@@ -39,8 +41,10 @@ def to_tf32(x):
 class Rounding:
     """Patches F.conv1d / F.conv2d as seen by oracle.nets; the family of a call is decided from the weight's shape."""
 
-    def __init__(self, families, rnd):
-        self.families, self.rnd = set(families), rnd
+    def __init__(self, families, rnd, rnd_w=None, others=None):
+        """families: rounded with ``rnd`` (activations) / ``rnd_w`` (weights; default = rnd); every other family with
+        ``others`` (both operands) if given."""
+        self.families, self.rnd, self.rnd_w, self.others = set(families), rnd, rnd_w or rnd, others
 
     @staticmethod
     def family(w):
@@ -64,15 +68,16 @@ class Rounding:
         self.c1, self.c2 = F.conv1d, F.conv2d
         me = self
 
-        def conv1d(x, w, *a, **k):
+        def operands(x, w):
             if me.family(w) in me.families:
-                x, w = me.rnd(x), me.rnd(w)
-            return me.c1(x, w, *a, **k)
+                return me.rnd(x), me.rnd_w(w)
+            return (me.others(x), me.others(w)) if me.others else (x, w)
+
+        def conv1d(x, w, *a, **k):
+            return me.c1(*operands(x, w), *a, **k)
 
         def conv2d(x, w, *a, **k):
-            if me.family(w) in me.families:
-                x, w = me.rnd(x), me.rnd(w)
-            return me.c2(x, w, *a, **k)
+            return me.c2(*operands(x, w), *a, **k)
 
         nets.F.conv1d, nets.F.conv2d = conv1d, conv2d
         return self
@@ -119,7 +124,29 @@ def report(name, got, want):
     print(f"  {name:<44s} max-abs {err:9.2e}   min cos {cos:.6f}", flush=True)
 
 
+def settings():
+    """cat_bf16 = 1: the bottleneck / transit GEMMs read bf16 activations (then BN + ReLU, tf32 stage), weights tf32;
+    cat_bf16 = 2: their operands are bf16.  Everything else TF32, as on the GPU.  The BN + ReLU between the stored activation
+    and the MMA operand is not re-rounded here (setting 1 rounds the stored value; the tf32 rounding after BN is implied by
+    rounding the convolution input), which is what the kernels do up to the order of two roundings."""
+    wavs = [synth.mixed(i, n) for i, n in enumerate((48000, 25600, 64000, 16000 * 7 + 123))]
+    fam = ("bottleneck", "transit")
+    with torch.inference_mode():
+        for kind in ("W0", "W1", "W2"):
+            sdc = weights.campplus_state_dict(kind)
+            want = nets.campplus_embed_wavs(sdc, wavs)
+            print(f"CAMPPlus {kind}: |x-vector| max {np.abs(want).max():.3f}")
+            with Rounding((), to_tf32, others=to_tf32):
+                report("tf32 everywhere (cat_bf16 = 0)", nets.campplus_embed_wavs(sdc, wavs), want)
+            with Rounding(fam, to_bf16, rnd_w=to_tf32, others=to_tf32):
+                report("cat_bf16 = 1 (bf16 activations into those GEMMs)", nets.campplus_embed_wavs(sdc, wavs), want)
+            with Rounding(fam, to_bf16, others=to_tf32):
+                report("cat_bf16 = 2 (bf16 operands)", nets.campplus_embed_wavs(sdc, wavs), want)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "settings":
+        return settings()
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     secs = float(sys.argv[2]) if len(sys.argv) > 2 else 4.0
     torch.set_num_threads(os.cpu_count() or 1)
