@@ -67,7 +67,8 @@ class WeightSync:
 
     def _cbx_fingerprint(self, dev):
         ts = self._cbx_tensors()
-        return (dev, id(self), len(ts), sum(v._version for _, v in ts), ts[0][1].data_ptr(), ts[-1][1].data_ptr())
+        # every tensor's storage address and version: `p.data = ...` / `set_()` of any tensor is seen, not only in-place edits
+        return (dev, id(self), len(ts), hash(tuple((v.data_ptr(), v._version) for _, v in ts)))
 
     def _apply(self, fn, *args, **kwargs):
         self.__dict__.pop("_cbx_cache", None)

@@ -213,7 +213,7 @@ int cbx_create(int device, cbx_ctx** out) {
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, device);
   if (prop.major != 10) { g_create_err = "libcbx is built for sm_100a only; found sm_" + std::to_string(prop.major * 10 + prop.minor); return CBX_ERR_CUDA; }
-  cudaSetDevice(device);
+  DeviceGuard dev_guard(device);
   cbx_ctx* c = new cbx_ctx();
   c->device = device;
   int rc = build_frontend_tables(c);
@@ -222,6 +222,7 @@ int cbx_create(int device, cbx_ctx** out) {
   cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming);
   cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking);
   for (auto& s : c->slot) {
@@ -235,7 +236,7 @@ int cbx_create(int device, cbx_ctx** out) {
 
 void cbx_destroy(cbx_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaFree(c->ve.blob); cudaFree(c->xv.blob); cudaFree(c->ft.blob);
   cudaDeviceSynchronize();
   cudaFree(c->own_ws);
@@ -257,6 +258,7 @@ void cbx_destroy(cbx_ctx* c) {
   if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_order) cudaEventDestroy(c->ev_order);
   if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   delete c;
@@ -272,12 +274,14 @@ int cbx_set_option(cbx_ctx* c, const char* key, int64_t v) {
   else if (k == "lstm_chunk_partials" && v >= 1) c->lstm_chunk_slots = v;
   else if (k == "mode" && (v == 0 || v == 1)) c->mode = v;
   else if (k == "overlap" && (v == 0 || v == 1)) c->overlap = v;
+#ifdef CBX_DEV_TOOLS   // timing experiments of tools/ (results are wrong while "probe" is set): not in the product library
   else if (k == "lstm_dbg") c->lstm_dbg = v;
   else if (k == "probe") c->probe = v;
+  else if (k == "lstm_impl" && (v == 1 || v == 2)) c->lstm_impl = v;
+#endif
   else if (k == "cat_bf16" && v >= 0 && v <= 2) c->cat_bf16 = v;
   else if (k == "pdl") c->pdl = v;
   else if (k == "batch_invariant") c->batch_invariant = v;
-  else if (k == "lstm_impl" && (v == 1 || v == 2)) c->lstm_impl = v;
   else if (k == "lstm_trace") c->lstm_trace = v;
   else { c->err = "bad option " + k; return CBX_ERR_ARG; }
   return CBX_OK;
@@ -293,14 +297,16 @@ int64_t cbx_get_option(const cbx_ctx* c, const char* key) {
   if (k == "overlap") return c->overlap;
   if (k == "pdl") return c->pdl;
   if (k == "batch_invariant") return c->batch_invariant;
+#ifdef CBX_DEV_TOOLS
   if (k == "probe") return c->probe;
+#endif
   if (k == "cat_bf16") return c->cat_bf16;
   return -1;
 }
 
 int cbx_load_weights(cbx_ctx* c, int which, int n, const char* const* names, const float* const* data, const int64_t* numel) {
   if (!c || !names || !data || !numel || n <= 0) return CBX_ERR_ARG;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   std::map<std::string, std::pair<const float*, int64_t>> t;
   for (int i = 0; i < n; ++i) t[names[i]] = {data[i], numel[i]};
   if (which == 0) return load_ve(c, t);
@@ -322,8 +328,9 @@ int cbx_embed(cbx_ctx* c, const float* pcm, const int64_t* off, int n, float tri
   int rc = check_inputs(c, off, n, step, flags);
   if (rc) return rc;
   if (!pcm || !ws || !status || ((flags & CBX_DO_VE) && !ve_out) || ((flags & CBX_DO_XV) && !xv_out)) { c->err = "null device pointer"; return CBX_ERR_ARG; }
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
+  enter_stream(c, st);
   Batch b{n, off, step, min_cov};
   if (ws_bytes < workspace_bytes_for(c, b, flags)) { c->err = "workspace too small"; return CBX_ERR_WORKSPACE; }
   ChunkSets cs = make_chunks(c, b, flags);
@@ -397,7 +404,7 @@ int cbx_embed_host_submit(cbx_ctx* c, int slot_id, const float* pcm_host, const 
   if (slot_id < 0 || slot_id > 1) { c->err = "slot must be 0 or 1"; return CBX_ERR_ARG; }
   cbx_ctx::HostSlot& s = c->slot[slot_id];
   if (s.busy) { c->err = "slot still holds an unclaimed batch: call cbx_embed_host_wait first"; return CBX_ERR_STATE; }
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   const int64_t total = off[n] - off[0];
   Batch b{n, off, step, min_cov};
   const int64_t need_ws = workspace_bytes_for(c, b, flags);
@@ -439,7 +446,7 @@ int cbx_embed_host_wait(cbx_ctx* c, int slot_id, float* ve_out_host, float* xv_o
   if (slot_id < 0 || slot_id > 1) { c->err = "slot must be 0 or 1"; return CBX_ERR_ARG; }
   cbx_ctx::HostSlot& s = c->slot[slot_id];
   if (!s.busy) { c->err = "nothing was submitted to this slot"; return CBX_ERR_STATE; }
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   CBX_CUDA_OK(c, cudaEventSynchronize(s.d2h));
   s.busy = false;
   const int n = s.n;
@@ -472,7 +479,8 @@ int cbx_ve_forward_partials(cbx_ctx* c, const float* mels, int n, float* out, vo
   if (!mels || !out || !ws || n <= 0) { c->err = "bad argument"; return CBX_ERR_ARG; }
   if (!c->ve.loaded) { c->err = "VoiceEncoder weights not loaded"; return CBX_ERR_STATE; }
   if (ws_bytes < cbx_ve_forward_workspace_bytes(c, n)) { c->err = "workspace too small"; return CBX_ERR_WORKSPACE; }
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
+  enter_stream(c, (cudaStream_t)stream);
   run_ve_forward_partials(c, mels, n, out, ws, (cudaStream_t)stream);
   CBX_CUDA_OK(c, cudaGetLastError());
   return CBX_OK;
@@ -511,7 +519,7 @@ int cbx_profile_enable(cbx_ctx* c, int on) {
 
 int64_t cbx_profile_report(cbx_ctx* c, char* buf, int64_t cap) {
   if (!c) return CBX_ERR_ARG;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaDeviceSynchronize();
   struct Acc { int64_t n = 0; double ms = 0, flops = 0, bytes = 0; };
   std::map<std::string, Acc> acc;

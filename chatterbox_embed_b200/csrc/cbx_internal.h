@@ -183,12 +183,41 @@ struct cbx_ctx {
   // S3Tokenizer log-mel (frontend_tc.cu): clip table, per-clip maxima, [frames][128] scratch
   void* s3_clips = nullptr; int s3_clips_cap = 0;
   float* s3_tmp = nullptr; int64_t s3_tmp_cap = 0;
+  // Stream discipline (include/cbx.h "Conventions"): the context's tables and scratch buffers (clip tables of the resampler /
+  // prompt mel / S3 front-end, their scratch, the shared workspace of the host path, the aux stream's fork / join events) are
+  // single buffers.  Every stream-ordered entry point calls cbx::enter_stream(): when the caller's stream differs from the
+  // one the previous call used, the new stream first waits for everything the previous stream had been given, so two calls on
+  // different streams can never overlap on those buffers (they serialise instead of corrupting each other).
+  cudaStream_t last_stream = nullptr; bool last_stream_valid = false;
+  cudaEvent_t ev_order = nullptr;
   // last-run bookkeeping for the stage taps
   std::vector<cbx::ClipPlan> last_plan;
   std::map<std::string, std::vector<int64_t>> taps;   // name -> {byte_offset, rows, cols, ld}
 };
 
 namespace cbx {
+
+// RAII: make the context's device current for the duration of an entry point and put the caller's device back afterwards
+// (a single-process multi-GPU caller must not find its current device switched under it)
+struct DeviceGuard {
+  int prev = -1; bool changed = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) { cudaSetDevice(dev); changed = true; }
+  }
+  ~DeviceGuard() { if (changed && prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// see cbx_ctx::last_stream
+inline void enter_stream(cbx_ctx* c, cudaStream_t st) {
+  if (c->last_stream_valid && c->last_stream != st && c->ev_order) {
+    cudaEventRecord(c->ev_order, c->last_stream);
+    cudaStreamWaitEvent(st, c->ev_order, 0);
+  }
+  c->last_stream = st; c->last_stream_valid = true;
+}
 
 // host integer logic (host_plan.cpp)
 int ve_frame_step(double overlap, double rate);

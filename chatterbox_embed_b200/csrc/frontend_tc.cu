@@ -329,8 +329,9 @@ int64_t cbx_s3_log_mel_frames(int64_t n_samples) {
 int cbx_s3_log_mel(cbx_ctx* c, const float* pcm_dev, const int64_t* offsets_host, int n_clips, float* out_dev, void* stream) {
   if (!c) return CBX_ERR_ARG;
   if (!pcm_dev || !out_dev || !offsets_host || n_clips <= 0) { c->err = "bad argument"; return CBX_ERR_ARG; }
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
+  enter_stream(c, st);
   // host image of the device table: n_clips S3Clip records followed by n_clips floats of -inf (the identity of note_max)
   const size_t table_bytes = (sizeof(fe::S3Clip) + sizeof(float)) * (size_t)n_clips;
   std::vector<uint8_t> host(table_bytes);

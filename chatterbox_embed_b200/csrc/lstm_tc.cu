@@ -110,6 +110,7 @@ __device__ __forceinline__ float tanh_acc(float x) {
   return fmaf(2.f, rcp_approx(1.f + e), -1.f);
 }
 
+#ifdef CBX_DEV_TOOLS   // v1 of the recurrence (DSMEM pushes), kept for tools/ comparisons only
 struct Params {
   const float* xw;            // [rows][1024], columns permuted: col = 128 j + 4 u + g  <->  gate g of unit 32 j + u
   const int32_t* slot_row;    // layer 0: first xw row of each partial slot (mel row); nullptr: row = slot * 160
@@ -306,6 +307,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) lstm_re
   }
 }
 
+
+#endif  // CBX_DEV_TOOLS
 
 // =====================================================================================================================
 // v2 of the recurrence.  Same decomposition (8-CTA cluster, W_hh slice in TMEM as the A operand, two ping-pong sub-tiles
@@ -607,6 +610,7 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
 
 }  // namespace lstm
 
+#ifdef CBX_DEV_TOOLS
 void run_lstm_rec_tc(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
                      int n_slots, cudaStream_t st) {
   if (n_slots <= 0) return;
@@ -623,7 +627,7 @@ void run_lstm_rec_tc(cbx_ctx* c, const float* xw, const int32_t* slot_row, const
 extern "C" int cbx_lstm_max_clusters(cbx_ctx* c) {
   using namespace cbx;
   if (!c) return -1;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaFuncSetAttribute(lstm::lstm_rec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lstm::SMEM_BYTES);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(lstm::CL * 64); cfg.blockDim = dim3(lstm::THREADS); cfg.dynamicSmemBytes = lstm::SMEM_BYTES;
@@ -635,6 +639,9 @@ extern "C" int cbx_lstm_max_clusters(cbx_ctx* c) {
   if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return -2; }
   return n;
 }
+#else
+}  // namespace cbx
+#endif  // CBX_DEV_TOOLS
 
 namespace cbx {
 // v2 entry point.  hseq / xw rows are in the tiled time-major order (see lstm_rec_tc2_kernel); both must hold

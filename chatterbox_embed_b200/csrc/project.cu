@@ -73,8 +73,9 @@ extern "C" int cbx_project(cbx_ctx* c, const float* x_dev, int64_t n, int in_dim
   if (!c) return CBX_ERR_ARG;
   if (!x_dev || !w_dev || !y_dev || n < 0 || in_dim <= 0 || in_dim > proj::MAX_K || out_dim <= 0) { c->err = "cbx_project: bad argument"; return CBX_ERR_ARG; }
   if (n == 0) return CBX_OK;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
+  enter_stream(c, st);
   const size_t smem = (size_t)proj::ROWS * (in_dim + 1) * sizeof(float);
   ensure_max_smem(proj::project_kernel, proj::ROWS * (proj::MAX_K + 1) * 4);
   const long long blocks = (n + proj::ROWS - 1) / proj::ROWS;

@@ -305,8 +305,9 @@ int64_t cbx_prompt_mel_frames(int64_t n_samples) {
 int cbx_prompt_mel(cbx_ctx* c, const float* pcm_dev, const int64_t* offsets_host, int n_clips, float* out_dev, void* stream) {
   if (!c) return CBX_ERR_ARG;
   if (!pcm_dev || !out_dev || !offsets_host || n_clips <= 0) { c->err = "bad argument"; return CBX_ERR_ARG; }
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
+  enter_stream(c, st);
   PromptMelTables& T = c->pm;
   if (!T.ready) { int rc = pm::build_tables(c); if (rc) return rc; }
   std::vector<pm::Clip> clips(n_clips);

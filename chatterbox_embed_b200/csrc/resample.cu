@@ -89,8 +89,9 @@ int cbx_resample(cbx_ctx* c, const float* x_dev, const int64_t* in_offsets_host,
                  float* y_dev, const int64_t* out_offsets_host, void* stream) {
   if (!c) return CBX_ERR_ARG;
   if (!x_dev || !y_dev || !in_offsets_host || !out_offsets_host || n_clips <= 0 || src_sr <= 0 || dst_sr <= 0) { c->err = "bad argument"; return CBX_ERR_ARG; }
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
+  enter_stream(c, st);
   const int g = std::gcd(src_sr, dst_sr);
   const int orig = src_sr / g, nnew = dst_sr / g;
   const double lpw = 6.0, rolloff = 0.99;

@@ -80,6 +80,7 @@ CUtensorMap make_map_2d_bf16(const void* base, int64_t rows, int64_t cols, int64
 }  // namespace tc
 }  // namespace cbx
 
+#ifdef CBX_DEV_TOOLS   // kernel unit-test / timing entry points for the scripts under tools/: NOT part of the product library (build.py, CBX_DEV_TOOLS=1)
 using namespace cbx;
 
 // same functor under a type of this translation unit: the kernel template is then instantiated HERE (next to the trace pointer
@@ -90,7 +91,7 @@ extern "C" int cbx_test_tgemm(cbx_ctx* c, const float* A, int64_t lda, const flo
                               int M, int N, int K, const float* bias, const float* pro_a, const float* pro_b, int variant,
                               int shift1, void* stream) {
   if (!c) return CBX_ERR_ARG;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (!tc::encode_fn()) { c->err = "cuTensorMapEncodeTiled unavailable"; return CBX_ERR_CUDA; }
   tc::TapMap tap = tc::plain_map(K);
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(128) shift_gemm_kernel(const __grid_constant__
 extern "C" int cbx_test_shift_gemm(cbx_ctx* c, const float* A /*[256][32]*/, const float* W /*[32][32]*/, float* C /*[128][32]*/,
                                    int shift, int use_base_offset) {
   if (!c) return CBX_ERR_ARG;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   CUtensorMap tmA = tc::make_map_2d(A, 256, 32, 32, 128, true);
   CUtensorMap tmW = tc::make_map_2d(W, 32, 32, 32, 32, true);
   const int smem = 256 * 128 + 32 * 128 + 1024 + 64;
@@ -192,3 +193,4 @@ extern "C" int cbx_test_shift_gemm(cbx_ctx* c, const float* A /*[256][32]*/, con
   CBX_CUDA_OK(c, cudaDeviceSynchronize());
   return CBX_OK;
 }
+#endif  // CBX_DEV_TOOLS

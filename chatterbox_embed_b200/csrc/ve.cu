@@ -281,7 +281,10 @@ void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st) {
     // hop 77 < 160) and the recurrence gathers rows through slot_row.
     CUtensorMap tmA = tc::make_map_2d(ch.mel, ch.mel_rows, kVeMels, kVeMels, tc::BM, true);
     tc::pgemm_bias_tma<256, 4>(L, st, "lstm_xw0_gemm", tmA, W.tm_wih_p256[0], ch.xw0, kVeGates, W.bias_p[0], ch.mel_rows, kVeGates, kVeMels);
-    if (c->lstm_impl == 2) {
+#ifdef CBX_DEV_TOOLS
+    if (c->lstm_impl == 2)
+#endif
+    {
       // L2-exchange recurrence: hseq / xw of layers 1, 2 in the tiled time-major row order over whole 224-partial tiles
       const int prow = lstm_padded_slots(ch.slots) * kVePartial;
       run_lstm_rec_tc2(c, ch.xw0, ch.slot_row, W.whh_p[0], ch.hseq, nullptr, ch.slots, st);
@@ -293,6 +296,7 @@ void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st) {
       { Scope sc(L, st, "ve_proj_kernel"); ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hlast, (size_t)kVeHidden, W.wpT, W.bp, ch.pemb); }
       return;
     }
+#ifdef CBX_DEV_TOOLS   // v1 recurrence (DSMEM pushes), tools/ comparisons only
     run_lstm_rec_tc(c, ch.xw0, ch.slot_row, W.whh_p[0], ch.hseq, nullptr, ch.slots, st);
     for (int l = 1; l < 3; ++l) {
       CUtensorMap tmH = tc::make_map_2d(ch.hseq, rows, kVeHidden, kVeHidden, tc::BM, true);
@@ -302,6 +306,7 @@ void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st) {
     }
     { Scope sc(L, st, "ve_proj_kernel"); ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hlast, (size_t)kVeHidden, W.wpT, W.bp, ch.pemb); }
     return;
+#endif
   }
   // strict-fp32 path
   const int nb = (ch.slots + LSTM_MT - 1) / LSTM_MT;

@@ -483,9 +483,12 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
                                  tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
       else
         sgemm(L, st, "dense_bottleneck_gemm", M, kBnC, D.cin, BnReluA{cat, ld, D.a1, D.b1}, D.w1, D.cin, BiasReluMaskEpi{ch.u, kBnC, D.t2, ch.td_row_clip});
+#ifdef CBX_DEV_TOOLS
       if (ch.segs > 0 && tcm && (c->probe & 1)) {
         // timing probe: what the step costs without this kernel on the chain (stale gates, sums never zeroed: wrong results)
-      } else if (ch.segs > 0 && tcm) {
+      } else
+#endif
+      if (ch.segs > 0 && tcm) {
         Scope sc(L, st, "cam_gate_kernel");
         tc::launch_pdl(cam_gate_clip_kernel, dim3(ch.n_clips), dim3(256), 0, st, pdl, reinterpret_cast<unsigned long long*>(ch.seg_sum), ch.plan, D, ch.gate);
       } else if (ch.segs > 0) {

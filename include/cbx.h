@@ -16,7 +16,13 @@
  * from cbx_last_error(); device pointers are caller-owned; work is stream
  * ordered on the stream passed in (a cudaStream_t cast to void*; NULL = the
  * legacy default stream) and the calls do not synchronise unless stated; one
- * context per GPU, not thread-safe.  There is NO CPU fallback: every compute
+ * context per GPU, not thread-safe (one host thread at a time per context).
+ * The context's device tables and scratch buffers are single buffers: when a
+ * call arrives on a different stream than the previous call, the library makes
+ * the new stream wait (event) for everything queued on the previous one, so
+ * calls on two streams serialise instead of overwriting each other's tables.
+ * Every entry point restores the caller's current device before returning.
+ * There is NO CPU fallback: every compute
  * entry point fails with CBX_ERR_CUDA when no sm_100 device is usable.
  */
 #ifndef CBX_H_
