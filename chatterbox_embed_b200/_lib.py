@@ -57,6 +57,8 @@ _SIGS = {
     "cbx_resample": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_void_p, _P(C.c_int64), C.c_void_p]),
     "cbx_ve_forward_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "cbx_ve_forward_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int]),
+    "cbx_campplus_forward_feats": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_int64), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cbx_campplus_forward_workspace_bytes": (C.c_int64, [C.c_void_p, _P(C.c_int64), C.c_int]),
     "cbx_locate": (C.c_int, [C.c_void_p, C.c_char_p, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64), _P(C.c_int64)]),
     "cbx_clip_rows": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64), _P(C.c_int64)]),
     "cbx_launch_count": (C.c_int64, [C.c_void_p]),
@@ -223,6 +225,18 @@ class Context:
         self._check(lib().cbx_embed_host_wait(self._h, int(slot), ve.ctypes.data if ve is not None else None,
                                               xv.ctypes.data if xv is not None else None, status.ctypes.data), "cbx_embed_host_wait")
         return ve, xv, status
+
+    def campplus_forward_workspace_bytes(self, frame_offsets: Sequence[int]) -> int:
+        keep, a = _i64(frame_offsets)
+        n = lib().cbx_campplus_forward_workspace_bytes(self._h, a, len(frame_offsets) - 1)
+        if n < 0:
+            raise CbxError("cbx_campplus_forward_workspace_bytes: bad argument")
+        return int(n)
+
+    def campplus_forward_feats(self, feats_ptr: int, frame_offsets: Sequence[int], xv_ptr: int, status_ptr: int, ws_ptr: int, ws_bytes: int, stream: int):
+        keep, a = _i64(frame_offsets)
+        self._check(lib().cbx_campplus_forward_feats(self._h, feats_ptr, a, len(frame_offsets) - 1, xv_ptr, status_ptr, ws_ptr, ws_bytes, stream),
+                    "cbx_campplus_forward_feats")
 
     def resample(self, x_ptr: int, in_offsets: Sequence[int], src_sr: int, dst_sr: int, y_ptr: int, out_offsets: Sequence[int], stream: int):
         n = len(in_offsets) - 1

@@ -158,6 +158,26 @@ class CAMPPlus(_host.WeightSync, nn.Module):
         _host.raise_for_status(status.cpu().numpy(), flags)
         return out
 
+    @torch.inference_mode()
     def forward(self, x):
-        raise NotImplementedError("CAMPPlus.forward on precomputed features is not part of the B200 path; "
-                                  "use inference(audio_list) (xvector.py:425-428)")
+        """(B, T, 80) features (what extract_feature returns: log-fbank, mean-normalised) -> (B, 192)  (xvector.py:417-423).
+        A list of (T_i, 80) tensors is taken as a ragged batch (each clip pooled over its own frames)."""
+        ctx = self._ctx()
+        dev = self.device
+        if torch.is_tensor(x):
+            assert x.dim() == 3 and x.shape[2] == 80, "expected (B, T, 80) features"
+            feats = x.to(dev, torch.float32).contiguous()
+            frames = [int(x.shape[1])] * int(x.shape[0])
+        else:
+            rows = [torch.as_tensor(f).to(dev, torch.float32).reshape(-1, 80) for f in x]
+            frames = [int(r.shape[0]) for r in rows]
+            feats = torch.cat(rows).contiguous()
+        n = len(frames)
+        assert n > 0 and min(frames) > 0, "expected at least one frame per clip"
+        off = np.concatenate([[0], np.cumsum(frames)]).astype(np.int64)
+        out = torch.empty((n, 192), dtype=torch.float32, device=dev)
+        status = torch.zeros(n, dtype=torch.int32, device=dev)
+        ws = self._ws.get(ctx.campplus_forward_workspace_bytes(off), dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ctx.campplus_forward_feats(feats.data_ptr(), off, out.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        return out

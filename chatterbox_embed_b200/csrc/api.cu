@@ -42,6 +42,8 @@ VeLayout plan_ve(const Batch& b, int c0, int c1) {
 VeChunk carve_ve(Carver& cv, const VeLayout& L, cbx_ctx* c) {
   VeChunk ch{};
   ch.n_clips = (int)L.plan.size(); ch.mel_rows = L.mel_rows; ch.slots = L.slots; ch.trim_blocks = L.trim_blocks;
+  ch.pcm_samples = 0;
+  for (const ClipPlan& p : L.plan) ch.pcm_samples += p.n_samples;
   ch.plan = cv.take<ClipPlan>(ch.n_clips);
   ch.dyn = cv.take<ClipDyn>(ch.n_clips);
   ch.trim_scratch = cv.take<float>(L.trim_blocks);
@@ -54,12 +56,13 @@ VeChunk carve_ve(Carver& cv, const VeLayout& L, cbx_ctx* c) {
   const int64_t pslots = lstm_padded_slots(L.slots);       // the tensor-core recurrence works on whole 224-partial tiles
   ch.xw = cv.take<float>(pslots * kVePartial * kVeGates);
   ch.hseq = cv.take<float>(pslots * kVePartial * kVeHidden);
-  ch.hlast = cv.take<float>((int64_t)L.slots * kVeHidden);
+  ch.hlast = cv.take<float>((int64_t)3 * L.slots * kVeHidden);    // last hidden state of every layer (layer l at l * slots * 256)
   ch.pemb = cv.take<float>((int64_t)L.slots * kVeEmbed);
   if (cv.base && c) {
     c->taps["ve_dyn"] = {(char*)ch.dyn - cv.base, ch.n_clips, 6, 6};
     c->taps["ve_mel"] = {(char*)ch.mel - cv.base, L.mel_rows, kVeMels, kVeMels};
     c->taps["ve_partial_emb"] = {(char*)ch.pemb - cv.base, L.slots, kVeEmbed, kVeEmbed};
+    c->taps["ve_hlast"] = {(char*)ch.hlast - cv.base, 3 * (int64_t)L.slots, kVeHidden, kVeHidden};
   }
   return ch;
 }
@@ -323,11 +326,13 @@ int64_t cbx_workspace_bytes(cbx_ctx* c, int n, const int64_t* lengths, int step,
   return workspace_bytes_for(c, b, flags);
 }
 
-int cbx_embed(cbx_ctx* c, const float* pcm, const int64_t* off, int n, float trim_top_db, int step, double min_cov,
-              float* ve_out, float* xv_out, int32_t* status, void* ws, int64_t ws_bytes, void* stream, int flags) {
+// pcm: the clips' samples; or (CAMPPlus.forward on precomputed features) feats [sum T_i][80] with feat_off[n + 1] in frames and
+// `off` the equivalent sample offsets (a clip of T frames plans like one of 400 + 160 (T - 1) samples)
+static int embed_core(cbx_ctx* c, const float* pcm, const float* feats, const int64_t* feat_off, const int64_t* off, int n, float trim_top_db,
+                      int step, double min_cov, float* ve_out, float* xv_out, int32_t* status, void* ws, int64_t ws_bytes, void* stream, int flags) {
   int rc = check_inputs(c, off, n, step, flags);
   if (rc) return rc;
-  if (!pcm || !ws || !status || ((flags & CBX_DO_VE) && !ve_out) || ((flags & CBX_DO_XV) && !xv_out)) { c->err = "null device pointer"; return CBX_ERR_ARG; }
+  if ((!pcm && !feats) || !ws || !status || ((flags & CBX_DO_VE) && !ve_out) || ((flags & CBX_DO_XV) && !xv_out)) { c->err = "null device pointer"; return CBX_ERR_ARG; }
   DeviceGuard dev_guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
   enter_stream(c, st);
@@ -373,7 +378,7 @@ int cbx_embed(cbx_ctx* c, const float* pcm, const int64_t* off, int n, float tri
     XvChunk ch = carve_xv(cv_abs, L, c, c->cat_bf16 != 0);
     ch.hplan = L.plan.data();
     CBX_CUDA_OK(c, cudaMemcpyAsync(ch.plan, L.plan.data(), sizeof(ClipPlan) * L.plan.size(), cudaMemcpyHostToDevice, sx));
-    run_xv_chunk(c, pcm, ch, xv_out, status, sx);
+    run_xv_chunk(c, pcm, ch, xv_out, status, sx, feats, feat_off);
     for (size_t i = 0; i < L.plan.size(); ++i) {
       ClipPlan& lp = c->last_plan[r.first + i];
       lp.fb_row = L.plan[i].fb_row; lp.td_row = L.plan[i].td_row; lp.xv_frames = L.plan[i].xv_frames; lp.xv_tdnn = L.plan[i].xv_tdnn;
@@ -385,6 +390,39 @@ int cbx_embed(cbx_ctx* c, const float* pcm, const int64_t* off, int n, float tri
   }
   CBX_CUDA_OK(c, cudaGetLastError());
   return CBX_OK;
+}
+
+int cbx_embed(cbx_ctx* c, const float* pcm, const int64_t* off, int n, float trim_top_db, int step, double min_cov,
+              float* ve_out, float* xv_out, int32_t* status, void* ws, int64_t ws_bytes, void* stream, int flags) {
+  if (c && !pcm) { c->err = "null device pointer"; return CBX_ERR_ARG; }
+  return embed_core(c, pcm, nullptr, nullptr, off, n, trim_top_db, step, min_cov, ve_out, xv_out, status, ws, ws_bytes, stream, flags);
+}
+
+// CAMPPlus.forward (xvector.py:417-423): features in, x-vectors out -- the fbank / CMN front end is skipped
+static std::vector<int64_t> feat_sample_offsets(const int64_t* frame_off, int n) {
+  std::vector<int64_t> off(n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    const int64_t t = frame_off[i + 1] - frame_off[i];
+    off[i + 1] = off[i] + (t > 0 ? kKWin + kKHop * (t - 1) : 0);
+  }
+  return off;
+}
+
+int64_t cbx_campplus_forward_workspace_bytes(cbx_ctx* c, const int64_t* frame_off, int n) {
+  if (!c || !frame_off || n <= 0) return CBX_ERR_ARG;
+  for (int i = 0; i < n; ++i) if (frame_off[i + 1] < frame_off[i]) return CBX_ERR_ARG;
+  std::vector<int64_t> off = feat_sample_offsets(frame_off, n);
+  Batch b{n, off.data(), 77, 0.8};
+  return workspace_bytes_for(c, b, CBX_DO_XV);
+}
+
+int cbx_campplus_forward_feats(cbx_ctx* c, const float* feats, const int64_t* frame_off, int n, float* xv_out, int32_t* status,
+                               void* ws, int64_t ws_bytes, void* stream) {
+  if (!c) return CBX_ERR_ARG;
+  if (!feats || !frame_off || n <= 0) { c->err = "bad argument"; return CBX_ERR_ARG; }
+  for (int i = 0; i < n; ++i) if (frame_off[i + 1] < frame_off[i]) { c->err = "frame offsets must be non-decreasing"; return CBX_ERR_ARG; }
+  std::vector<int64_t> off = feat_sample_offsets(frame_off, n);
+  return embed_core(c, nullptr, feats, frame_off, off.data(), n, 0.f, 77, 0.8, nullptr, xv_out, status, ws, ws_bytes, stream, CBX_DO_XV | CBX_NO_TRIM);
 }
 
 static int grow(cbx_ctx* c, void** p, int64_t* have, int64_t want, bool pinned) {   // sizes in bytes
@@ -470,7 +508,7 @@ int64_t cbx_ve_forward_workspace_bytes(cbx_ctx* c, int n) {
   cv.take<int32_t>(n);
   cv.take<float>((int64_t)lstm_padded_slots(n) * kVePartial * kVeGates);
   cv.take<float>((int64_t)lstm_padded_slots(n) * kVePartial * kVeHidden);
-  cv.take<float>((int64_t)n * kVeHidden);
+  cv.take<float>((int64_t)3 * n * kVeHidden);
   return cv.off + 1024;
 }
 

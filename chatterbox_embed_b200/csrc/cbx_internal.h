@@ -247,6 +247,7 @@ struct Carver {
 
 struct VeChunk {            // device buffers of one VoiceEncoder chunk
   int n_clips; int mel_rows; int slots; int trim_blocks;
+  int64_t pcm_samples;      // samples of the chunk's clips (algorithmic bytes of the trim kernel)
   ClipPlan* plan; ClipDyn* dyn;
   float* trim_scratch;
   int32_t* mel_row_clip;    // [mel_rows]
@@ -257,7 +258,7 @@ struct VeChunk {            // device buffers of one VoiceEncoder chunk
   float* xw0;               // [mel_rows][1024]
   float* xw;                // [slots*160][1024]
   float* hseq;              // [slots*160][256]
-  float* hlast;             // [slots][256]  final hidden state of layer 3 (tensor-core recurrence)
+  float* hlast;             // [3][slots][256]  final hidden state of each layer (stage tap; layer 3 feeds the projection)
   float* pemb;              // [slots][256]
 };
 
@@ -301,7 +302,10 @@ void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const 
                      const char* tag = "fcm_conv_gemm", bool pdl = false);   // fcm_tc.cu
 void run_lstm_rec_tc(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
                      int n_slots, cudaStream_t st);   // lstm_tc.cu
-void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out, int32_t* status, cudaStream_t st);
+// feats != nullptr: CAMPPlus.forward on precomputed (already mean-normalised) features [sum T][80]; feat_off (host, frames, indexed by the
+// clip's position in the call) says where each clip's rows start; the fbank / CMN kernels are skipped
+void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out, int32_t* status, cudaStream_t st,
+                  const float* feats = nullptr, const int64_t* feat_off = nullptr);
 
 }  // namespace cbx
 

@@ -276,7 +276,7 @@ void launch(cbx_ctx* c, cudaStream_t st, const char* tag, const CUtensorMap& hi0
   if (rows <= 0) return;
   auto kern = dftmel_kernel<Rows, NB1, NMEL, LOG>;
   ensure_max_smem(kern, SMEM_BYTES);
-  Scope sc(c->launches, st, tag, 3.0 * 2.0 * rows * (256 + NB1) * KTOT, 4.0 * rows * (160 + NMEL));   // one hop of PCM in, one feature row out
+  Scope sc(c->launches, st, tag, 2.0 * rows * (256 + NB1) * KTOT, 4.0 * rows * (160 + NMEL));   // ALGORITHMIC: one fp32 DFT per frame (the 3xTF32 split executes 3x this on the tensor pipe); one hop of PCM in, one feature row out
   kern<<<(rows + BM - 1) / BM, 192, SMEM_BYTES, st>>>(hi0, lo0, hi1, lo1, pcm, rf, reinterpret_cast<const float4*>(bintab), out, rows);
 }
 

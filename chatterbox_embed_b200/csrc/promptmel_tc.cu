@@ -328,7 +328,7 @@ int cbx_prompt_mel(cbx_ctx* c, const float* pcm_dev, const int64_t* offsets_host
   }
   CBX_CUDA_OK(c, cudaMemcpyAsync(T.clips, clips.data(), sizeof(pm::Clip) * n_clips, cudaMemcpyHostToDevice, st));
   {
-    Scope sc(c->launches, st, "promptmel_tc_kernel", 3.0 * 2.0 * rows * pm::NCOLS * pm::NFFT, 4.0 * rows * (pm::HOP + pm::NMEL));
+    Scope sc(c->launches, st, "promptmel_tc_kernel", 2.0 * rows * pm::NCOLS * pm::NFFT,   /* algorithmic; executed = 3x (3xTF32) */ 4.0 * rows * (pm::HOP + pm::NMEL));
     pm::promptmel_kernel<<<(unsigned)((rows + tc::BM - 1) / tc::BM), 192, pm::SMEM_BYTES, st>>>(
         T.tm_hi, T.tm_lo, pcm_dev, (const pm::Clip*)T.clips, n_clips, reinterpret_cast<const float4*>(T.bins), out_dev, (int)rows);
   }

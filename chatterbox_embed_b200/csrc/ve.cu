@@ -287,13 +287,14 @@ void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st) {
     {
       // L2-exchange recurrence: hseq / xw of layers 1, 2 in the tiled time-major row order over whole 224-partial tiles
       const int prow = lstm_padded_slots(ch.slots) * kVePartial;
-      run_lstm_rec_tc2(c, ch.xw0, ch.slot_row, W.whh_p[0], ch.hseq, nullptr, ch.slots, st);
+      const size_t hl = (size_t)ch.slots * kVeHidden;
+      run_lstm_rec_tc2(c, ch.xw0, ch.slot_row, W.whh_p[0], ch.hseq, ch.hlast, ch.slots, st);
       for (int l = 1; l < 3; ++l) {
         CUtensorMap tmH = tc::make_map_2d(ch.hseq, prow, kVeHidden, kVeHidden, tc::BM, true);
         tc::pgemm_bias_tma<256, 4>(L, st, "lstm_xw_gemm", tmH, W.tm_wih_p256[l], ch.xw, kVeGates, W.bias_p[l], prow, kVeGates, kVeHidden);
-        run_lstm_rec_tc2(c, ch.xw, nullptr, W.whh_p[l], ch.hseq, l == 2 ? ch.hlast : nullptr, ch.slots, st);
+        run_lstm_rec_tc2(c, ch.xw, nullptr, W.whh_p[l], ch.hseq, ch.hlast + l * hl, ch.slots, st);
       }
-      { Scope sc(L, st, "ve_proj_kernel"); ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hlast, (size_t)kVeHidden, W.wpT, W.bp, ch.pemb); }
+      { Scope sc(L, st, "ve_proj_kernel", 2.0 * ch.slots * kVeHidden * kVeEmbed, 4.0 * ((double)ch.slots * (kVeHidden + kVeEmbed) + (double)kVeHidden * kVeEmbed)); ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hlast + 2 * hl, (size_t)kVeHidden, W.wpT, W.bp, ch.pemb); }
       return;
     }
 #ifdef CBX_DEV_TOOLS   // v1 recurrence (DSMEM pushes), tools/ comparisons only
@@ -302,9 +303,9 @@ void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st) {
       CUtensorMap tmH = tc::make_map_2d(ch.hseq, rows, kVeHidden, kVeHidden, tc::BM, true);
       tc::tgemm<128, 3>(L, st, "lstm_xw_gemm", tmH, W.tm_wih_p[l], rows, kVeGates, kVeHidden, tc::plain_map(kVeHidden), 1, tc::NoPrologue{},
                         tc::EpiBias{ch.xw, kVeGates, W.bias_p[l], rows});
-      run_lstm_rec_tc(c, ch.xw, nullptr, W.whh_p[l], l == 2 ? nullptr : ch.hseq, l == 2 ? ch.hlast : nullptr, ch.slots, st);
+      run_lstm_rec_tc(c, ch.xw, nullptr, W.whh_p[l], l == 2 ? nullptr : ch.hseq, l == 2 ? ch.hlast + 2 * (size_t)ch.slots * kVeHidden : nullptr, ch.slots, st);
     }
-    { Scope sc(L, st, "ve_proj_kernel"); ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hlast, (size_t)kVeHidden, W.wpT, W.bp, ch.pemb); }
+    { Scope sc(L, st, "ve_proj_kernel", 2.0 * ch.slots * kVeHidden * kVeEmbed, 4.0 * ((double)ch.slots * (kVeHidden + kVeEmbed) + (double)kVeHidden * kVeEmbed)); ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hlast + 2 * (size_t)ch.slots * kVeHidden, (size_t)kVeHidden, W.wpT, W.bp, ch.pemb); }
     return;
 #endif
   }
@@ -312,17 +313,24 @@ void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st) {
   const int nb = (ch.slots + LSTM_MT - 1) / LSTM_MT;
   sgemm(L, st, "lstm_xw0_gemm", ch.mel_rows, kVeGates, kVeMels, PlainA{ch.mel, kVeMels}, W.wih0, kVeMels, StoreBias{ch.xw0, kVeGates, W.bias[0]});
   { Scope sc(L, st, "lstm_rec_kernel", 2.0 * ch.slots * kVePartial * kVeHidden * kVeGates); lstm_rec_kernel<true><<<nb, 256, 0, st>>>(ch.xw0, ch.slot_row, W.whhT[0], ch.hseq, ch.slots); }
+  // stage tap: last hidden state of every layer -> hlast[l] (hseq is reused by the next layer)
+  auto tap_last = [&](int l) {
+    cudaMemcpy2DAsync(ch.hlast + (size_t)l * ch.slots * kVeHidden, sizeof(float) * kVeHidden, ch.hseq + (size_t)(kVePartial - 1) * kVeHidden,
+                      sizeof(float) * kVePartial * kVeHidden, sizeof(float) * kVeHidden, ch.slots, cudaMemcpyDeviceToDevice, st);
+  };
+  tap_last(0);
   for (int l = 1; l < 3; ++l) {
     sgemm(L, st, "lstm_xw_gemm", rows, kVeGates, kVeHidden, PlainA{ch.hseq, kVeHidden}, W.wih[l], kVeHidden, StoreBias{ch.xw, kVeGates, W.bias[l]});
     { Scope sc(L, st, "lstm_rec_kernel", 2.0 * ch.slots * kVePartial * kVeHidden * kVeGates); lstm_rec_kernel<false><<<nb, 256, 0, st>>>(ch.xw, ch.slot_row, W.whhT[l], ch.hseq, ch.slots); }
+    tap_last(l);
   }
-  { Scope sc(L, st, "ve_proj_kernel"); ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hseq + (size_t)(kVePartial - 1) * kVeHidden, (size_t)kVePartial * kVeHidden, W.wpT, W.bp, ch.pemb); }
+  { Scope sc(L, st, "ve_proj_kernel", 2.0 * ch.slots * kVeHidden * kVeEmbed, 4.0 * ((double)ch.slots * (kVeHidden + kVeEmbed) + (double)kVeHidden * kVeEmbed)); ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hseq + (size_t)(kVePartial - 1) * kVeHidden, (size_t)kVePartial * kVeHidden, W.wpT, W.bp, ch.pemb); }
 }
 
 void run_ve_chunk(cbx_ctx* c, const float* pcm, const VeChunk& ch, float trim_top_db, bool no_trim, int step,
                   double min_cov, float* ve_out, int32_t* status, cudaStream_t st) {
   Launches& L = c->launches;
-  { Scope sc(L, st, "trim_plan_kernel"); trim_plan_kernel<<<ch.n_clips, 256, 0, st>>>(pcm, ch.plan, ch.dyn, ch.trim_scratch, trim_top_db, no_trim ? 1 : 0, step, min_cov); }
+  { Scope sc(L, st, "trim_plan_kernel", 0.0, 4.0 * (double)ch.pcm_samples); trim_plan_kernel<<<ch.n_clips, 256, 0, st>>>(pcm, ch.plan, ch.dyn, ch.trim_scratch, trim_top_db, no_trim ? 1 : 0, step, min_cov); }
   cudaMemsetAsync(ch.mel_row_clip, 0xff, sizeof(int32_t) * ch.mel_rows, st);
   { Scope sc(L, st, "ve_maps_kernel"); ve_maps_kernel<<<ch.n_clips, 256, 0, st>>>(ch.plan, ch.dyn, step, ch.mel_row_clip, ch.slot_clip, ch.slot_row); }
   if (c->mode == 1) {
@@ -333,7 +341,7 @@ void run_ve_chunk(cbx_ctx* c, const float* pcm, const VeChunk& ch, float trim_to
     { Scope sc(L, st, "ve_mel_kernel"); ve_mel_kernel<<<(ch.mel_rows + 7) / 8, 256, 0, st>>>(ch.spec, c->ft.ve_mel, ch.plan, ch.dyn, ch.mel_row_clip, ch.mel, ch.mel_rows); }
   }
   run_ve_lstm(c, ch, st);
-  { Scope sc(L, st, "ve_clip_mean_kernel"); ve_clip_mean_kernel<<<ch.n_clips, 256, 0, st>>>(ch.pemb, ch.plan, ch.dyn, ve_out, status); }
+  { Scope sc(L, st, "ve_clip_mean_kernel", 0.0, 4.0 * kVeEmbed * ((double)ch.slots + ch.n_clips)); ve_clip_mean_kernel<<<ch.n_clips, 256, 0, st>>>(ch.pemb, ch.plan, ch.dyn, ve_out, status); }
 }
 
 // VoiceEncoder.forward on pre-cut partials: every partial is its own 160-row "clip".
@@ -351,7 +359,7 @@ void run_ve_forward_partials(cbx_ctx* c, const float* mels, int n, float* out, v
   ch.xw0 = cv.take<float>((int64_t)lstm_padded_slots(n) * kVePartial * kVeGates);
   ch.xw = ch.xw0;                       // layer-0 rows are exactly slot*160+t here, so one buffer serves both
   ch.hseq = cv.take<float>((int64_t)lstm_padded_slots(n) * kVePartial * kVeHidden);
-  ch.hlast = cv.take<float>((int64_t)n * kVeHidden);
+  ch.hlast = cv.take<float>((int64_t)3 * n * kVeHidden);
   ch.pemb = out;
   { Scope sc(c->launches, st, "ve_identity_slots_kernel"); ve_identity_slots_kernel<<<(n + 255) / 256, 256, 0, st>>>(ch.slot_row, n); }
   run_ve_lstm(c, ch, st);

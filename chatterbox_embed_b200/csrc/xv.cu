@@ -321,23 +321,72 @@ struct GateEpi {
 };
 
 // ---- K15/K16: out_nonlinear BN+ReLU, statistics pooling (mean, unbiased std), dense + BN -----------------
-__global__ void __launch_bounds__(512) stats_pool_kernel(const float* __restrict__ x, const ClipPlan* __restrict__ plan,
-                                                         const float* __restrict__ a, const float* __restrict__ b,
-                                                         float* __restrict__ stats) {
-  const ClipPlan cp = plan[blockIdx.x];
-  const int ch = threadIdx.x;
-  const float sa = a[ch], sb = b[ch];
-  const int T = cp.xv_tdnn;
-  float s = 0.f;
-  for (int t = 0; t < T; ++t) s += fmaxf(fmaf(x[(size_t)(cp.td_row + t) * kStatsC + ch], sa, sb), 0.f);
-  const float mean = T > 0 ? s / (float)T : nanf("");
-  float q = 0.f;
-  for (int t = 0; t < T; ++t) {
-    const float d = fmaxf(fmaf(x[(size_t)(cp.td_row + t) * kStatsC + ch], sa, sb), 0.f) - mean;
-    q = fmaf(d, d, q);
+// Warp-reduction kernel (xvector.py:146-152): one CTA per (clip, 32-channel slab) -- 16 slabs x clips CTAs fill the GPU even for a
+// handful of clips.  A lane is (time phase 0..3) x (channel quad 0..7): one warp instruction reads four consecutive rows x 128
+// contiguous bytes; the four phases are folded with two shuffles, the eight warps through shared memory in a fixed order
+// (deterministic).  Two passes like torch.std (mean first, then squared deviations; the second pass hits L2).
+constexpr int kSpSlab = 32, kSpWarps = 8;
+__device__ __forceinline__ float4 sp_fold(float4 v) {
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o); v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, o); v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
   }
-  stats[(size_t)blockIdx.x * 2 * kStatsC + ch] = mean;
-  stats[(size_t)blockIdx.x * 2 * kStatsC + kStatsC + ch] = sqrtf(q / (float)(T - 1));   // T'=1 -> 0/0 = NaN like torch.std
+  return v;
+}
+__global__ void __launch_bounds__(32 * kSpWarps) stats_pool_kernel(const float* __restrict__ x, const ClipPlan* __restrict__ plan,
+                                                                   const float* __restrict__ a, const float* __restrict__ b,
+                                                                   float* __restrict__ stats) {
+  __shared__ float4 red[kSpWarps][8];
+  __shared__ float4 mean_s[8];
+  const ClipPlan cp = plan[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, quad = lane & 7, phase = lane >> 3;
+  const int c0 = blockIdx.y * kSpSlab + quad * 4;
+  const float4 sa = *reinterpret_cast<const float4*>(a + c0), sb = *reinterpret_cast<const float4*>(b + c0);
+  const int T = cp.xv_tdnn;
+  const float* base = x + (size_t)cp.td_row * kStatsC + c0;
+  auto act = [&](int t) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)t * kStatsC));
+    v.x = fmaxf(fmaf(v.x, sa.x, sb.x), 0.f); v.y = fmaxf(fmaf(v.y, sa.y, sb.y), 0.f);
+    v.z = fmaxf(fmaf(v.z, sa.z, sb.z), 0.f); v.w = fmaxf(fmaf(v.w, sa.w, sb.w), 0.f);
+    return v;
+  };
+  auto across_warps = [&](float4 v) {      // -> the CTA-wide sum in threads 0..7 (quad = threadIdx.x)
+    v = sp_fold(v);
+    if (phase == 0) red[warp][quad] = v;
+    __syncthreads();
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x < 8) {
+#pragma unroll
+      for (int w = 0; w < kSpWarps; ++w) { const float4 r = red[w][threadIdx.x]; t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w; }
+    }
+    return t;
+  };
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int t = warp * 4 + phase; t < T; t += 4 * kSpWarps) { const float4 v = act(t); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+  s = across_warps(s);
+  const float nanv = nanf("");
+  if (threadIdx.x < 8) {
+    const float ft = (float)T;
+    mean_s[threadIdx.x] = T > 0 ? make_float4(s.x / ft, s.y / ft, s.z / ft, s.w / ft) : make_float4(nanv, nanv, nanv, nanv);
+  }
+  __syncthreads();
+  const float4 m = mean_s[quad];
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int t = warp * 4 + phase; t < T; t += 4 * kSpWarps) {
+    const float4 v = act(t);
+    const float dx = v.x - m.x, dy = v.y - m.y, dz = v.z - m.z, dw = v.w - m.w;
+    q.x = fmaf(dx, dx, q.x); q.y = fmaf(dy, dy, q.y); q.z = fmaf(dz, dz, q.z); q.w = fmaf(dw, dw, q.w);
+  }
+  q = across_warps(q);
+  if (threadIdx.x < 8) {
+    const float d = (float)(T - 1);          // T'=1 -> 0/0 = NaN like torch.std
+    float* o = stats + (size_t)blockIdx.x * 2 * kStatsC + blockIdx.y * kSpSlab + threadIdx.x * 4;
+    *reinterpret_cast<float4*>(o) = mean_s[threadIdx.x];
+    *reinterpret_cast<float4*>(o + kStatsC) = make_float4(sqrtf(q.x / d), sqrtf(q.y / d), sqrtf(q.z / d), sqrtf(q.w / d));
+  }
 }
 
 __global__ void __launch_bounds__(256) xv_final_kernel(const float* __restrict__ stats, const ClipPlan* __restrict__ plan,
@@ -358,7 +407,8 @@ __global__ void __launch_bounds__(256) xv_final_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------
-void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out, int32_t* status, cudaStream_t st) {
+void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out, int32_t* status, cudaStream_t st,
+                  const float* feats, const int64_t* feat_off) {
   const XvWeights& W = c->xv;
   Launches& L = c->launches;
   const ClipPlan* hp = ch.hplan;
@@ -385,13 +435,21 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
       i = j;
     }
   }
-  if (c->mode == 1) run_kaldi_fbank_tc(c, pcm, ch, st);
+  if (feats) {
+    // CAMPPlus.forward (xvector.py:417-423): the caller's feature rows go where the fbank kernel would have written them; no CMN
+    cudaMemsetAsync(ch.fbank, 0, sizeof(float) * (size_t)ch.fb_rows * kKMels, st);
+    cudaMemsetAsync(ch.cmn_sum, 0, sizeof(float) * (size_t)ch.n_clips * kKMels, st);
+    for (int i = 0; i < ch.n_clips; ++i)
+      if (hp[i].xv_frames > 0)
+        cudaMemcpyAsync(ch.fbank + (size_t)hp[i].fb_row * kKMels, feats + (size_t)feat_off[hp[i].out_index] * kKMels,
+                        sizeof(float) * (size_t)hp[i].xv_frames * kKMels, cudaMemcpyDeviceToDevice, st);
+  } else if (c->mode == 1) run_kaldi_fbank_tc(c, pcm, ch, st);
   else for (const Sub& s : subs) {
     const int rows = s.r1 - s.r0;
     sgemm(L, st, "kaldi_dft_gemm", rows, kKSpecN, kKWin, KaldiFrameGather{pcm, ch.plan, ch.fb_row_clip, s.r0}, c->ft.k_dft, kKWin, StoreRM{ch.spec, kKSpecN});
     { Scope sc(L, st, "fbank_from_spec_kernel"); fbank_from_spec_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ch.spec, c->ft.k_mel, ch.fb_row_clip, ch.fbank, s.r0, rows); }
   }
-  { Scope sc(L, st, "cmn_mean_kernel"); cmn_mean_kernel<<<ch.n_clips, 320, 0, st>>>(ch.fbank, ch.plan, ch.cmn_sum); }
+  if (!feats) { Scope sc(L, st, "cmn_mean_kernel", 0.0, 4.0 * kKMels * ((double)ch.fb_rows + ch.n_clips)); cmn_mean_kernel<<<ch.n_clips, 320, 0, st>>>(ch.fbank, ch.plan, ch.cmn_sum); }
 
   for (const Sub& s : subs) {
     const int rows = s.r1 - s.r0;
@@ -402,7 +460,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     float* b3 = ch.b3 + 40 * kFcmC; float* b6 = ch.b6 + 20 * kFcmC;
     {
       const long long npos = (long long)rows * kKMels;
-      if (c->mode == 1) { Scope sc(L, st, "fcm_conv1_kernel"); fcm_conv1_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ch.fbank, ch.cmn_sum, ch.fb_row_clip, W.conv1_w, W.conv1_b, b0, s.r0, rows, ch.fb_rows); }
+      if (c->mode == 1) { Scope sc(L, st, "fcm_conv1_kernel", 2.0 * rows * 80 * kFcmC * 9, 4.0 * rows * (kKMels + 80.0 * kFcmC)); fcm_conv1_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ch.fbank, ch.cmn_sum, ch.fb_row_clip, W.conv1_w, W.conv1_b, b0, s.r0, rows, ch.fb_rows); }
       else { Scope sc(L, st, "fcm_conv1_kernel"); fcm_conv1_kernel<<<(unsigned)((npos + 7) / 8), 256, 0, st>>>(ch.fbank, ch.cmn_sum, ch.fb_row_clip, W.conv1_w, W.conv1_b, b0, s.r0, rows, ch.fb_rows); }
     }
     // in: [row][F_in][32] (pad row in front), optional shortcut source sc [row][F_sc][32], residual res / out [row][F_out][32]
@@ -489,7 +547,9 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
       } else
 #endif
       if (ch.segs > 0 && tcm) {
-        Scope sc(L, st, "cam_gate_kernel");
+        // latency-bound (one CTA per clip); bytes: the fixed-point segment sums in, the gates out, the two small weight matrices per CTA (L2)
+        Scope sc(L, st, "cam_gate_kernel", 2.0 * (ch.segs + ch.n_clips) * (kBnC * kCamHid + kCamHid * kGrowth),
+                 8.0 * ch.segs * kBnC + 4.0 * ch.segs * kGrowth + 4.0 * ch.n_clips * (kBnC * kCamHid + kCamHid * kGrowth));
         tc::launch_pdl(cam_gate_clip_kernel, dim3(ch.n_clips), dim3(256), 0, st, pdl, reinterpret_cast<unsigned long long*>(ch.seg_sum), ch.plan, D, ch.gate);
       } else if (ch.segs > 0) {
         { Scope sc(L, st, "seg_sum_kernel"); seg_sum_kernel<<<ch.segs, 128, 0, st>>>(ch.u, ch.plan, ch.seg_clip, ch.seg_sum); }
@@ -515,8 +575,8 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     else
       sgemm(L, st, "transit_gemm", M, T.cout, T.cin, BnReluA{cat, ld, T.a, T.b}, T.w, T.cin, MaskEpi{out, ldo, ch.td_row_clip});
   }
-  { Scope sc(L, st, "stats_pool_kernel"); stats_pool_kernel<<<ch.n_clips, 512, 0, st>>>(ch.tr3, ch.plan, W.out_a, W.out_b, ch.stats); }
-  { Scope sc(L, st, "xv_final_kernel"); xv_final_kernel<<<ch.n_clips, 256, 0, st>>>(ch.stats, ch.plan, W.fin_w, W.fin_b, xv_out, status); }
+  { Scope sc(L, st, "stats_pool_kernel", 0.0, 4.0 * kStatsC * ((double)ch.td_rows + 2.0 * ch.n_clips)); stats_pool_kernel<<<dim3(ch.n_clips, kStatsC / kSpSlab), 32 * kSpWarps, 0, st>>>(ch.tr3, ch.plan, W.out_a, W.out_b, ch.stats); }
+  { Scope sc(L, st, "xv_final_kernel", 2.0 * ch.n_clips * 2 * kStatsC * 192, 4.0 * ((double)ch.n_clips * (2 * kStatsC + 192) + 2.0 * kStatsC * 192)); xv_final_kernel<<<ch.n_clips, 256, 0, st>>>(ch.stats, ch.plan, W.fin_w, W.fin_b, xv_out, status); }
 }
 
 }  // namespace cbx

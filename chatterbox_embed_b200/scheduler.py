@@ -95,6 +95,41 @@ class SpeakerEmbedder:
         return ve_out, xv_out, status
 
 
+def batch_bounds(lengths: Sequence[int], max_clips: int = 256, max_samples: int = 256 * 160000) -> List[Tuple[int, int]]:
+    """Cut a shard (clip lengths in processing order) into consecutive batches of at most ``max_clips`` clips and
+    ``max_samples`` PCM samples (a single longer clip is a batch of its own): the unit of one cbx_embed_host_submit."""
+    out, i, n = [], 0, len(lengths)
+    while i < n:
+        j, acc = i, 0
+        while j < n and j - i < max_clips and (j == i or acc + int(lengths[j]) <= max_samples):
+            acc += int(lengths[j]); j += 1
+        out.append((i, j))
+        i = j
+    return out
+
+
+def embed_shard(emb: "SpeakerEmbedder", fetch, lengths: Sequence[int], max_clips: int = 256, max_samples: int = 256 * 160000,
+                pinned: bool = True, **kw) -> Tuple[np.ndarray, np.ndarray]:
+    """Voice-bank extraction of one rank's shard (BASELINE config 4): ``fetch(b, i0, i1)`` returns the flat host PCM of
+    clips [i0, i1) of the shard (batch number b); batches stream through ``embed_stream`` (two in flight).  Returns the
+    (n, 448) float32 block [VE | XV] in shard order and the per-clip status words."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    bounds = batch_bounds(lengths, max_clips, max_samples)
+    local = np.empty((len(lengths), EMB), dtype=np.float32)
+    status = np.empty(len(lengths), dtype=np.int32)
+
+    def gen():
+        for b, (i0, i1) in enumerate(bounds):
+            off = np.concatenate([[0], np.cumsum(lengths[i0:i1])]).astype(np.int64)
+            yield fetch(b, i0, i1), off
+
+    for (i0, i1), (ve, xv, st) in zip(bounds, emb.embed_stream(gen(), pinned=pinned, **kw)):
+        local[i0:i1, :256] = ve
+        local[i0:i1, 256:] = xv
+        status[i0:i1] = st
+    return local, status
+
+
 def gather_embeddings(local: torch.Tensor, shards: Sequence[np.ndarray], n_total: int, group=None) -> torch.Tensor:
     """local: (len(shards[rank]), 448) on this rank's device (or CPU with gloo).  Returns (n_total, 448) in the
     original clip order on every rank, via one all_gather_into_tensor of the padded per-rank block."""

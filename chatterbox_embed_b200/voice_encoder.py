@@ -2,6 +2,8 @@
 libcbx.so on a B200.  Same constructor, same state_dict keys, same method signatures and return types."""
 from __future__ import annotations
 
+import warnings
+
 from typing import List, Optional, Union
 
 import numpy as np
@@ -112,11 +114,26 @@ class VoiceEncoder(_host.WeightSync, nn.Module):
 
     def embeds_from_wavs(self, wavs: List[np.ndarray], sample_rate, as_spk=False, batch_size=32,
                          trim_top_db: Optional[float] = 20, **kwargs):
-        """List of 16 kHz float waveforms -> (B, 256) float32 numpy (voice_encoder.py:246-274).  The whole chain
-        (trim, mel, partials, LSTM, mean) runs in one libcbx call on HOST buffers."""
+        """List of float waveforms -> (B, 256) float32 numpy (voice_encoder.py:246-274).  The whole chain (trim, mel,
+        partials, LSTM, mean) runs in one libcbx call on HOST buffers.
+
+        ``sample_rate != 16000``: the reference resamples with ``librosa.resample(res_type="kaiser_fast")``
+        (voice_encoder.py:260-264) -- resampy's Kaiser-windowed sinc table, a third-party algorithm that is neither in the
+        reference tree nor installed here, so it has no oracle.  DOCUMENTED SUBSTITUTE: the library's own polyphase
+        windowed-sinc resampler (``cbx_resample``, torchaudio ``Resample`` defaults, bit-pinned to torchaudio by
+        tests/test_oracle.py) -- the resampler the reference itself uses in front of CAMPPlus (s3gen.py:41-44).  Both are
+        linear-phase low-pass interpolators; the embeddings agree to the extent the pass bands do (not bit-level parity,
+        and not covered by the parity claim).  A warning says so once.  Integer sample rates only."""
         if sample_rate != self.hp.sample_rate:
-            raise NotImplementedError("resampling (librosa kaiser_fast, voice_encoder.py:260-264) is outside the B200 path: "
-                                      f"pass {self.hp.sample_rate} Hz audio")
+            from .resample import Resample
+            if not getattr(VoiceEncoder, "_warned_resample", False):
+                warnings.warn("VoiceEncoder.embeds_from_wavs: resampling with the torchaudio-style windowed-sinc resampler of libcbx "
+                              "instead of librosa's kaiser_fast (third-party, no oracle): close, not bit-level, parity for non-16 kHz input")
+                VoiceEncoder._warned_resample = True
+            dev = self.device
+            rs = Resample(int(sample_rate), self.hp.sample_rate)
+            outs = rs.ragged([torch.as_tensor(np.asarray(w, dtype=np.float32)).to(dev) for w in wavs])
+            wavs = [o.cpu().numpy() for o in outs]
         rate = kwargs.pop("rate", 1.3)          # Resemble's default value (voice_encoder.py:269-270)
         overlap = kwargs.pop("overlap", 0.5)
         min_coverage = kwargs.pop("min_coverage", 0.8)

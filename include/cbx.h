@@ -191,6 +191,14 @@ int cbx_ve_forward_partials(cbx_ctx* ctx, const float* mels_dev, int n_partials,
                             void* workspace_dev, int64_t workspace_bytes, void* stream);
 int64_t cbx_ve_forward_workspace_bytes(cbx_ctx* ctx, int n_partials);
 
+/* CAMPPlus.forward on precomputed features (s3gen/xvector.py:417-423; what CAMPPlus.inference hands it after
+ * extract_feature): feats_dev [sum T_i][80] fp32 (already mean-normalised, clip i = rows frame_offsets_host[i] ..
+ * frame_offsets_host[i+1]) -> xv_out_dev [n_clips][192].  Skips the fbank / CMN kernels; everything after them is the
+ * path of cbx_embed(CBX_DO_XV).  status_dev [n_clips] as in cbx_embed (T_i = 0 sets CBX_CLIP_XV_TOO_SHORT). */
+int cbx_campplus_forward_feats(cbx_ctx* ctx, const float* feats_dev, const int64_t* frame_offsets_host, int n_clips,
+                               float* xv_out_dev, int32_t* status_dev, void* workspace_dev, int64_t workspace_bytes, void* stream);
+int64_t cbx_campplus_forward_workspace_bytes(cbx_ctx* ctx, const int64_t* frame_offsets_host, int n_clips);
+
 /* ---- stage taps for parity tests --------------------------------------------------------- */
 /* After cbx_embed (single chunk), locate an intermediate inside the caller's workspace.
  * name in {"ve_trim","ve_mel","ve_partial_emb","xv_fbank","xv_fcm","xv_cat1","xv_cat2","xv_cat3","xv_stats",...};

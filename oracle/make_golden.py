@@ -92,7 +92,7 @@ def main():
     wavs = golden_wavs()
     import librosa  # the oracle shim registered by refload
     trims = np.array([librosa.effects.trim(w, top_db=20)[1] for w in wavs], dtype=np.int64)
-    for kind in ("W0", "W1"):
+    for kind in ("W0", "W1", "W2"):
         ve = refload.make_voice_encoder(weights.ve_state_dict(kind))
         cp = refload.make_campplus(weights.campplus_state_dict(kind))
         out = {"trim": trims}
@@ -107,6 +107,8 @@ def main():
             padded = np.concatenate([mel, np.zeros((400, 40), np.float32)])
             parts = np.stack([padded[77 * p: 77 * p + 160] for p in range(n_p)])
             out["partial_emb_1"] = ve(torch.from_numpy(parts)).numpy()
+            _, (h_n, _) = ve.lstm(torch.from_numpy(parts))     # last hidden state of each of the three layers (3, P, 256)
+            out["lstm_h_1"] = h_n.numpy()
             feat, _, _ = refload.xvector_module().extract_feature([torch.from_numpy(wavs[1])])
             out["fbank_cmn_1"] = feat[0].numpy()
             fcm = cp.head(feat.permute(0, 2, 1))
@@ -115,6 +117,14 @@ def main():
             out["tdnn_1"] = td[0, :, ::8].numpy()
             b1 = cp.xvector.block1(td)
             out["block1_1"] = b1[0, :, ::16].numpy()
+            xvm = cp.xvector
+            b2 = xvm.block2(xvm.transit1(b1))
+            out["block2_1"] = b2[0, :, ::16].numpy()          # (1024, T'/16): first 256 rows = transit1 output
+            b3 = xvm.block3(xvm.transit2(b2))
+            out["block3_1"] = b3[0, :, ::16].numpy()          # (1024, T'/16): first 512 rows = transit2 output
+            t3 = xvm.transit3(b3)
+            out["transit3_1"] = t3[0, :, ::16].numpy()        # (512, T'/16), before out_nonlinear
+            out["stats_1"] = xvm.stats(xvm.out_nonlinear(t3))[0].numpy()   # (1024,) mean | unbiased std
         np.savez_compressed(os.path.join(OUT, f"ref_{kind}.npz"), **out)
         print(kind, {k: v.shape for k, v in out.items()})
 

@@ -71,38 +71,33 @@ def test_golden_embeddings(models, golden_dir, kind):
     assert min(cos(a, b) for a, b in zip(xv, g["xv_emb"])) > 0.99999
 
 
+# Per-stage tolerances against the golden tensors of the verbatim reference (tests/stage_taps.py).  Errors are relative to the
+# stage's max |value| unless noted.  Mode 0 (strict fp32 SIMT) is held to fp32 rounding; mode 1 (tcgen05 TF32, the shipping
+# mode and the one bench.py times) to TF32 operand rounding (2^-11 per operand, accumulating through ~60 stacked layers).
+# The mode-1 numbers are 3x what was measured on a B200 (tests/tools/stage_report.py, profiles/r02_stage_report.json).
+STAGE_TOL = {
+    0: dict(mel=5e-6, lstm_h0=1e-5, lstm_h1=1e-5, lstm_h2=1e-5, partial_emb=1e-5, fbank_mean=1e-3, fbank_max=5e-2, fcm=1e-3, tdnn=1e-3,
+            block1=1e-3, block2=1e-3, block3=1e-3, transit3=1e-3, stats=1e-3, ve_emb=1e-5, xv_emb=1e-4),
+    1: dict(mel=5e-6, lstm_h0=1e-3, lstm_h1=1e-3, lstm_h2=1e-3, partial_emb=1e-3, fbank_mean=1e-3, fbank_max=5e-2, fcm=3e-3, tdnn=3e-3,
+            block1=3e-3, block2=3e-3, block3=3e-3, transit3=3e-3, stats=3e-3, ve_emb=1e-3, xv_emb=1e-3),
+}
+
+
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("kind", ["W0", "W1"])
-def test_golden_stages(models, golden_dir, kind):
+def test_golden_stages(models, golden_dir, kind, mode):
+    """Every stage of both encoders against what the verbatim reference modules produced, in BOTH modes: the embedding gate
+    alone has almost no power with default-init weights (SURVEY.md 8d hazard 1)."""
+    import stage_taps
     g = np.load(os.path.join(golden_dir, f"ref_{kind}.npz"))
     sdv, sdc, emb = _emb(models, kind)
-    wavs = make_golden.golden_wavs()
-    ctx = emb.ctx()
-    flat = np.concatenate(wavs); off = np.concatenate([[0], np.cumsum([len(w) for w in wavs])]).astype(np.int64)
-    pcm = torch.from_numpy(flat).to(DEV)
-    emb.embed_device(pcm, off)
-    torch.cuda.synchronize()
-    ws = emb._ws.buf
-
-    def tap(name):
-        o, r, c, ld = ctx.locate(name)
-        return ws[o:o + r * ld * 4].view(torch.float32).view(r, ld)[:, :c].cpu().numpy()
-
-    dyn = ws[ctx.locate("ve_dyn")[0]:][:5 * 24].view(torch.int32).view(5, 6).cpu().numpy()
-    assert (dyn[:, :2] == g["trim"]).all()                                  # trim indices: bit-exact
-    rows = ctx.clip_rows(1)
-    mel = tap("ve_mel")[rows["mel_row"]:rows["mel_row"] + 301]
-    assert relerr(mel, g["mel_1"]) < 5e-6
-    pe = tap("ve_partial_emb")[rows["slot"]:rows["slot"] + 3]
-    assert np.abs(pe - g["partial_emb_1"]).max() < 1e-5
-    fb = tap("xv_fbank")[rows["fb_row"]:rows["fb_row"] + 298] - tap("xv_cmn_mean")[1]
-    d = np.abs(fb - g["fbank_cmn_1"])
-    assert d.mean() < 1e-3 and d.max() < 5e-2                             # log domain, floor bins of a chirp
-    fcm = tap("xv_fcm")[rows["fb_row"]:rows["fb_row"] + 298]               # [t][f*32+c] -> reference channel c*10+f
-    fcm = fcm.reshape(298, 10, 32).transpose(2, 1, 0).reshape(320, 298)[:, ::16]
-    assert relerr(fcm, g["fcm_1"]) < 1e-3
-    cat1 = tap("xv_cat1")[rows["td_row"]:rows["td_row"] + 149].T
-    assert relerr(cat1[:128, ::8], g["tdnn_1"]) < 1e-3
-    assert relerr(cat1[:, ::16], g["block1_1"]) < 1e-3
+    ctx = _lib.context(0)
+    ctx.set_option("mode", mode)
+    err = stage_taps.stage_errors(emb, g)
+    assert err["trim"] == 0                                                  # trim indices: bit-exact
+    bad = {k: (err[k], tol) for k, tol in STAGE_TOL[mode].items() if not err[k] <= tol}
+    assert not bad, (kind, mode, bad, err)
+    assert err["ve_min_cos"] >= 0.9999 and err["xv_min_cos"] >= 0.9999
 
 
 # ---- oracle on the same seeded inputs ---------------------------------------------------------------------------------
@@ -169,11 +164,43 @@ def test_error_conventions(models):
         cp.inference([torch.zeros(399)])                     # Kaldi window does not fit (kaldi.py:142-144)
     with pytest.raises(ValueError):
         ve.embeds_from_wavs([np.zeros(100, np.float32) + 0.1], 16000)
-    with pytest.raises(NotImplementedError):
-        ve.embeds_from_wavs([synth.clip(0, 16000)], 22050)
+    VoiceEncoder._warned_resample = False
+    with pytest.warns(UserWarning):                          # non-16 kHz input: documented substitute resampler (no kaiser_fast oracle)
+        got = ve.embeds_from_wavs([synth.clip(0, 22050)], 22050)
+    want = nets.ve_embed_wavs(sdv, [frontend.resample_torchaudio(synth.clip(0, 22050), 22050, 16000)])
+    assert got.shape == (1, 256) and np.abs(got - want).max() < 1e-4
     # 400..719 samples -> T'=1 -> unbiased std is NaN in the reference too (xvector.py:148)
     out = cp.inference([torch.from_numpy(synth.clip(0, 500))])
     assert torch.isnan(out).any()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_campplus_forward_on_features(models, mode):
+    """CAMPPlus.forward(x (B, T, 80)) (xvector.py:417-423): precomputed, mean-normalised features in, x-vectors out -- the same
+    network as inference() without the fbank / CMN kernels; also as a ragged list of (T_i, 80)."""
+    sdv, sdc, ve, cp = models["W1"]
+    _lib.context(0).set_option("mode", mode)
+    tol = 1e-4 if mode == 0 else 1e-3
+    wavs = [synth.clip(i, 40000) for i in range(3)]
+    feats = np.stack([frontend.campplus_features(w) for w in wavs])                     # (3, 248, 80)
+    with torch.inference_mode():
+        want = nets.campplus_forward(sdc, torch.from_numpy(feats)).numpy()
+    scale = max(1.0, float(np.abs(want).max()))
+    got = cp(torch.from_numpy(feats).to(DEV))
+    assert tuple(got.shape) == (3, 192) and got.dtype == torch.float32 and got.device.type == "cuda"
+    assert np.abs(got.cpu().numpy() - want).max() < tol * scale
+    assert min(cos(a, b) for a, b in zip(got.cpu().numpy(), want)) > 0.9999
+    # agrees with inference() on the waveforms up to the front end's own rounding
+    inf = cp.inference([torch.from_numpy(w) for w in wavs]).cpu().numpy()
+    assert np.abs(inf - got.cpu().numpy()).max() < 1e-3 * scale
+    # ragged list: every clip pooled over its own frames
+    rag = [frontend.campplus_features(synth.clip(5, n)) for n in (16000, 52000, 720)]
+    with torch.inference_mode():
+        want_r = np.concatenate([nets.campplus_forward(sdc, torch.from_numpy(f)[None]).numpy() for f in rag])
+    got_r = cp([torch.from_numpy(f) for f in rag]).cpu().numpy()
+    assert np.abs(got_r - want_r).max() < tol * max(1.0, float(np.abs(want_r).max()))
+    with pytest.raises(AssertionError):
+        cp(torch.zeros(2, 10, 40, device=DEV))
 
 
 def test_save_voice_clone_npy(models, tmp_path):
