@@ -78,8 +78,20 @@ def test_golden_embeddings(models, golden_dir, kind):
 STAGE_TOL = {
     0: dict(mel=5e-6, lstm_h0=1e-5, lstm_h1=1e-5, lstm_h2=1e-5, partial_emb=1e-5, fbank_mean=1e-3, fbank_max=5e-2, fcm=1e-3, tdnn=1e-3,
             block1=1e-3, block2=1e-3, block3=1e-3, transit3=1e-3, stats=1e-3, ve_emb=1e-5, xv_emb=1e-4),
-    1: dict(mel=5e-6, lstm_h0=1e-3, lstm_h1=1e-3, lstm_h2=1e-3, partial_emb=1e-3, fbank_mean=1e-3, fbank_max=5e-2, fcm=3e-3, tdnn=3e-3,
-            block1=3e-3, block2=3e-3, block3=3e-3, transit3=3e-3, stats=3e-3, ve_emb=1e-3, xv_emb=1e-3),
+    # measured (W0 / W1, profiles/r02_stage_report.log): mel 7.1e-6 (3xTF32 DFT), lstm_h 2.1e-4 / 5.8e-5 / 1.8e-5, partial_emb 2.6e-5,
+    # fcm 5.9e-4, tdnn 6.5e-4, block1..3 7.3e-4 / 7.0e-4 / 8.7e-4, transit3 8.0e-4, stats 3.6e-4, ve_emb 1.4e-5, x-vector 5.7e-4 of
+    # max|x| (absolute 1.1e-4 with W0, 8.0e-4 with W1: inside the north_star's absolute 1e-3 with both)
+    1: dict(mel=2e-5, lstm_h0=7e-4, lstm_h1=2e-4, lstm_h2=1e-4, partial_emb=1e-4, fbank_mean=1e-3, fbank_max=5e-2, fcm=2e-3, tdnn=2e-3,
+            block1=2.5e-3, block2=2.5e-3, block3=3e-3, transit3=2.5e-3, stats=1.2e-3, ve_emb=1e-4, xv_emb=1.5e-3, xv_emb_abs=1e-3),
+}
+# W2 (sensitised LSTM, BN-calibrated CAMPPlus: O(1) activations, the weight set with the most power per stage).  The golden
+# clips are OUT of W2's calibration range (pure chirps, a clip with 1e-4-scaled silence: |x-vector| up to 1446), where the
+# network amplifies any perturbation ~100x per dense block: fp32 vs fp32 already differs by 1.8e-2 at block 3 (mode 0), and
+# TF32 operand rounding gives 0.1 .. 0.4 there -- on the B200 exactly as in the CPU emulation of the rounding
+# (tests/tools/w2_chirp_emulation.py).  So W2 holds the stages up to dense block 1, where it has power.
+STAGE_TOL_W2 = {
+    0: dict(mel=5e-6, lstm_h0=2e-5, lstm_h1=1e-5, lstm_h2=1e-5, partial_emb=1e-5, fcm=1.5e-3, tdnn=1.5e-3, block1=2e-3, ve_emb=1e-5),
+    1: dict(mel=2e-5, lstm_h0=2e-2, lstm_h1=3e-3, lstm_h2=2e-3, partial_emb=1e-3, fcm=4e-3, tdnn=4e-3, block1=6e-3, ve_emb=1e-3),
 }
 
 
@@ -98,6 +110,19 @@ def test_golden_stages(models, golden_dir, kind, mode):
     bad = {k: (err[k], tol) for k, tol in STAGE_TOL[mode].items() if not err[k] <= tol}
     assert not bad, (kind, mode, bad, err)
     assert err["ve_min_cos"] >= 0.9999 and err["xv_min_cos"] >= 0.9999
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_golden_stages_sensitised(models, golden_dir, mode):
+    import stage_taps
+    g = np.load(os.path.join(golden_dir, "ref_W2.npz"))
+    sdv, sdc, emb = _emb(models, "W2")
+    _lib.context(0).set_option("mode", mode)
+    err = stage_taps.stage_errors(emb, g)
+    assert err["trim"] == 0
+    bad = {k: (err[k], tol) for k, tol in STAGE_TOL_W2[mode].items() if not err[k] <= tol}
+    assert not bad, (mode, bad, err)
+    assert err["ve_min_cos"] >= 0.9999
 
 
 # ---- oracle on the same seeded inputs ---------------------------------------------------------------------------------
