@@ -234,12 +234,14 @@ def setup(args):
 
 def precision_fields(args, ctx):
     cat_bf16 = int(ctx.get_option("cat_bf16"))                # opt-in (--opt cat_bf16=1|2): not the parity mode, say so in the line
-    dtype = "f32" if args.mode == 0 else ("tf32" if not cat_bf16 else "tf32+bf16")
+    xw_bf16 = int(ctx.get_option("xw_bf16"))
+    dtype = "f32" if args.mode == 0 else ("tf32" if not (cat_bf16 or xw_bf16) else "tf32+bf16")
     note = None if args.mode == 0 else ("tcgen05 kind::tf32 with fp32 accumulation everywhere; the front-end DFT is 3xTF32 "
                                         "(hi/lo split, fp32-accurate); activations and state are stored in fp32"
                                         + ("" if not cat_bf16 else f"; EXCEPT option cat_bf16={cat_bf16}: the D-TDNN bottleneck / transit GEMMs read a bf16 "
                                            "copy of the concatenation buffers" + (" and run on bf16 operands (kind::f16)" if cat_bf16 == 2 else "")
-                                           + " -- a looser-tolerance setting, not the fp32/TF32 parity mode"))
+                                           + " -- a looser-tolerance setting, not the fp32/TF32 parity mode")
+                                        + ("" if not xw_bf16 else "; the LSTM input projections are stored as bf16 (bf16 mode, --mode 2: tolerance table in tests/test_gpu_parity.py MODE2_TOL)"))
     return dtype, note
 
 
@@ -559,7 +561,7 @@ def main():
             "audio_s_per_s": world * audio_s * K / (ms / 1e3), "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": dtype, "data": "synthetic", "precision_note": note,
-            "config": {"workload": WORKLOADS[args.config], "mode": "strict-fp32 SIMT" if args.mode == 0 else "tcgen05 TF32",
+            "config": {"workload": WORKLOADS[args.config], "mode": {0: "strict-fp32 SIMT", 1: "tcgen05 TF32", 2: "bf16 mode (tcgen05 TF32 + bf16 D-TDNN GEMM operands + bf16 LSTM input projections)"}[args.mode],
                        "l2": f"inputs ({total * 4 / 1e6:.0f} MB PCM per step) and activations exceed the 126 MB L2; no flush needed",
                        "parallelism": f"dp{world}", "clips_per_gpu": n_clips, "audio_seconds_per_gpu": audio_s},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": total * 4,

@@ -156,6 +156,7 @@ struct cbx_ctx {
   int64_t lstm_trace = 0;             // device pointer of the clock trace buffer
   int64_t lstm_impl = 2;              // 1: DSMEM-push recurrence, 2: L2 multicast-TMA recurrence
   int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)
+  int64_t xw_bf16 = 0;                // 1 = the LSTM input projections are stored as bf16 (bf16 mode)
   int64_t cat_bf16 = 0;               // 1 = the D-TDNN GEMMs read a bf16 copy of the concatenation buffers, 2 = and run on bf16 operands (kind::f16)
   int64_t probe = 0;                  // timing experiments, results are WRONG while set: bit 0 = no CAM gate kernel (tools/probe_bounds.py)
   int64_t batch_invariant = 0;        // 1: exact warp-level segment sums: x-vectors bit-identical whatever the batch (about 0.5 ms per step)
@@ -295,7 +296,7 @@ void run_kaldi_fbank_tc(cbx_ctx* c, const float* pcm, const XvChunk& ch, cudaStr
 void run_local_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmU, const CUtensorMap& tmW, const CUtensorMap& tmOut, int M, int dil,
                        int col0, const float* gate, const int32_t* row_seg, bool pdl = false, uint16_t* shadow = nullptr, int ldh = 0);   // local_tc.cu
 int lstm_padded_slots(int n_slots);     // slots rounded up to whole 224-partial cluster tiles (lstm_tc.cu)
-void run_lstm_rec_tc2(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
+void run_lstm_rec_tc2(cbx_ctx* c, const void* xw, bool xw_bf16, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
                       int n_slots, cudaStream_t st);
 void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const float* bias, const float* in, int F_in, int F_out, int sf,
                      const float* sc, int F_sc, const float* res, float* out, const int32_t* row_clip, int rows, int prows, double flops,

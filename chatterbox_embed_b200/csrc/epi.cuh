@@ -2,6 +2,7 @@
 // held in registers (fp32, straight from TMEM).
 #pragma once
 #include "cbx_internal.h"
+#include "tc.cuh"
 
 namespace cbx {
 namespace tc {
@@ -13,11 +14,7 @@ __device__ __forceinline__ void store32(float* dst, const float* v) {
 }
 
 // 32 values -> 32 bf16 (round to nearest even), 64 contiguous bytes: the bf16 copy of the concatenation buffer (option cat_bf16)
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));      // upper half <- first source, lower half <- second
-  return r;
-}
+// (pack_bf16x2 lives in tc.cuh)
 __device__ __forceinline__ void store32_bf16(uint16_t* dst, const float* v) {
   uint4* o = reinterpret_cast<uint4*>(dst);
 #pragma unroll

@@ -17,6 +17,8 @@
 //     it to the 7 peers with cp.async.bulk over distributed shared memory, completing on the peers' "full" mbarriers.
 //     "free" mbarriers (one remote arrive per CTA per step) tell the senders that every peer's MMA has finished reading
 //     h_{t-1} before it is overwritten.
+#include <type_traits>
+
 #include "cbx_internal.h"
 #include "tc.cuh"
 
@@ -332,8 +334,15 @@ __device__ __forceinline__ float ldg_stream_f32(const float* p) {
   return v;
 }
 
+// the same for an input projection stored as bf16 (bf16 mode): 2-byte load, the value is the upper half of the fp32 pattern
+__device__ __forceinline__ float ldg_stream_bf16(const uint16_t* p) {
+  uint16_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return __uint_as_float((uint32_t)v << 16);
+}
+
 struct Params2 {
-  const float* xw;            // layer 0: [mel rows][1024] gathered through slot_row; else tiled time-major [tiles*160*224][1024]
+  const void* xw;             // fp32 or bf16 (kXw16); layer 0: [mel rows][1024] gathered through slot_row; else tiled time-major [tiles*160*224][1024]
   const int32_t* slot_row;    // layer 0 only
   const float* whh;
   float* hseq;                // tiled time-major [tiles*160*224][256] (tf32-rounded h), also the exchange medium
@@ -366,7 +375,7 @@ __device__ __forceinline__ void rcp4(float d0, float d1, float d2, float d3, flo
   i0 = r01 * d1; i1 = r01 * d0; i2 = r23 * d3; i3 = r23 * d2;
 }
 
-template <bool kLayer0>
+template <bool kLayer0, bool kXw16>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS2, 1)
 lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
   extern __shared__ uint8_t smem_raw[];
@@ -476,7 +485,11 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
     const float neg_m_log2e = -m * 1.4426950408889634f, one_minus_m = 1.f - m;
     const int gt = threadIdx.x - 32;               // 0..255
     const int n0 = hf * HALF;                      // first partial (within a sub-tile) of this warp
-    const float* xq = p.xw + (kLayer0 ? (size_t)0 : (blk0 + n0) * kVeGates) + j * 128 + r;
+    using XwT = typename std::conditional<kXw16, uint16_t, float>::type;
+    const XwT* xq = static_cast<const XwT*>(p.xw) + (kLayer0 ? (size_t)0 : (blk0 + n0) * kVeGates) + j * 128 + r;
+    auto ldx = [](const XwT* q) -> float {
+      if constexpr (kXw16) return ldg_stream_bf16(q); else return ldg_stream_f32(q);
+    };
     float* hq = p.hseq + (blk0 + n0 + g) * kVeHidden + j * UNITS + u;
     const uint32_t dcol = tmem_base + ((uint32_t)(qd * 32) << 16) + COL_D + n0;
     float cst[2][HALF / 4];
@@ -490,9 +503,9 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
     auto xw_load = [&](int hs, int n) -> float {     // input projection of partial n0 + n for half-step hs = 2 t + x
       if (kLayer0) {
         const int x = hs & 1, t = hs >> 1;
-        return ldg_stream_f32(xq + (size_t)(rowbase[x * NSUB + n0 + n] + t) * kVeGates);
+        return ldx(xq + (size_t)(rowbase[x * NSUB + n0 + n] + t) * kVeGates);
       }
-      return ldg_stream_f32(xq + ((size_t)hs * NSUB + n) * kVeGates);
+      return ldx(xq + ((size_t)hs * NSUB + n) * kVeGates);
     };
     // activations of one 8-column chunk: own gate of 8 partials; two shared reciprocals
     auto activate = [&](int x, int c, const float* xin, float* a) {
@@ -648,17 +661,20 @@ namespace cbx {
 // lstm_padded_slots(n_slots) * 160 rows.
 int lstm_padded_slots(int n_slots) { return (n_slots + lstm::TILE - 1) / lstm::TILE * lstm::TILE; }
 
-void run_lstm_rec_tc2(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
+void run_lstm_rec_tc2(cbx_ctx* c, const void* xw, bool xw_bf16, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
                       int n_slots, cudaStream_t st) {
   if (n_slots <= 0) return;
-  ensure_max_smem(lstm::lstm_rec_tc2_kernel<true>, lstm::SMEM_BYTES);
-  ensure_max_smem(lstm::lstm_rec_tc2_kernel<false>, lstm::SMEM_BYTES);
   const int tiles = (n_slots + lstm::TILE - 1) / lstm::TILE;
   const int64_t rows = (int64_t)tiles * lstm::TILE * kVePartial;
   CUtensorMap tmH = tc::make_map_2d(hseq, rows, kVeHidden, kVeHidden, lstm::NSUB, false);
   lstm::Params2 p{xw, slot_row, whh_perm, hseq, hlast, n_slots, (long long*)c->lstm_trace};
-  Scope sc(c->launches, st, "lstm_rec_tc_kernel", 2.0 * n_slots * kVePartial * kVeHidden * kVeGates, 4.0 * n_slots * kVePartial * (kVeGates + kVeHidden));
-  if (slot_row) lstm::lstm_rec_tc2_kernel<true><<<tiles * lstm::CL, lstm::THREADS2, lstm::SMEM_BYTES, st>>>(tmH, p);
-  else lstm::lstm_rec_tc2_kernel<false><<<tiles * lstm::CL, lstm::THREADS2, lstm::SMEM_BYTES, st>>>(tmH, p);
+  Scope sc(c->launches, st, "lstm_rec_tc_kernel", 2.0 * n_slots * kVePartial * kVeHidden * kVeGates,
+           (double)n_slots * kVePartial * ((xw_bf16 ? 2.0 : 4.0) * kVeGates + 4.0 * kVeHidden));
+  auto go = [&](auto kern) {
+    ensure_max_smem(kern, lstm::SMEM_BYTES);
+    kern<<<tiles * lstm::CL, lstm::THREADS2, lstm::SMEM_BYTES, st>>>(tmH, p);
+  };
+  if (slot_row) { if (xw_bf16) go(lstm::lstm_rec_tc2_kernel<true, true>); else go(lstm::lstm_rec_tc2_kernel<true, false>); }
+  else { if (xw_bf16) go(lstm::lstm_rec_tc2_kernel<false, true>); else go(lstm::lstm_rec_tc2_kernel<false, false>); }
 }
 }  // namespace cbx

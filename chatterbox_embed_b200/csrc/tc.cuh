@@ -624,6 +624,12 @@ tgemm_bnrelu_kernel(const void* __restrict__ Xv, int lda, int M, int K, const fl
   if (tr && threadIdx.x == 0) tr[7] = gtime();
 }
 
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));      // upper half <- first source, lower half <- second
+  return r;
+}
+
 // ---------------------------------------------------------------- persistent GEMM
 //   C[m][n] = sum_k A[m][k] * W[n][k] + bias[n],   one CTA per SM looping over 128 x BN output tiles (n fastest).
 // The shared-memory stage ring and the barriers' phases run on across tiles, and the fp32 accumulator is double-buffered
@@ -633,7 +639,9 @@ tgemm_bnrelu_kernel(const void* __restrict__ Xv, int lda, int M, int K, const fl
 // buffers and TMA tensor stores (one 128 x 32 box per accumulator chunk) instead of per-thread 16-byte stores scattered over
 // 32 rows.  (A second epilogue group, as in the convolution kernels, made this one slower: it is bound by its 4 KB per row
 // of C writes, and the extra staging buffers cost a pipeline stage.)
-template <int BN, int STAGES>
+// OUT16: C is stored as bf16 (the bf16 mode's LSTM input projections: the kernel is bound by its C writes, 4 KB -> 2 KB per row);
+// one staging tile then carries 64 columns (128 bytes of bf16 per row) and tmC is a bf16 tensor map with a {64, 128} box.
+template <int BN, int STAGES, bool OUT16 = false>
 __global__ void __launch_bounds__(192, 1)
 pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
              const float* __restrict__ bias, int n_tiles_n, int n_tiles, int nkb) {
@@ -711,6 +719,39 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int a = ti & 1, pa = (ti >> 1) & 1;
       mbar_wait(&tfull[a], pa);
       tc_fence_after();
+      if constexpr (OUT16) {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+          float v[64];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c), v);
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c + 32), v + 32);
+          if (c + 64 >= BN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[a]);
+          }
+          const int buf = (c >> 6) & 1;
+          const float4* b4 = reinterpret_cast<const float4*>(bias + n0 + c);
+          uint32_t pk[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 bb = __ldg(b4 + j);
+            pk[2 * j] = pack_bf16x2(v[4 * j] + bb.x, v[4 * j + 1] + bb.y);
+            pk[2 * j + 1] = pack_bf16x2(v[4 * j + 2] + bb.z, v[4 * j + 3] + bb.w);
+          }
+          if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          uint4* so = reinterpret_cast<uint4*>(sC + buf * (BM * 128)) + i * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) so[j ^ (i & 7)] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          fence_proxy_async();
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (warp == 2 && lane == 0) {
+            tma_store_2d(&tmC, sC + buf * (BM * 128), n0 + c, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         float v[32];
@@ -737,6 +778,7 @@ pgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tma_store_2d(&tmC, sC + buf * (BM * 128), n0 + c, m0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+      }
       }
     }
     if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -773,16 +815,16 @@ inline void tgemm(Launches& L, cudaStream_t st, const char* tag, const CUtensorM
 
 // persistent GEMM launcher: C[M][N] (row-major, leading dimension ldc) = A . W^T + bias, C written with TMA tensor stores
 int sm_count();
-template <int BN, int STAGES>
-inline void pgemm_bias_tma(Launches& L, cudaStream_t st, const char* tag, const CUtensorMap& tmA, const CUtensorMap& tmB, float* C, int ldc,
+template <int BN, int STAGES, bool OUT16 = false>
+inline void pgemm_bias_tma(Launches& L, cudaStream_t st, const char* tag, const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int ldc,
                            const float* bias, int M, int N, int K) {
   if (M <= 0 || N <= 0) return;
-  auto kern = pgemm_kernel<BN, STAGES>;
+  auto kern = pgemm_kernel<BN, STAGES, OUT16>;
   constexpr int SMEM = smem_bytes(BN, STAGES) + 1024 + 2 * BM * 128;
   ensure_max_smem(kern, SMEM);
   const int tn = (N + BN - 1) / BN, tiles = ((M + BM - 1) / BM) * tn;
-  CUtensorMap tmC = make_map_2d(C, M, N, ldc, BM, false);
-  Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * ((double)M * K + (double)M * N));
+  CUtensorMap tmC = OUT16 ? make_map_2d_bf16(C, M, N, ldc, BM) : make_map_2d(static_cast<float*>(C), M, N, ldc, BM, false);
+  Scope sc(L, st, tag, 2.0 * M * N * K, 4.0 * (double)M * K + (OUT16 ? 2.0 : 4.0) * (double)M * N);
   kern<<<tiles < sm_count() ? tiles : sm_count(), 192, SMEM, st>>>(tmA, tmB, tmC, bias, tn, tiles, (K + BK - 1) / BK);
 }
 

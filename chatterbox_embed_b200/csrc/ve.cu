@@ -280,7 +280,9 @@ void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st) {
     // recurrence as the persistent cluster kernel of lstm_tc.cu.  Layer 0 projects once per mel frame (partials overlap:
     // hop 77 < 160) and the recurrence gathers rows through slot_row.
     CUtensorMap tmA = tc::make_map_2d(ch.mel, ch.mel_rows, kVeMels, kVeMels, tc::BM, true);
-    tc::pgemm_bias_tma<256, 4>(L, st, "lstm_xw0_gemm", tmA, W.tm_wih_p256[0], ch.xw0, kVeGates, W.bias_p[0], ch.mel_rows, kVeGates, kVeMels);
+    const bool x16 = c->xw_bf16 != 0;        // bf16 mode: the projections are stored as bf16 (the GEMM is bound by its C writes)
+    if (x16) tc::pgemm_bias_tma<256, 4, true>(L, st, "lstm_xw0_gemm", tmA, W.tm_wih_p256[0], ch.xw0, kVeGates, W.bias_p[0], ch.mel_rows, kVeGates, kVeMels);
+    else tc::pgemm_bias_tma<256, 4>(L, st, "lstm_xw0_gemm", tmA, W.tm_wih_p256[0], ch.xw0, kVeGates, W.bias_p[0], ch.mel_rows, kVeGates, kVeMels);
 #ifdef CBX_DEV_TOOLS
     if (c->lstm_impl == 2)
 #endif
@@ -288,11 +290,12 @@ void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st) {
       // L2-exchange recurrence: hseq / xw of layers 1, 2 in the tiled time-major row order over whole 224-partial tiles
       const int prow = lstm_padded_slots(ch.slots) * kVePartial;
       const size_t hl = (size_t)ch.slots * kVeHidden;
-      run_lstm_rec_tc2(c, ch.xw0, ch.slot_row, W.whh_p[0], ch.hseq, ch.hlast, ch.slots, st);
+      run_lstm_rec_tc2(c, ch.xw0, x16, ch.slot_row, W.whh_p[0], ch.hseq, ch.hlast, ch.slots, st);
       for (int l = 1; l < 3; ++l) {
         CUtensorMap tmH = tc::make_map_2d(ch.hseq, prow, kVeHidden, kVeHidden, tc::BM, true);
-        tc::pgemm_bias_tma<256, 4>(L, st, "lstm_xw_gemm", tmH, W.tm_wih_p256[l], ch.xw, kVeGates, W.bias_p[l], prow, kVeGates, kVeHidden);
-        run_lstm_rec_tc2(c, ch.xw, nullptr, W.whh_p[l], ch.hseq, ch.hlast + l * hl, ch.slots, st);
+        if (x16) tc::pgemm_bias_tma<256, 4, true>(L, st, "lstm_xw_gemm", tmH, W.tm_wih_p256[l], ch.xw, kVeGates, W.bias_p[l], prow, kVeGates, kVeHidden);
+        else tc::pgemm_bias_tma<256, 4>(L, st, "lstm_xw_gemm", tmH, W.tm_wih_p256[l], ch.xw, kVeGates, W.bias_p[l], prow, kVeGates, kVeHidden);
+        run_lstm_rec_tc2(c, ch.xw, x16, nullptr, W.whh_p[l], ch.hseq, ch.hlast + l * hl, ch.slots, st);
       }
       { Scope sc(L, st, "ve_proj_kernel", 2.0 * ch.slots * kVeHidden * kVeEmbed, 4.0 * ((double)ch.slots * (kVeHidden + kVeEmbed) + (double)kVeHidden * kVeEmbed)); ve_proj_kernel<<<ch.slots, 256, 0, st>>>(ch.hlast + 2 * hl, (size_t)kVeHidden, W.wpT, W.bp, ch.pemb); }
       return;

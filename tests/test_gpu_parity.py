@@ -422,6 +422,78 @@ def test_cat_bf16_option(models, mode1, setting, kind, tol, min_cos):
     assert np.array_equal(ve3, ve0) and np.array_equal(xv3, xv0)
 
 
+# ---- the bf16 mode (mode 2, BASELINE config 5): its own tolerance, stated separately from the fp32 / TF32 gate --------------------
+# mode 2 = mode 1 with (a) the D-TDNN bottleneck / transit GEMMs on bf16 operands (bf16 copy of the concatenation buffers, bf16
+# weight copies, tcgen05 kind::f16, fp32 accumulation) and (b) the LSTM input projections xw stored as bf16 (the projection GEMM
+# is bound by its C writes).  Everything else (front-ends, FCM head, local convolutions, recurrent product, all state) as in mode 1.
+# Tolerance table against the fp32 oracle, per weight set: the CPU emulation of exactly these roundings (tests/tools/bf16_study.py)
+# predicts VE 1.1e-4 (W0) .. 7.6e-4 (W2) and x-vector 1.4e-4 (W0) / 2.9e-3 (W1) / 1.4e-1 at |x| <= 9.8, cos 0.9996 (W2).
+MODE2_TOL = {          # kind: (VE max-abs, x-vector max-abs / max(1, max|x|), x-vector min cos)
+    "W0": (1e-3, 1e-3, 0.9999),          # the north_star's gate weights: the bf16 mode still passes the fp32 gate
+    "W1": (1e-3, 6e-3, 0.9999),
+    "W2": (3e-3, 5e-2, 0.998),
+}
+
+
+@pytest.fixture
+def mode2(models):
+    ctx = _lib.context(0)
+    ctx.set_option("mode", 2)
+    yield ctx
+    ctx.set_option("mode", 1)
+
+
+@pytest.mark.parametrize("kind", ["W0", "W1", "W2"])
+def test_mode2_tolerances(models, mode2, kind):
+    assert mode2.get_option("mode") == 2 and mode2.get_option("cat_bf16") == 2 and mode2.get_option("xw_bf16") == 1
+    sdv, sdc, emb = _emb(models, kind)
+    lens = [int(x) for x in synth.ragged_lengths(6)] + EDGE[:4]
+    wavs = [synth.mixed(i, n) for i, n in enumerate(lens)]
+    ve, xv = emb.embed_wavs(wavs)
+    want_ve = nets.ve_embed_wavs(sdv, wavs)
+    want_xv = nets.campplus_embed_wavs(sdc, wavs)
+    tol_ve, tol_xv, min_cos = MODE2_TOL[kind]
+    ok = np.isfinite(want_xv).all(axis=1)                       # 720 samples -> T' = 2 is finite; keep the filter for safety
+    scale = max(1.0, float(np.abs(want_xv[ok]).max()))
+    assert np.abs(ve - want_ve).max() <= tol_ve and min(cos(a, b) for a, b in zip(ve, want_ve)) >= 0.9999
+    assert np.abs(xv[ok] - want_xv[ok]).max() <= tol_xv * scale
+    assert min(cos(a, b) for a, b in zip(xv[ok], want_xv[ok])) >= min_cos
+    # reproducible run to run, and chunking stays invisible up to rounding
+    ve2, xv2 = emb.embed_wavs(wavs)
+    assert np.array_equal(ve, ve2) and np.array_equal(xv, xv2)
+    old = {k: mode2.get_option(k) for k in ("xv_chunk_rows", "lstm_chunk_partials")}
+    try:
+        mode2.set_option("xv_chunk_rows", 900); mode2.set_option("lstm_chunk_partials", 7)
+        ve3, xv3 = emb.embed_wavs(wavs)
+    finally:
+        for k, v in old.items():
+            mode2.set_option(k, v)
+    assert np.abs(ve3 - ve).max() < 1e-4 and np.abs(xv3[ok] - xv[ok]).max() <= tol_xv * scale
+
+
+def test_mode2_stages_and_switch_back(models, mode2, golden_dir):
+    """Stage taps of the bf16 mode against the golden tensors (W1): the stages in front of the bf16 GEMMs are those of mode 1, the
+    LSTM hidden states and dense blocks carry the bf16 rounding; switching back to mode 1 restores it bit for bit."""
+    import stage_taps
+    g = np.load(os.path.join(golden_dir, "ref_W1.npz"))
+    sdv, sdc, emb = _emb(models, "W1")
+    err = stage_taps.stage_errors(emb, g)
+    tol = dict(mel=2e-5, lstm_h0=5e-3, lstm_h1=2e-3, lstm_h2=1e-3, partial_emb=1e-3, fcm=2e-3, tdnn=2e-3, block1=1e-2, block2=1e-2, block3=1e-2,
+               transit3=1e-2, stats=5e-3, ve_emb=1e-3, xv_emb=6e-3)
+    bad = {k: (err[k], v) for k, v in tol.items() if not err[k] <= v}
+    assert err["trim"] == 0 and not bad, (bad, err)
+    assert err["block1"] > 7.5e-4 and err["lstm_h1"] > 6e-5            # the mode is really on (mode 1 measures 6.0e-4 / 5.8e-5)
+    wavs = make_golden.golden_wavs()
+    m2 = emb.embed_wavs(wavs)
+    mode2.set_option("mode", 1)
+    a = emb.embed_wavs(wavs)
+    mode2.set_option("mode", 2)
+    assert np.array_equal(emb.embed_wavs(wavs)[1], m2[1])
+    mode2.set_option("mode", 1)
+    b = emb.embed_wavs(wavs)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and not np.array_equal(a[1], m2[1])
+
+
 def test_weight_updates_are_picked_up(mode1):
     """The modules push their tensors to libcbx lazily and cache the tensor list: in-place edits (version counters), a new
     load_state_dict and a fresh module must all be seen."""
