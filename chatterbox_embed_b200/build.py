@@ -24,7 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 DEV = os.environ.get("CBX_DEV_TOOLS") == "1"
 LIB = os.path.join(HERE, "libcbx_dev.so" if DEV else "libcbx.so")
-SOURCES = ["host_plan.cpp", "weights.cu", "ve.cu", "frontend_tc.cu", "lstm_tc.cu", "fcm_tc.cu", "local_tc.cu", "xv.cu", "resample.cu", "promptmel_tc.cu", "project.cu", "tc.cu", "api.cu"]
+SOURCES = ["host_plan.cpp", "weights.cu", "ve.cu", "frontend_tc.cu", "lstm_tc.cu", "fcm_tc.cu", "fcm_block_tc.cu", "local_tc.cu", "xv.cu", "resample.cu", "promptmel_tc.cu", "project.cu", "tc.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",

@@ -156,6 +156,7 @@ struct cbx_ctx {
   int64_t lstm_trace = 0;             // device pointer of the clock trace buffer
   int64_t lstm_impl = 2;              // 1: DSMEM-push recurrence, 2: L2 multicast-TMA recurrence
   int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)
+  int64_t fcm_fuse = 1;               // identity residual blocks of the FCM head as one fused kernel (fcm_block_tc.cu); 0 = two convolution kernels
   int64_t xw_bf16 = 0;                // 1 = the LSTM input projections are stored as bf16 (bf16 mode)
   int64_t cat_bf16 = 0;               // 1 = the D-TDNN GEMMs read a bf16 copy of the concatenation buffers, 2 = and run on bf16 operands (kind::f16)
   int64_t probe = 0;                  // timing experiments, results are WRONG while set: bit 0 = no CAM gate kernel (tools/probe_bounds.py)
@@ -300,7 +301,10 @@ void run_lstm_rec_tc2(cbx_ctx* c, const void* xw, bool xw_bf16, const int32_t* s
                       int n_slots, cudaStream_t st);
 void run_fcm_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW, const float* bias, const float* in, int F_in, int F_out, int sf,
                      const float* sc, int F_sc, const float* res, float* out, const int32_t* row_clip, int rows, int prows, double flops,
-                     const char* tag = "fcm_conv_gemm", bool pdl = false);   // fcm_tc.cu
+                     const char* tag = "fcm_conv_gemm", bool pdl = false);
+// fcm_block_tc.cu: an identity residual block (conv 3x3 -> BN -> ReLU -> conv 3x3 -> BN -> + x -> ReLU) as one kernel
+void run_fcm_block_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW1, const float* bias1, const CUtensorMap& tmW2, const float* bias2,
+                      const float* in, int F, float* out, const int32_t* row_clip, int rows, int prows, const char* tag, bool pdl);   // fcm_tc.cu
 void run_lstm_rec_tc(cbx_ctx* c, const float* xw, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
                      int n_slots, cudaStream_t st);   // lstm_tc.cu
 // feats != nullptr: CAMPPlus.forward on precomputed (already mean-normalised) features [sum T][80]; feat_off (host, frames, indexed by the

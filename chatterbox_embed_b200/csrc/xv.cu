@@ -479,13 +479,28 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     // layer1: 80 -> 40
     conv(W.res[0][0][0], W.tm_res[0][0][0], b0, 80, 40, 2, nullptr, 0, nullptr, b1);
     conv(W.res[0][0][1], W.tm_res[0][0][1], b1, 40, 40, 1, b0, 80, nullptr, b2);
-    conv(W.res[0][1][0], W.tm_res[0][1][0], b2, 40, 40, 1, nullptr, 0, nullptr, b1);
-    conv(W.res[0][1][1], W.tm_res[0][1][1], b1, 40, 40, 1, nullptr, 0, b2, b3);
+    // identity residual blocks: ONE fused kernel (the intermediate stays in shared memory, fcm_block_tc.cu) unless fcm_fuse = 0
+    const bool fuse = c->mode == 1 && c->fcm_fuse != 0;
+    const bool fpdl = c->pdl != 0 && !c->launches.prof;
+    if (fuse) run_fcm_block_tc(c, st, W.tm_res[0][1][0], W.res[0][1][0].bias, W.tm_res[0][1][1], W.res[0][1][1].bias, b2, 40, b3, rc, rows, ch.fcm_rows + 2,
+                               c->launches.prof ? "fcm_block:l1b1" : "fcm_block", fpdl);
+    else {
+      conv_idx = 2;
+      conv(W.res[0][1][0], W.tm_res[0][1][0], b2, 40, 40, 1, nullptr, 0, nullptr, b1);
+      conv(W.res[0][1][1], W.tm_res[0][1][1], b1, 40, 40, 1, nullptr, 0, b2, b3);
+    }
+    conv_idx = 4;
     // layer2: 40 -> 20
     conv(W.res[1][0][0], W.tm_res[1][0][0], b3, 40, 20, 2, nullptr, 0, nullptr, b4);
     conv(W.res[1][0][1], W.tm_res[1][0][1], b4, 20, 20, 1, b3, 40, nullptr, b5);
-    conv(W.res[1][1][0], W.tm_res[1][1][0], b5, 20, 20, 1, nullptr, 0, nullptr, b4);
-    conv(W.res[1][1][1], W.tm_res[1][1][1], b4, 20, 20, 1, nullptr, 0, b5, b6);
+    if (fuse) run_fcm_block_tc(c, st, W.tm_res[1][1][0], W.res[1][1][0].bias, W.tm_res[1][1][1], W.res[1][1][1].bias, b5, 20, b6, rc, rows, ch.fcm_rows + 2,
+                               c->launches.prof ? "fcm_block:l2b1" : "fcm_block", fpdl);
+    else {
+      conv_idx = 6;
+      conv(W.res[1][1][0], W.tm_res[1][1][0], b5, 20, 20, 1, nullptr, 0, nullptr, b4);
+      conv(W.res[1][1][1], W.tm_res[1][1][1], b4, 20, 20, 1, nullptr, 0, b5, b6);
+    }
+    conv_idx = 8;
     // head.conv2: 20 -> 10, written straight into the chunk-level [row][f*32+c] buffer
     conv(W.head_conv2, W.tm_head2, b6, 20, 10, 2, nullptr, 0, nullptr, ch.fcm_out + (size_t)s.r0 * kFcmOut);
   }

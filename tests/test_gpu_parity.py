@@ -346,6 +346,41 @@ def test_mode1_ragged_config3(models, mode1):
         assert pl.xv_frames == 1 + (n - 400) // 160 and pl.xv_tdnn == (pl.xv_frames - 1) // 2 + 1
 
 
+def test_fcm_fused_block_matches_separate_convolutions(models, mode1):
+    """The identity residual blocks of the FCM head run as one fused kernel (intermediate in a shared-memory ring,
+    fcm_block_tc.cu).  Same arithmetic as the two separate convolution kernels (option fcm_fuse = 0) up to the tf32 rounding
+    of the intermediate; several FCM sub-chunks, ragged clips (guard rows inside a CTA's tile range), clips shorter than a tile."""
+    sdv, sdc, emb = _emb(models, "W1")
+    lens = [int(x) for x in synth.ragged_lengths(12)] + [720, 1200, 16000]
+    wavs = [synth.clip(i, n) for i, n in enumerate(lens)]
+    ctx = _lib.context(0)
+    flat = np.concatenate(wavs); off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    pcm = torch.from_numpy(flat).to(DEV)
+
+    def run():
+        ve_o, xv_o, _ = emb.embed_device(pcm, off)
+        torch.cuda.synchronize()
+        o, r, c, ld = ctx.locate("xv_fcm")
+        return xv_o.cpu().numpy(), emb._ws.buf[o:o + r * ld * 4].view(torch.float32).view(r, ld)[:, :c].cpu().numpy()
+
+    old = ctx.get_option("fcm_chunk_rows")
+    try:
+        xv_f, fcm_f = run()
+        ctx.set_option("fcm_chunk_rows", 3000)
+        xv_fc, fcm_fc = run()                                  # many sub-chunks
+        ctx.set_option("fcm_fuse", 0)
+        xv_s, fcm_s = run()
+    finally:
+        ctx.set_option("fcm_fuse", 1); ctx.set_option("fcm_chunk_rows", old)
+    assert ctx.get_option("fcm_fuse") == 1
+    assert np.isfinite(fcm_f).all()
+    assert relerr(fcm_f, fcm_s) < 1e-3 and relerr(fcm_fc, fcm_s) < 1e-3
+    scale = max(1.0, float(np.abs(xv_s[:-3]).max()))
+    assert np.abs(xv_f[:-3] - xv_s[:-3]).max() < 5e-4 * scale and np.abs(xv_fc[:-3] - xv_s[:-3]).max() < 5e-4 * scale
+    want = nets.campplus_embed_wavs(sdc, wavs[:4])
+    assert np.abs(xv_f[:4] - want).max() <= 1e-3 * max(1.0, float(np.abs(want).max()))
+
+
 def test_mode1_results_are_reproducible(models, mode1):
     """Bit-identical embeddings from run to run, with the two encoder chains on two streams and programmatic dependent launch
     on: no float atomics on the path (segment sums are 64-bit fixed-point reductions) and no racy staging.  An earlier build
