@@ -156,6 +156,7 @@ struct cbx_ctx {
   int64_t lstm_trace = 0;             // device pointer of the clock trace buffer
   int64_t lstm_impl = 2;              // 1: DSMEM-push recurrence, 2: L2 multicast-TMA recurrence
   int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)
+  int64_t lstm_gate_warps = 4;        // gate warps per TMEM lane quadrant of the recurrence kernel: 4 (16 gate warps) or 2 (8, round 1)
   int64_t fcm_fuse = 1;               // identity residual blocks of the FCM head as one fused kernel (fcm_block_tc.cu); 0 = two convolution kernels
   int64_t xw_bf16 = 0;                // 1 = the LSTM input projections are stored as bf16 (bf16 mode)
   int64_t cat_bf16 = 0;               // 1 = the D-TDNN GEMMs read a bf16 copy of the concatenation buffers, 2 = and run on bf16 operands (kind::f16)

@@ -22,6 +22,8 @@
 //     staging tile and one TMA tensor store.
 // The first and last tile of a CTA's range also need the intermediate of the neighbouring range's edge tile: conv 1 is simply
 // run for one extra tile on either side (2 of ~580 tiles per CTA).
+#include <algorithm>
+
 #include "cbx_internal.h"
 #include "tc.cuh"
 
@@ -38,7 +40,7 @@ constexpr int MAX_STAGES = 3;
 
 struct Params {
   int F, pitch, BR, rows, ntiles, per_cta, nstages;
-  uint32_t stage_bytes, ring_bytes;
+  uint32_t stage_bytes, ring_bytes, tail_bytes;
   const float* bias1; const float* bias2; const float* res; const int32_t* row_clip;
 };
 
@@ -52,7 +54,7 @@ fcm_block_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
   uint8_t* sOut = sW2 + W_BYTES;
   uint8_t* sRing = sOut + OUT_BYTES;                    // [1 + SLOTS * BR + 1 (+ slack)][pitch][128 B]; physical row 0 = logical row -1
   uint8_t* sIn = sRing + p.ring_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + p.nstages * p.stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sIn + p.nstages * p.stage_bytes + p.tail_bytes);    // tail: over-read slack of the last stage
   uint64_t* full = bars;                    // [MAX_STAGES] input stage landed
   uint64_t* empty = full + MAX_STAGES;      // [MAX_STAGES] conv-1 MMAs of the stage completed
   uint64_t* a1full = empty + MAX_STAGES;    // [2] conv-1 accumulator ready
@@ -133,7 +135,7 @@ fcm_block_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
       __syncwarp();
     };
     auto conv2 = [&](int j) {                // local tile j (1 .. n1 - 2) = ring slot j % SLOTS; needs the intermediate of tiles j - 1 .. j + 1
-      const int a = j & 1, pa = (j >> 1) & 1;
+      const int a = (j - 1) & 1, pa = ((j - 1) >> 1) & 1;        // accumulator 2 is first used by tile 1: the phase counts from there
       mbar_wait(&a2empty[a], pa ^ 1);
       mbar_wait(&midfull[(j + 1) % SLOTS], ((j + 1) / SLOTS) & 1);      // epilogue 1 works in order: tiles j - 1 and j are in place too
       tc_fence_after();
@@ -152,10 +154,13 @@ fcm_block_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
       }
       __syncwarp();
     };
+    // conv 1 runs TWO tiles ahead of conv 2: conv 2 of tile j needs the intermediate of tile j + 1, whose epilogue (~1 us) must not
+    // sit between two consecutive entries of the tensor pipe's queue
     conv1(0);
-    if (n1 > 1) conv1(1);
+    conv1(1);
+    if (n1 > 2) conv1(2);
     for (int j = 1; j <= n1 - 2; ++j) {
-      if (j + 1 < n1) conv1(j + 1);
+      if (j + 2 < n1) conv1(j + 2);
       conv2(j);
     }
   } else if (warp < 6) {
@@ -212,7 +217,7 @@ fcm_block_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant
     const bool issuer = warp == 6 && lane == 0;
     pdl_wait();
     for (int j = 1; j <= n1 - 2; ++j) {
-      const int a = j & 1, pa = (j >> 1) & 1;
+      const int a = (j - 1) & 1, pa = ((j - 1) >> 1) & 1;
       const int tile = t_lo - 1 + j;
       const int row = tile * BR + t;
       const bool has = t < BR && fr < p.F && row < p.rows;
@@ -302,11 +307,16 @@ void run_fcm_block_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmW1, cons
   p.bias1 = bias1; p.bias2 = bias2; p.res = in; p.row_clip = row_clip;
   auto align1k = [](uint32_t x) { return (x + 1023u) & ~1023u; };
   p.stage_bytes = align1k((uint32_t)((BR + 2) * pitch * 128));
-  // 1 + SLOTS * BR + 1 rows, plus slack for the two junk positions (M rows 126, 127) of the deepest tap of the last slot
-  p.ring_bytes = align1k((uint32_t)((SLOTS * BR + 2) * pitch * 128 + 4 * 128));
+  // An A operand is always 128 positions: with BR * pitch < 128 the junk accumulator rows read past the halo block (their results
+  // are dropped).  The deepest tap starts at position 2 * pitch + 2, so a block of (BR + 2) * pitch positions is over-read by
+  // `over` bytes: the ring is sized for the last slot's reads, and the input stages are followed by that much slack.
+  const uint32_t over = (uint32_t)std::max(0, (2 * pitch + 2 + 128) - (BR + 2) * pitch) * 128u;
+  p.ring_bytes = align1k((uint32_t)((SLOTS * BR + 2) * pitch * 128) + over);
+  const int tail = (int)align1k(over + 128);
   constexpr int kSmemMax = 227 * 1024;
   p.nstages = MAX_STAGES;
-  auto need = [&]() { return 2 * W_BYTES + OUT_BYTES + (int)p.ring_bytes + p.nstages * (int)p.stage_bytes + 256 + 1024; };
+  p.tail_bytes = (uint32_t)tail;
+  auto need = [&]() { return 2 * W_BYTES + OUT_BYTES + (int)p.ring_bytes + p.nstages * (int)p.stage_bytes + tail + 256 + 1024; };
   if (need() > kSmemMax) p.nstages = 2;
   const int smem = need();
   if (smem > kSmemMax) { fprintf(stderr, "libcbx: fcm block kernel does not fit shared memory (F=%d)\n", F); return; }

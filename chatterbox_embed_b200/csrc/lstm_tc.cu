@@ -323,9 +323,9 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) lstm_re
 //     the addressing in the loop is immediate offsets from two running pointers;
 //   * the gate math of a half-step is spread over all 8 gate warps (two per TMEM lane quadrant, 56 partials each) and the
 //     xw loads of the NEXT half-step are issued chunk by chunk while the current one is being computed.
-constexpr int HALF = NSUB / 2;             // partials per gate warp and half-step
-constexpr int CH2 = 8;                     // partials per tcgen05.ld in v2
-static_assert(HALF % CH2 == 0, "chunking");
+// Gate warps per TMEM lane quadrant (NGW): 2 -> 8 gate warps, 56 partials and 8-column chunks per thread (round 1); 4 -> 16 gate
+// warps (four per SM sub-partition), 28 partials and 4-column chunks per thread: the same instructions in total, but twice the
+// warps to hide the TMEM-load / MUFU / shuffle latencies of the dependent chain behind (the gate math is latency bound).
 
 // streaming 4-byte load that does not allocate in L1: the unified L1 / shared-memory array is busy feeding the tensor core
 __device__ __forceinline__ float ldg_stream_f32(const float* p) {
@@ -372,7 +372,15 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, 
       : "memory");
 }
 
-constexpr int THREADS2 = 320;              // warp 0: MMA issuer, warps 1-8: gate warps, warp 9: exchange
+// (Loading a half-step's 28 accumulator columns with back-to-back tcgen05.ld and ONE wait was measured slower than the per-chunk
+// loads: 3.25 -> 3.53 ms for the three layers -- the gate phase is bound by its instruction count, not by TMEM latency.)
+constexpr int threads2(int ngw) { return 32 * (2 + 4 * ngw); }      // warp 0: MMA issuer, warps 1 .. 4 NGW: gate warps, last warp: exchange
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 // 4 reciprocals for one MUFU: r = 1/(d0 d1 d2 d3); the d's are 1 + 2^x with x clamped to 30, so the product stays finite
 __device__ __forceinline__ void rcp4(float d0, float d1, float d2, float d3, float& i0, float& i1, float& i2, float& i3) {
@@ -382,9 +390,15 @@ __device__ __forceinline__ void rcp4(float d0, float d1, float d2, float d3, flo
   i0 = r01 * d1; i1 = r01 * d0; i2 = r23 * d3; i3 = r23 * d2;
 }
 
-template <bool kLayer0, bool kXw16>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS2, 1)
+template <bool kLayer0, bool kXw16, int NGW>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(threads2(NGW), 1)
 lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
+  constexpr int THREADS2 = threads2(NGW);
+  constexpr int HALF = NSUB / NGW;           // partials per gate warp and half-step
+  constexpr int CH2 = NGW == 2 ? 8 : 4;      // partials per tcgen05.ld
+  constexpr int NGRP = CH2 / 4;              // groups of four partials per chunk (one 4x4 transpose each)
+  constexpr int XWARP = 1 + 4 * NGW;         // the exchange warp
+  static_assert(HALF % CH2 == 0 && NSUB % NGW == 0, "chunking");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* hbuf = smem;                                                   // [2][8 K blocks][NSUB rows x 128 B]
@@ -404,7 +418,7 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmH);
-    for (int x = 0; x < 2; ++x) { mbar_init(&full[x], 1); mbar_init(&freeb[x], CL); mbar_init(&accum[x], 1); mbar_init(&ready[x], 256); }
+    for (int x = 0; x < 2; ++x) { mbar_init(&full[x], 1); mbar_init(&freeb[x], CL); mbar_init(&accum[x], 1); mbar_init(&ready[x], 128 * NGW); }
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -464,7 +478,7 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
         __syncwarp();
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == XWARP) {
     // ===================== exchange: slice stored -> peers' MMAs done with h_{t-1} -> multicast TMA load into all 8 B tiles
     if (lane == 0) {
       for (int t = 0; t < kVePartial - 1; ++t) {
@@ -472,6 +486,11 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
         for (int x = 0; x < 2; ++x) {
           const int hs = 2 * t + x;
           mbar_wait(&ready[x], t & 1);
+          // ONE gpu-scope fence per half-step, here: the gate threads' stores of h_t were ordered before their (release.cta)
+          // arrivals on `ready`, which this thread has just acquired, and fences are cumulative -- so this fence makes all of
+          // them visible at L2, where the TMA load below reads them.  (Round 1 had every gate thread execute __threadfence():
+          // MEMBAR.SC + ERRBAR + CCTL.IVALL in 512 threads was 16 % of the kernel's warp-stall samples, ncu source page.)
+          __threadfence();
           asm volatile("fence.proxy.async.global;" ::: "memory");
           if (tr) p.trace[(t * 2 + x) * 8 + 5] = clock64();
           mbar_wait_cluster(&freeb[x], t & 1);
@@ -490,7 +509,7 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
     const bool P0 = g & 1, P1 = g & 2;
     const float m = g == 2 ? 2.f : 1.f;
     const float neg_m_log2e = -m * 1.4426950408889634f, one_minus_m = 1.f - m;
-    const int gt = threadIdx.x - 32;               // 0..255
+    const int gt = threadIdx.x - 32;               // 0 .. 128 NGW - 1
     const int n0 = hf * HALF;                      // first partial (within a sub-tile) of this warp
     using XwT = typename std::conditional<kXw16, uint16_t, float>::type;
     const XwT* xq = static_cast<const XwT*>(p.xw) + (kLayer0 ? (size_t)0 : (blk0 + n0) * kVeGates) + j * 128 + r;
@@ -520,7 +539,7 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
     // activations of one 8-column chunk: own gate of 8 partials; two shared reciprocals
     auto activate = [&](int x, int c, const uint32_t* xin, float* a) {
       float v[CH2];
-      tmem_ld8(dcol + x * NSUB + c * CH2, v);
+      if constexpr (CH2 == 8) tmem_ld8(dcol + x * NSUB + c * CH2, v); else tmem_ld4(dcol + x * NSUB + c * CH2, v);
 #ifndef CBX_LSTM_EXP_RCP_ACT
       // MUFU.TANH: sigmoid(s) = 0.5 tanh(0.5 s) + 0.5.  Measured against the oracle the embedding error is the same as with
       // the ex2 + rcp formulation below (W1 1.5e-5, W2 3.6e-4: the TF32 products dominate), at 3 instructions per gate value.
@@ -536,8 +555,8 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
 #pragma unroll
       for (int i = 0; i < CH2; ++i) d[i] = 1.f + ex2_approx(fminf((v[i] + xval(xin[c * CH2 + i])) * neg_m_log2e, 30.f));
       float inv[CH2];
-      rcp4(d[0], d[1], d[2], d[3], inv[0], inv[1], inv[2], inv[3]);
-      rcp4(d[4], d[5], d[6], d[7], inv[4], inv[5], inv[6], inv[7]);
+#pragma unroll
+      for (int i = 0; i < CH2; i += 4) rcp4(d[i], d[i + 1], d[i + 2], d[i + 3], inv[i], inv[i + 1], inv[i + 2], inv[i + 3]);
 #pragma unroll
       for (int i = 0; i < CH2; ++i) a[i] = fmaf(m, inv[i], one_minus_m);
 #endif
@@ -557,13 +576,6 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
         tc_fence_after();
         if (trt) p.trace[(t * 2 + x) * 8 + 3] = clock64();
         if (gt < CL) remote_arrive(peer_free[x]);
-        if (hs > 0) {
-          // publish the PREVIOUS half-step's slice now: its stores have had the whole accumulator wait to reach L2, so the
-          // fence is cheap, and the exchange it triggers is not needed before this half-step's math is over anyway
-          __threadfence();
-          asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy GLOBAL stores ordered before the exchange warp's TMA read
-          mbar_arrive(&ready[x ^ 1]);
-        }
         float* hrow = hq + (size_t)hs * NSUB * kVeHidden;
         // software pipeline over the 7 chunks: the activations (MUFU) of chunk c+1 are issued alongside the transpose and
         // cell update (ALU / shuffle) of chunk c
@@ -578,9 +590,9 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
             for (int i = 0; i < CH2; ++i) xv[c * CH2 + i] = xw_load(hs + 1, c * CH2 + i);
           }
           const float* v = act[c & 1];
-          float cn[2], gout[2];
+          float cn[NGRP], gout[NGRP];
 #pragma unroll
-          for (int grp = 0; grp < 2; ++grp) {
+          for (int grp = 0; grp < NGRP; ++grp) {
             const float a0 = v[4 * grp], a1 = v[4 * grp + 1], a2 = v[4 * grp + 2], a3 = v[4 * grp + 3];
             const float k0 = P0 ? a1 : a0, s0 = P0 ? a0 : a1;
             const float k1 = P0 ? a3 : a2, s1 = P0 ? a2 : a3;
@@ -592,29 +604,40 @@ lstm_rec_tc2_kernel(const __grid_constant__ CUtensorMap tmH, Params2 p) {
             const float e1 = P0 ? par2 : own2, o1 = P0 ? own2 : par2;
             const float gi = P1 ? e1 : e0, gg = P1 ? e0 : e1, gf = P1 ? o1 : o0;
             gout[grp] = P1 ? o0 : o1;
-            const int ci = c * 2 + grp;
+            const int ci = c * NGRP + grp;
             cn[grp] = fmaf(gf, cst[x][ci], gi * gg);
             cst[x][ci] = cn[grp];
           }
-          // tanh(c) of the two cells with one reciprocal
+          // tanh(c) of the chunk's cells, h = o * tanh(c), stored (tf32-rounded) into the layer's hseq buffer = the exchange medium
+          float hh[NGRP];
 #ifndef CBX_LSTM_EXP_RCP_ACT
-          float th0, th1;
-          asm("tanh.approx.f32 %0, %1;" : "=f"(th0) : "f"(cn[0]));
-          asm("tanh.approx.f32 %0, %1;" : "=f"(th1) : "f"(cn[1]));
-          const float h0 = gout[0] * th0, h1 = gout[1] * th1;
-#else
-          const float d0 = 1.f + ex2_approx(fminf(cn[0] * (-2.f * 1.4426950408889634f), 60.f));
-          const float d1 = 1.f + ex2_approx(fminf(cn[1] * (-2.f * 1.4426950408889634f), 60.f));
-          const float rr = rcp_approx(d0 * d1);
-          const float h0 = gout[0] * fmaf(2.f, rr * d1, -1.f), h1 = gout[1] * fmaf(2.f, rr * d0, -1.f);
-#endif
-          hrow[(size_t)(c * CH2) * kVeHidden] = to_tf32(h0);           // partial n0 + c*8 + g
-          hrow[(size_t)(c * CH2 + 4) * kVeHidden] = to_tf32(h1);       // partial n0 + c*8 + 4 + g
-          if (last && p.hlast) {
-            const int q = q_tile + x * NSUB + n0 + c * CH2 + g;
-            if (q < p.n_slots) p.hlast[(size_t)q * kVeHidden + j * UNITS + u] = h0;
-            if (q + 4 < p.n_slots) p.hlast[(size_t)(q + 4) * kVeHidden + j * UNITS + u] = h1;
+#pragma unroll
+          for (int grp = 0; grp < NGRP; ++grp) {
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(cn[grp]));
+            hh[grp] = gout[grp] * th;
           }
+#else
+#pragma unroll
+          for (int grp = 0; grp < NGRP; ++grp) {
+            const float dd = 1.f + ex2_approx(fminf(cn[grp] * (-2.f * 1.4426950408889634f), 60.f));
+            hh[grp] = gout[grp] * fmaf(2.f, rcp_approx(dd), -1.f);
+          }
+#endif
+#pragma unroll
+          for (int grp = 0; grp < NGRP; ++grp) {
+            hrow[(size_t)(c * CH2 + 4 * grp) * kVeHidden] = to_tf32(hh[grp]);           // partial n0 + c * CH2 + 4 grp + g
+            if (last && p.hlast) {
+              const int q = q_tile + x * NSUB + n0 + c * CH2 + 4 * grp + g;
+              if (q < p.n_slots) p.hlast[(size_t)q * kVeHidden + j * UNITS + u] = hh[grp];
+            }
+          }
+        }
+        // publish this half-step's slice of h_t at once: the exchange (fence, wait for the peers, multicast TMA) and the MMA of
+        // the next step of this sub-tile then run while the gate warps are in the other sub-tile's math
+        if (hs + 2 < 2 * kVePartial) {
+          asm volatile("fence.proxy.async.global;" ::: "memory");   // generic-proxy GLOBAL stores ordered before the exchange warp's TMA read
+          mbar_arrive(&ready[x]);
         }
         if (trt) p.trace[(t * 2 + x) * 8 + 4] = clock64();
         tc_fence_before();
@@ -680,11 +703,16 @@ void run_lstm_rec_tc2(cbx_ctx* c, const void* xw, bool xw_bf16, const int32_t* s
   lstm::Params2 p{xw, slot_row, whh_perm, hseq, hlast, n_slots, (long long*)c->lstm_trace};
   Scope sc(c->launches, st, "lstm_rec_tc_kernel", 2.0 * n_slots * kVePartial * kVeHidden * kVeGates,
            (double)n_slots * kVePartial * ((xw_bf16 ? 2.0 : 4.0) * kVeGates + 4.0 * kVeHidden));
-  auto go = [&](auto kern) {
+  auto go = [&](auto kern, int ngw) {
     ensure_max_smem(kern, lstm::SMEM_BYTES);
-    kern<<<tiles * lstm::CL, lstm::THREADS2, lstm::SMEM_BYTES, st>>>(tmH, p);
+    kern<<<tiles * lstm::CL, lstm::threads2(ngw), lstm::SMEM_BYTES, st>>>(tmH, p);
   };
-  if (slot_row) { if (xw_bf16) go(lstm::lstm_rec_tc2_kernel<true, true>); else go(lstm::lstm_rec_tc2_kernel<true, false>); }
-  else { if (xw_bf16) go(lstm::lstm_rec_tc2_kernel<false, true>); else go(lstm::lstm_rec_tc2_kernel<false, false>); }
+  if (c->lstm_gate_warps == 4) {
+    if (slot_row) { if (xw_bf16) go(lstm::lstm_rec_tc2_kernel<true, true, 4>, 4); else go(lstm::lstm_rec_tc2_kernel<true, false, 4>, 4); }
+    else { if (xw_bf16) go(lstm::lstm_rec_tc2_kernel<false, true, 4>, 4); else go(lstm::lstm_rec_tc2_kernel<false, false, 4>, 4); }
+  } else {
+    if (slot_row) { if (xw_bf16) go(lstm::lstm_rec_tc2_kernel<true, true, 2>, 2); else go(lstm::lstm_rec_tc2_kernel<true, false, 2>, 2); }
+    else { if (xw_bf16) go(lstm::lstm_rec_tc2_kernel<false, true, 2>, 2); else go(lstm::lstm_rec_tc2_kernel<false, false, 2>, 2); }
+  }
 }
 }  // namespace cbx

@@ -346,6 +346,23 @@ def test_mode1_ragged_config3(models, mode1):
         assert pl.xv_frames == 1 + (n - 400) // 160 and pl.xv_tdnn == (pl.xv_frames - 1) // 2 + 1
 
 
+def test_lstm_gate_warp_variants_agree(models, mode1):
+    """The recurrence kernel with 16 gate warps (four per SM sub-partition, the default) computes exactly what the 8-warp layout
+    of round 1 computes: the same per-element arithmetic, only distributed differently -> bit-identical embeddings."""
+    sdv, sdc, ve, cp = models["W2"]
+    g = torch.Generator().manual_seed(5)
+    parts = (torch.rand((300, 160, 40), generator=g) * 0.3).to(DEV)
+    ctx = _lib.context(0)
+    assert ctx.get_option("lstm_gate_warps") == 4
+    a = ve(parts).cpu().numpy()
+    try:
+        ctx.set_option("lstm_gate_warps", 2)
+        b = ve(parts).cpu().numpy()
+    finally:
+        ctx.set_option("lstm_gate_warps", 4)
+    assert np.isfinite(a).all() and np.array_equal(a, b)
+
+
 def test_fcm_fused_block_matches_separate_convolutions(models, mode1):
     """The identity residual blocks of the FCM head run as one fused kernel (intermediate in a shared-memory ring,
     fcm_block_tc.cu).  Same arithmetic as the two separate convolution kernels (option fcm_fuse = 0) up to the tf32 rounding
