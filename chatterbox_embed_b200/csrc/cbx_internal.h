@@ -112,7 +112,7 @@ struct XvWeights {
   TransitW transit[3];
   const float *out_a, *out_b;                     // out_nonlinear BN
   const float *fin_w, *fin_b;                     // [192][1024] (BN folded), [192]
-  CUtensorMap tm_tdnn, tm_w1[52], tm_wl[52], tm_tr[3];   // TMA maps of the GEMM B operands
+  CUtensorMap tm_tdnn, tm_w1[52], tm_wl[52], tm_tr[3], tm_tr256[3];   // TMA maps of the GEMM B operands (tm_tr256: 256-row boxes for the N = 256 transit tiles)
   CUtensorMap tm_w1h[52], tm_trh[3];                     // bf16 copies: box {64 channels, 128 rows}
   CUtensorMap tm_res[2][2][2], tm_head2;
 };
@@ -157,6 +157,7 @@ struct cbx_ctx {
   int64_t lstm_impl = 2;              // 1: DSMEM-push recurrence, 2: L2 multicast-TMA recurrence
   int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)
   int64_t lstm_gate_warps = 4;        // gate warps per TMEM lane quadrant of the recurrence kernel: 4 (16 gate warps) or 2 (8, round 1)
+  int64_t transit_n256 = 1;           // transit GEMMs with 128 x 256 output tiles
   int64_t fcm_fuse = 1;               // identity residual blocks of the FCM head as one fused kernel (fcm_block_tc.cu); 0 = two convolution kernels
   int64_t xw_bf16 = 0;                // 1 = the LSTM input projections are stored as bf16 (bf16 mode)
   int64_t cat_bf16 = 0;               // 1 = the D-TDNN GEMMs read a bf16 copy of the concatenation buffers, 2 = and run on bf16 operands (kind::f16)

@@ -302,6 +302,7 @@ int load_xv(cbx_ctx* c, const TensorMap& t) {
       for (int k = 0; k < 2; ++k) W.tm_res[l][b][k] = tc::make_map_2d(W.res[l][b][k].w, kFcmC, W.res[l][b][k].K, W.res[l][b][k].K, 32, true);
   W.tm_head2 = tc::make_map_2d(W.head_conv2.w, kFcmC, 288, 288, 32, true);
   for (int b = 0; b < 3; ++b) W.tm_tr[b] = tc::make_map_2d(W.transit[b].w, W.transit[b].cout, W.transit[b].cin, W.transit[b].cin, 128, true);
+  for (int b = 0; b < 3; ++b) W.tm_tr256[b] = tc::make_map_2d(W.transit[b].w, W.transit[b].cout, W.transit[b].cin, W.transit[b].cin, 256, true);
   for (int b = 0; b < 3; ++b) W.tm_trh[b] = tc::make_map_2d_bf16(W.transit[b].wh, W.transit[b].cout, W.transit[b].cin, W.transit[b].cin, 128);
   W.loaded = true;
   return CBX_OK;

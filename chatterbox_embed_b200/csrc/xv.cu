@@ -584,6 +584,11 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     else if (bf)
       tc::tgemm_bnrelu<128, 2, tc::EpiMask, 1>(L, st, "transit_gemm", cath[b], ld, T.a, T.b, W.tm_tr[b], out, ldo, M, T.cout, T.cin,
                                tc::EpiMask{nullptr, ldo, ch.td_row_clip, M, b < 2 ? cath[b + 1] : nullptr, ldo}, pdl);
+    else if (tcm && c->transit_n256 && T.cout % 256 == 0)
+      // N = 256 output tiles: the X tile (BN + ReLU producers, the stage stores) is made once per 256 output channels instead of once
+      // per 128, and the A operand is read from shared memory once per 256: 48 KB instead of 64 KB through the array per 128 x 128 x 32
+      tc::tgemm_bnrelu<256, 2>(L, st, "transit_gemm", cat, ld, T.a, T.b, W.tm_tr256[b], out, ldo, M, T.cout, T.cin,
+                               tc::EpiMask{nullptr, ldo, ch.td_row_clip, M}, pdl);
     else if (tcm)
       tc::tgemm_bnrelu<128, 2>(L, st, "transit_gemm", cat, ld, T.a, T.b, W.tm_tr[b], out, ldo, M, T.cout, T.cin,
                                tc::EpiMask{nullptr, ldo, ch.td_row_clip, M}, pdl);

@@ -35,13 +35,24 @@ def run(flags):
 
 
 BOTH, VE, XV = _lib.DO_VE | _lib.DO_XV, _lib.DO_VE, _lib.DO_XV
+DEFAULTS = {"overlap": 1, "pdl": 1, "probe": 0, "lstm_gate_warps": 4, "fcm_fuse": 1, "mode": 1, "transit_n256": 1}
 rows = []
 for name, flags, opts in (("both encoders (the bench step)", BOTH, {}), ("VoiceEncoder alone", VE, {}), ("CAMPPlus alone", XV, {}),
                           ("both, one stream (overlap 0)", BOTH, {"overlap": 0}), ("CAMPPlus alone, no dependent launch (pdl 0)", XV, {"pdl": 0}),
-                          ("CAMPPlus alone, CAM gate kernel removed (probe 1)", XV, {"probe": 1}),
-                          ("both, CAM gate kernel removed (probe 1)", BOTH, {"probe": 1})):
-    for k, v in opts.items(): ctx.set_option(k, v)
+                          ("both, 8 gate warps in the recurrence (lstm_gate_warps 2)", BOTH, {"lstm_gate_warps": 2}),
+                          ("VoiceEncoder alone, 8 gate warps", VE, {"lstm_gate_warps": 2}),
+                          ("both, FCM identity blocks as two convolutions (fcm_fuse 0)", BOTH, {"fcm_fuse": 0}),
+                          ("CAMPPlus alone, fcm_fuse 0", XV, {"fcm_fuse": 0}),
+                          ("CAMPPlus alone, transit GEMMs with 128-wide tiles (transit_n256 0)", XV, {"transit_n256": 0}),
+                          ("CAMPPlus alone again", XV, {}),
+                          ("both, bf16 mode (mode 2)", BOTH, {"mode": 2}),
+                          ("both encoders again (drift check)", BOTH, {}),
+                          ("CAMPPlus alone, CAM gate kernel removed (probe 1; dev build only)", XV, {"probe": 1})):
+    try:
+        for k, v in opts.items(): ctx.set_option(k, v)
+    except Exception as e:
+        print(f"{name:<66s} skipped ({e})"); continue
     ms = run(flags)
-    for k in opts: ctx.set_option(k, {"overlap": 1, "pdl": 1, "probe": 0}[k])
+    for k in opts: ctx.set_option(k, DEFAULTS[k])
     rows.append((name, ms))
-    print(f"{name:<52s} {ms:7.3f} ms", flush=True)
+    print(f"{name:<66s} {ms:7.3f} ms", flush=True)
