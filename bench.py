@@ -245,14 +245,13 @@ def precision_fields(args, ctx):
     return dtype, note
 
 
-def run_job(args):
-    """BASELINE configs[3]: the sharded voice-bank job (strong scaling)."""
+def job_core(args, world, rank, local, dev, emb, ctx, sdv, sdc, n, ragged, warm=1):
+    """BASELINE configs[3]: partition -> stream every rank's shard -> one all-gather -> un-permute -> parity sample.  Collective on
+    every rank; returns the result dict on rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
     from chatterbox_embed_b200 import scheduler, synth
-    world, rank, local, dev, emb, ctx, sdv, sdc = setup(args)
-    n = args.job_clips
-    lengths = synth.ragged_lengths(n, seed=77) if args.ragged else np.full(n, CLIP_SAMPLES, dtype=np.int64)
+    lengths = synth.ragged_lengths(n, seed=77) if ragged else np.full(n, CLIP_SAMPLES, dtype=np.int64)
     max_samples = CLIPS * CLIP_SAMPLES
     # host PCM store: a pinned "tape" of synthetic audio (noise and chirp clips back to back); batch b of rank r is the window
     # of its length starting at a batch-dependent offset, its clips are consecutive slices of that window.  Every batch is copied
@@ -275,7 +274,8 @@ def run_job(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def job():
+    def job(lengths):
+        n = len(lengths)
         t = {}
         t0 = time.perf_counter()
         shards = scheduler.partition(lengths, world)
@@ -300,59 +300,73 @@ def run_job(args):
 
     clk = ClockSampler(local).start()
     # warm-up: a short job (allocations, NCCL communicator, first-launch costs)
-    n_full, lengths_full = n, lengths
-    n = min(n_full, 4 * CLIPS * world); lengths = lengths_full[:n]
-    for _ in range(max(1, min(args.warmup, 2))):
-        job()
-    n, lengths = n_full, lengths_full
+    for _ in range(warm):
+        job(lengths[:min(n, 4 * CLIPS * world)])
     sync_all()
     l0 = ctx.launch_count()
     tw0 = time.time()
-    full, shards, status, t = job()
+    full, shards, status, t = job(lengths)
     sync_all()
     tw1 = time.time()
     launches = ctx.launch_count() - l0
     clocks = clk.summary(tw0, tw1)
     clk.stop()
     tt = torch.tensor([t["partition_ms"], t["stream_ms"], t["gather_unpermute_ms"], t["job_ms"]], device=dev, dtype=torch.float64)
+    bad_t = torch.tensor([int((status != 0).sum())], device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(bad_t)
     part_ms, stream_ms, gather_ms, job_ms = [float(x) for x in tt]
+    if rank != 0:
+        return None
     full_np = full.cpu().numpy()
-    bad = int((status != 0).sum())
+    # parity: 8 sampled clips (spread over the ranks, shortest and longest included) against the oracle
+    rng = np.random.RandomState(5)
+    pick = sorted(set([int(np.argmin(lengths)), int(np.argmax(lengths))] + [int(x) for x in rng.choice(n, 6, replace=False)]))
+    wavs = {}
+    rank_of = np.empty(n, dtype=np.int64)
+    for r, sh in enumerate(shards):
+        rank_of[sh] = r
+    for i in pick:
+        r = int(rank_of[i])
+        pos = int(np.searchsorted(shards[r], i))
+        ln = lengths[shards[r]]
+        for b, (i0, i1) in enumerate(scheduler.batch_bounds(ln, CLIPS, max_samples)):
+            if i0 <= pos < i1:
+                w = window(r, b, int(ln[i0:i1].sum()))
+                o = int(ln[i0:pos].sum())
+                wavs[i] = np.array(w[o:o + int(lengths[i])])
+    order = list(wavs)
+    par = parity_sample(sdv, sdc, [wavs[i] for i in order], list(range(len(order))), full_np[order, :256], full_np[order, 256:])
+    par["clips_checked"] = order
+    par["ranks_of_clips_checked"] = [int(rank_of[i]) for i in order]
+    audio_s = float(lengths.sum()) / 16000.0
+    return {"value": n / (job_ms / 1e3), "unit": "clips/s", "audio_s_per_s": audio_s / (job_ms / 1e3), "job_clips": n, "audio_seconds": audio_s,
+            "kind": "3-30 s ragged" if ragged else "10 s each", "scaling": "strong",
+            "partition_ms": part_ms, "stream_ms": stream_ms, "gather_unpermute_ms": gather_ms, "job_ms": job_ms,
+            "clips_per_rank": [int(len(sh)) for sh in shards], "clips_with_status": int(bad_t[0]),
+            "collective": "one all_gather_into_tensor of the padded (clips/rank, 448) fp32 block (NCCL)" if world > 1 else None,
+            "timing": "host wall clock per phase, max over ranks; the job is bracketed by barrier + cuda synchronize",
+            "h2d_bytes": int(lengths.sum()) * 4, "d2h_bytes": n * (448 + 1) * 4, "gpu_launches": int(launches), "clocks": clocks, "parity": par}
+
+
+def run_job(args):
+    """--config 4: the sharded voice-bank job as the bench line (strong scaling)."""
+    import torch.distributed as dist
+    world, rank, local, dev, emb, ctx, sdv, sdc = setup(args)
+    j = job_core(args, world, rank, local, dev, emb, ctx, sdv, sdc, args.job_clips, args.ragged, warm=max(1, min(args.warmup, 2)))
     if rank == 0:
-        # parity: 8 sampled clips (spread over the ranks, shortest and longest included) against the oracle
-        rng = np.random.RandomState(5)
-        pick = sorted(set([int(np.argmin(lengths)), int(np.argmax(lengths))] + [int(x) for x in rng.choice(n, 6, replace=False)]))
-        wavs = {}
-        for i in pick:
-            r = next(rr for rr, sh in enumerate(shards) if i in set(sh.tolist())) if world > 1 else 0
-            pos = int(np.searchsorted(shards[r], i))
-            ln = lengths[shards[r]]
-            for b, (i0, i1) in enumerate(scheduler.batch_bounds(ln, CLIPS, max_samples)):
-                if i0 <= pos < i1:
-                    w = window(r, b, int(ln[i0:i1].sum()))
-                    o = int(ln[i0:pos].sum())
-                    wavs[i] = np.array(w[o:o + int(lengths[i])])
-        order = list(wavs)
-        par = parity_sample(sdv, sdc, [wavs[i] for i in order], list(range(len(order))), full_np[order, :256], full_np[order, 256:])
-        par["clips_checked"] = order
         dtype, note = precision_fields(args, ctx)
-        audio_s = float(lengths.sum()) / 16000.0
-        value = n / (job_ms / 1e3)
-        line = {"metric": "speaker embeddings/sec (voice-bank job)", "value": value, "unit": "clips/s", "audio_s_per_s": audio_s / (job_ms / 1e3),
-                "n_gpus": world, "steps": 1, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": job_ms, "higher_is_better": True,
+        line = {"metric": "speaker embeddings/sec (voice-bank job)", "value": j["value"], "unit": "clips/s", "audio_s_per_s": j["audio_s_per_s"],
+                "n_gpus": world, "steps": 1, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": j["job_ms"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic", "precision_note": note,
-                "config": {"workload": WORKLOADS[4].format(n=n, kind="3-30 s ragged" if args.ragged else "10 s each"), "job_clips": n,
-                           "audio_seconds": audio_s, "parallelism": f"dp{world}", "batch_clips": CLIPS,
+                "config": {"workload": WORKLOADS[4].format(n=j["job_clips"], kind=j["kind"]), "job_clips": j["job_clips"],
+                           "audio_seconds": j["audio_seconds"], "parallelism": f"dp{world}", "batch_clips": CLIPS,
                            "l2": "every batch (<= 164 MB PCM) and its activations exceed the 126 MB L2; no flush needed"},
-                "job": {"partition_ms": part_ms, "stream_ms": stream_ms, "gather_unpermute_ms": gather_ms, "job_ms": job_ms,
-                        "clips_per_rank": [int(len(sh)) for sh in shards], "clips_with_status": bad,
-                        "collective": "one all_gather_into_tensor of the padded (clips/rank, 448) fp32 block (NCCL)" if world > 1 else None,
-                        "timing": "host wall clock per phase, max over ranks; the job is bracketed by barrier + cuda synchronize"},
-                "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": int(lengths.sum()) * 4, "d2h_bytes_per_step": n * (448 + 1) * 4,
+                "job": {k: j[k] for k in ("partition_ms", "stream_ms", "gather_unpermute_ms", "job_ms", "clips_per_rank", "clips_with_status", "collective", "timing")},
+                "e2e": {"value": j["value"], "unit": "clips/s", "h2d_bytes_per_step": j["h2d_bytes"], "d2h_bytes_per_step": j["d2h_bytes"],
                         "api": "scheduler.partition -> scheduler.embed_shard (embed_stream) -> scheduler.gather_embeddings"},
-                "gpu_launches": int(launches), "clocks": clocks, "parity": par}
+                "gpu_launches": j["gpu_launches"], "clocks": j["clocks"], "parity": j["parity"]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -370,6 +384,7 @@ def main():
     ap.add_argument("--ragged", action="store_true", help="--config 4: 3-30 s clips instead of 10 s")
     ap.add_argument("--opt", action="append", default=[], help="libcbx option key=value (cbx_set_option)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-job", action="store_true", help="N > 1: skip the 1e5-clip voice-bank job that is attached to the line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -533,6 +548,10 @@ def main():
         if k in EXEC_FACTOR and tfl:
             kernels[k]["exec_tflops"] = tfl * EXEC_FACTOR[k]
 
+    # ---- N > 1: BASELINE configs[3] as well -- the 1e5-clip voice-bank job (strong scaling) on the same ranks ------------------
+    job = None
+    if world > 1 and args.config == 2 and not args.no_job:
+        job = job_core(args, world, rank, local, dev, emb, ctx, sdv, sdc, args.job_clips, False, warm=1)
     if rank == 0:
         # ---- parity of the timed configuration itself -------------------------------------------------------------
         lens = np.diff(off)
@@ -569,7 +588,7 @@ def main():
                     "api": "SpeakerEmbedder.embed_stream (cbx_embed_host_submit/_wait, two batches in flight)"
                            + ("; one all_gather_into_tensor of the embeddings per step inside the timed region" if world > 1 else ""),
                     "single_call_value": e2e_sync_value, "single_call_api": "cbx_embed_host (copy, compute, copy back, sync)"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity, "job": job,
             "tf32_peak_tflops": tf32, "timed_region_s": ms / 1e3,
             "algorithmic_tflops": (value * FLOPS_PER_CLIP / 1e12) if args.config == 2 else None, "kernels": kernels,
         }

@@ -585,6 +585,31 @@ def test_launch_options_do_not_change_results(models, mode1):
         ctx.set_option("pdl", 1); ctx.set_option("overlap", 1); ctx.set_option("transit_n256", 1)
 
 
+def test_many_small_batches_match_serialised_launches(models, mode1):
+    """Many small batches (short kernels, deep overlap between consecutive dependent launches), two in flight through the host
+    path, each compared bit for bit with the run without programmatic dependent launch.  This is the shape on which loading
+    "already final" K blocks AHEAD of griddepcontrol.wait returned wrong x-vectors (tried in round 1 and again in round 2 with the
+    exact set of final columns: still wrong when consecutive calls carry different data -- stale lines of the non-coherent load
+    path -- and no faster).  The shipped kernels read nothing a predecessor wrote before the wait."""
+    sdv, sdc, emb = _emb(models, "W1")
+    ctx = _lib.context(0)
+    rng = np.random.RandomState(7)
+    batches = []
+    for b in range(60):
+        lens = [int(x) for x in rng.randint(2000, 40000, size=rng.randint(1, 5))]
+        wavs = [synth.clip(100 * b + i, n) for i, n in enumerate(lens)]
+        batches.append((np.concatenate(wavs), np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)))
+    try:
+        ctx.set_option("pdl", 0)
+        want = [emb.embed_host(f, o) for f, o in batches]
+    finally:
+        ctx.set_option("pdl", 1)
+    for rep in range(3):
+        got = list(emb.embed_stream(iter(batches)))
+        for k, ((ve_a, xv_a, _), (ve_b, xv_b, _)) in enumerate(zip(want, got)):
+            assert np.array_equal(ve_a, ve_b) and np.array_equal(xv_a, xv_b), (rep, k)
+
+
 def test_stream_api_equals_single_calls(models, mode1):
     """cbx_embed_host_submit / _wait with two batches in flight returns what the one-shot call returns, in order."""
     sdv, sdc, emb = _emb(models, "W1")
