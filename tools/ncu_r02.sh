@@ -3,7 +3,7 @@
 # family.  Reports land in gpurun_out/r02/; tools/profile_summary_r02.py turns them into the tracked summaries under profiles/.
 #   bash tools/ncu_r02.sh [tag] [families...]      families default: all
 TAG=${1:-r02}; shift
-FAMS=${@:-"bottleneck lstm_rec fcm_conv dftmel pgemm tdnn stats_pool trim local_conv cam_gate conv1"}
+FAMS=${@:-"bottleneck transit lstm_rec fcm_conv fcm_block dftmel pgemm tdnn stats_pool trim local_conv cam_gate conv1"}
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 # 1. sustained line (>= 300 steps, ~6 s timed) with an nvidia-smi trace beside it
@@ -24,9 +24,13 @@ run() {
 }
 for f in $FAMS; do
   case $f in
+    # tgemm_bnrelu_kernel launches per step: block 1 = 12 bottlenecks + transit 1, block 2 = 24 + transit 2, block 3 = 16 + transit 3 (55);
+    # the 4th step starts at launch 165: 200, 201 = block-2 layers with cin = 960 / 992; 202 = transit 2 (K = 1024, N = 512)
     bottleneck) run bottleneck tgemm_bnrelu_kernel 200 2 ;;
-    lstm_rec)   run lstm_rec lstm_rec_tc2 9 1 ;;
-    fcm_conv)   run fcm_conv "fcm_conv_kernel|fcm_block_kernel" 109 2 ;;
+    transit)    run transit tgemm_bnrelu_kernel 202 1 ;;
+    lstm_rec)   run lstm_rec lstm_rec_tc2 10 1 ;;
+    fcm_conv)   run fcm_conv fcm_conv_kernel 85 2 ;;
+    fcm_block)  run fcm_block fcm_block_kernel 24 2 ;;
     dftmel)     run dftmel dftmel 6 2 ;;
     pgemm)      run pgemm pgemm_kernel 10 2 ;;
     tdnn)       run tdnn ^tgemm_kernel 3 1 ;;
