@@ -32,7 +32,10 @@ constexpr int SA = 2;                           // A stages: hi + lo, 16 KB each
 constexpr int SB = 4;                           // B slots of 32 KB: [256 x 32] of either the hi or the lo matrix
 constexpr int A_BYTES = BM * BK * 4;            // 16 KB
 constexpr int B_BYTES = 256 * BK * 4;           // 32 KB
-constexpr int SMEM_BYTES = SA * 2 * A_BYTES + SB * B_BYTES + 1024 + 128 * 16 + 256;
+constexpr int PGRP = 2;                         // producer groups (4 warps each) on alternate K blocks
+constexpr int THREADS = 32 * (2 + 4 * PGRP + 4);   // warp 0 TMA, warp 1 MMA, 8 producer warps, 4 epilogue warps
+constexpr int MAX_BINS = 256;
+constexpr int SMEM_BYTES = SA * 2 * A_BYTES + SB * B_BYTES + 1024 + 2 * 128 * 16 + MAX_BINS * 16 + 256;
 
 struct RowDesc { long long base; int start; int n; };   // element k of the frame = pcm[base + reflect(start + k, n)]; n == 0: zero row
 
@@ -89,180 +92,206 @@ struct S3Rows {
 };
 
 // LOG: 0 = power mel, 1 = ln(max(., eps)) (Kaldi), 2 = log10(max(., 1e-10)) + per-clip maximum (S3Tokenizer)
+//
+// Persistent: one CTA per SM loops over 128-frame tiles.  Round 1 launched one CTA per tile with the frame producers doubling as
+// the epilogue: with the whole TMEM as one accumulator only one CTA fits an SM, so the tensor pipe idled through every tile's
+// set-up, pipeline fill and epilogue (tensor pipe 40 % active, ~45 us per tile of which 16 us of MMAs).  Now
+//   * warps 2..9 are two producer groups on alternate K blocks (the gather's L2 latency of one block hides behind the other's
+//     stores) and run straight on into the next tile while
+//   * warps 10..13 are the epilogue: TMEM -> power -> mel with TWO running accumulators in registers (bin table of weights.cu:
+//     no shared-memory read-modify-write chain) -> transform -> global store; they release the accumulator as soon as they have
+//     read it, so the MMAs of the next tile start while the last mel values are still being written;
+//   * the DFT-matrix tiles (TMA) and the first A stages of the next tile are already in flight when the accumulator is released.
 template <class Rows, int NB1, int NMEL, int LOG>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(THREADS, 1)
 dftmel_kernel(const __grid_constant__ CUtensorMap tmHi0, const __grid_constant__ CUtensorMap tmLo0,
               const __grid_constant__ CUtensorMap tmHi1, const __grid_constant__ CUtensorMap tmLo1,
-              const float* __restrict__ pcm, Rows rows_fn, const float4* __restrict__ bintab, float* __restrict__ out, int rows) {
+              const float* __restrict__ pcm, Rows rows_fn, const float4* __restrict__ bintab, float* __restrict__ out, int rows, int ntiles) {
   constexpr int NB0 = 256;
   constexpr int NTOT = NB0 + NB1;
-  constexpr int MELLD = NMEL + 1;
-  static_assert(BM * MELLD * 4 <= SA * 2 * A_BYTES + SB * B_BYTES, "mel accumulators overlay the (drained) A and B stages");
+  static_assert(NTOT / 2 <= MAX_BINS, "bin table");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                                   // [SA][hi | lo][128 x 128 B]
   uint8_t* sB = smem + SA * 2 * A_BYTES;                // [SB][256 x 128 B]
-  RowDesc* rdesc = reinterpret_cast<RowDesc*>(sB + SB * B_BYTES);     // [128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rdesc + BM);
+  RowDesc* rdesc = reinterpret_cast<RowDesc*>(sB + SB * B_BYTES);     // [2][128]: the tile's row descriptors, double-buffered
+  float4* sbins = reinterpret_cast<float4*>(rdesc + 2 * BM);          // [NTOT / 2] bin table
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbins + MAX_BINS);
   uint64_t* a_full = bars;                 // [SA] 128 producer arrivals
   uint64_t* a_empty = bars + SA;           // [SA] MMA commit
   uint64_t* b_full = bars + 2 * SA;        // [SB] TMA bytes
   uint64_t* b_empty = b_full + SB;         // [SB] MMA commit
-  uint64_t* accum = b_empty + SB;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
-  float* melacc = reinterpret_cast<float*>(sA);         // [128][MELLD], after the K loop
+  uint64_t* accum = b_empty + SB;          // accumulator ready (MMA commit)
+  uint64_t* drained = accum + 1;           // accumulator read out (4 epilogue warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmHi0); tma_prefetch_desc(&tmLo0); tma_prefetch_desc(&tmHi1); tma_prefetch_desc(&tmLo1);
     for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < SB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     mbar_init(accum, 1);
+    mbar_init(drained, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  if (warp >= 2) {
-    const int r = threadIdx.x - 64;
-    rdesc[r] = (m0 + r < rows) ? rows_fn(m0 + r) : RowDesc{0, 0, 0};
-  }
+  for (int i = threadIdx.x; i < NTOT / 2; i += THREADS) sbins[i] = __ldg(bintab + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer: per K block the slots are  hi(cols 0..255), lo(0..255), hi(256..), lo(256..)
+    // ===== TMA producer: per K block the slots are  hi(cols 0..255), lo(0..255), hi(256..), lo(256..); the ring runs on across tiles
     if (lane == 0) {
       int it = 0;
-      for (int kb = 0; kb < NKB; ++kb)
-        for (int q = 0; q < 4; ++q, ++it) {
-          const int s = it % SB, ph = (it / SB) & 1;
-          mbar_wait(&b_empty[s], ph ^ 1);
-          const int nb = q >> 1;
-          mbar_expect_tx(&b_full[s], (nb ? NB1 : NB0) * BK * 4);
-          const CUtensorMap* tm = nb ? ((q & 1) ? &tmLo1 : &tmHi1) : ((q & 1) ? &tmLo0 : &tmHi0);
-          tma_load_2d(sB + s * B_BYTES, tm, &b_full[s], kb * BK, nb * NB0);
-        }
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        for (int kb = 0; kb < NKB; ++kb)
+          for (int q = 0; q < 4; ++q, ++it) {
+            const int s = it % SB, ph = (it / SB) & 1;
+            mbar_wait(&b_empty[s], ph ^ 1);
+            const int nb = q >> 1;
+            mbar_expect_tx(&b_full[s], (nb ? NB1 : NB0) * BK * 4);
+            const CUtensorMap* tm = nb ? ((q & 1) ? &tmLo1 : &tmHi1) : ((q & 1) ? &tmLo0 : &tmHi0);
+            tma_load_2d(sB + s * B_BYTES, tm, &b_full[s], kb * BK, nb * NB0);
+          }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp runs the loop, one elected lane issues
     constexpr uint32_t idesc0 = make_idesc_tf32(BM, NB0), idesc1 = make_idesc_tf32(BM, NB1);
-    int it = 0;
-    for (int kb = 0; kb < NKB; ++kb) {
-      const int sa = kb % SA, pa = (kb / SA) & 1;
-      mbar_wait(&a_full[sa], pa);
+    int it = 0, ia = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      mbar_wait(drained, (ti & 1) ^ 1);               // the epilogue has read the previous tile's accumulator
       tc_fence_after();
-      const uint64_t ahi = make_desc_sw128(smem_u32(sA + sa * 2 * A_BYTES));
-      const uint64_t alo = make_desc_sw128(smem_u32(sA + sa * 2 * A_BYTES + A_BYTES));
-      const int ksteps = (kb == NKB - 1) ? (KTOT - (NKB - 1) * BK) / UMMA_K : BK / UMMA_K;
-      for (int q = 0; q < 4; ++q, ++it) {
-        const int s = it % SB, ph = (it / SB) & 1;
-        mbar_wait(&b_full[s], ph);
+      for (int kb = 0; kb < NKB; ++kb, ++ia) {
+        const int sa = ia % SA, pa = (ia / SA) & 1;
+        mbar_wait(&a_full[sa], pa);
         tc_fence_after();
-        const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
-        const int nb = q >> 1;
-        const uint32_t d = tmem_base + nb * NB0;
-        const uint32_t idesc = nb ? idesc1 : idesc0;
-        if (elect_one()) {
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ko = (uint64_t)(k * UMMA_K * 4 >> 4);
-            if ((q & 1) == 0) {       // B_hi: A_hi.B_hi + A_lo.B_hi
-              umma_tf32(d, ahi + ko, bd + ko, idesc, (kb | k) != 0);
-              umma_tf32(d, alo + ko, bd + ko, idesc, 1);
-            } else {                  // B_lo: A_hi.B_lo
-              umma_tf32(d, ahi + ko, bd + ko, idesc, 1);
+        const uint64_t ahi = make_desc_sw128(smem_u32(sA + sa * 2 * A_BYTES));
+        const uint64_t alo = make_desc_sw128(smem_u32(sA + sa * 2 * A_BYTES + A_BYTES));
+        const int ksteps = (kb == NKB - 1) ? (KTOT - (NKB - 1) * BK) / UMMA_K : BK / UMMA_K;
+        for (int q = 0; q < 4; ++q, ++it) {
+          const int s = it % SB, ph = (it / SB) & 1;
+          mbar_wait(&b_full[s], ph);
+          tc_fence_after();
+          const uint64_t bd = make_desc_sw128(smem_u32(sB + s * B_BYTES));
+          const int nb = q >> 1;
+          const uint32_t d = tmem_base + nb * NB0;
+          const uint32_t idesc = nb ? idesc1 : idesc0;
+          if (elect_one()) {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ko = (uint64_t)(k * UMMA_K * 4 >> 4);
+              if ((q & 1) == 0) {       // B_hi: A_hi.B_hi + A_lo.B_hi
+                umma_tf32(d, ahi + ko, bd + ko, idesc, (kb | k) != 0);
+                umma_tf32(d, alo + ko, bd + ko, idesc, 1);
+              } else {                  // B_lo: A_hi.B_lo
+                umma_tf32(d, ahi + ko, bd + ko, idesc, 1);
+              }
+            }
+            umma_commit(&b_empty[s]);
+            if (q == 3) {
+              umma_commit(&a_empty[sa]);
+              if (kb == NKB - 1) umma_commit(accum);
             }
           }
-          umma_commit(&b_empty[s]);
-          if (q == 3) {
-            umma_commit(&a_empty[sa]);
-            if (kb == NKB - 1) umma_commit(accum);
-          }
+          __syncwarp();
         }
-        __syncwarp();
+      }
+    }
+  } else if (warp < 2 + 4 * PGRP) {
+    // ===== frame producers: group g takes the K blocks kb = g, g + 2, ...; warp w of a group fills rows [32 w, 32 w + 32) of the A
+    // stage, lanes along K (coalesced PCM reads).  The row descriptors of a tile are computed by group 0's threads one tile ahead
+    // (double-buffered), published to the other group through a named barrier.
+    const int g = (warp - 2) >> 2, wq = (warp - 2) & 3;
+    const int r_own = (threadIdx.x - 64) & 127;        // row whose descriptor this thread computes (both groups: 2 x 128 threads, same values)
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int m0 = tile * BM;
+      RowDesc* rd = rdesc + (ti & 1) * BM;
+      if (g == 0) rd[r_own] = (m0 + r_own < rows) ? rows_fn(m0 + r_own) : RowDesc{0, 0, 0};
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // all 8 producer warps: the descriptors of this tile are in place (and the
+                                                       // previous tile's reads of the other buffer are over before it is rewritten next time)
+      for (int kb = g; kb < NKB; kb += PGRP) {
+        const int ia = ti * NKB + kb;
+        const int sa = ia % SA, pa = (ia / SA) & 1;
+        const int k = kb * BK + lane;
+        float v[32];
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          const RowDesc d = rd[wq * 32 + rr];
+          int i = d.start + k;
+          if (i < 0) i = -i; else if (i >= d.n) i = 2 * (d.n - 1) - i;
+          v[rr] = (d.n > 0 && k < KTOT) ? __ldg(pcm + d.base + i) : 0.f;
+        }
+        mbar_wait(&a_empty[sa], pa ^ 1);
+        uint8_t* hi = sA + sa * 2 * A_BYTES;
+        uint8_t* lo = hi + A_BYTES;
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          const int r = wq * 32 + rr;
+          const float vh = to_tf32(v[rr]);
+          const float vl = to_tf32(v[rr] - vh);
+          const uint32_t o = r * 128 + ((((uint32_t)lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4;
+          *reinterpret_cast<float*>(hi + o) = vh;
+          *reinterpret_cast<float*>(lo + o) = vl;
+        }
+        fence_proxy_async();
+        mbar_arrive(&a_full[sa]);
       }
     }
   } else {
-    // ===== frame producers: warp w fills rows [32 w', 32 w' + 32) of every A stage, lanes along K (coalesced PCM reads)
-    const int wq = warp - 2;
-    for (int kb = 0; kb < NKB; ++kb) {
-      const int sa = kb % SA, pa = (kb / SA) & 1;
-      const int k = kb * BK + lane;
-      // all 32 rows' loads in flight before the stage is even free (memory-level parallelism: the PCM comes from L2 / HBM)
-      float v[32];
-#pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
-        const RowDesc d = rdesc[wq * 32 + rr];
-        int i = d.start + k;
-        if (i < 0) i = -i; else if (i >= d.n) i = 2 * (d.n - 1) - i;
-        v[rr] = (d.n > 0 && k < KTOT) ? __ldg(pcm + d.base + i) : 0.f;
-      }
-      mbar_wait(&a_empty[sa], pa ^ 1);
-      uint8_t* hi = sA + sa * 2 * A_BYTES;
-      uint8_t* lo = hi + A_BYTES;
-#pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
-        const int r = wq * 32 + rr;
-        const float vh = to_tf32(v[rr]);
-        const float vl = to_tf32(v[rr] - vh);
-        const uint32_t o = r * 128 + ((((uint32_t)lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4;
-        *reinterpret_cast<float*>(hi + o) = vh;
-        *reinterpret_cast<float*>(lo + o) = vl;
-      }
-      fence_proxy_async();
-      mbar_arrive(&a_full[sa]);
-    }
-    // ===== epilogue: thread = frame row; D columns 2b, 2b+1 = re, im of bin b
-    mbar_wait(accum, 0);
-    tc_fence_after();
+    // ===== epilogue: thread = frame row; D columns 2b, 2b+1 = re, im of bin b.  Two running accumulators: filter `cur` (A) and
+    // `cur + 1` (B); the bin table says how many finished filters to retire before a bin and the bin's two weights.
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    float* acc = melacc + row * MELLD;
-#pragma unroll 1
-    for (int m = 0; m < NMEL; ++m) acc[m] = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < NTOT / 16; ++c) {
-      float v[16];
-      {
-        uint32_t* rv = reinterpret_cast<uint32_t*>(v);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(rv[0]), "=r"(rv[1]), "=r"(rv[2]), "=r"(rv[3]), "=r"(rv[4]), "=r"(rv[5]), "=r"(rv[6]), "=r"(rv[7]), "=r"(rv[8]),
-              "=r"(rv[9]), "=r"(rv[10]), "=r"(rv[11]), "=r"(rv[12]), "=r"(rv[13]), "=r"(rv[14]), "=r"(rv[15])
-            : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16))
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float pw = fmaf(v[2 * i], v[2 * i], v[2 * i + 1] * v[2 * i + 1]);
-        const float4 tb = __ldg(bintab + c * 8 + i);              // warp-uniform: {w0, w1, m0, m1}
-        const int ma = __float_as_int(tb.z), mb = __float_as_int(tb.w);
-        acc[ma] = fmaf(tb.x, pw, acc[ma]);
-        acc[mb] = fmaf(tb.y, pw, acc[mb]);
-      }
-    }
-    tc_fence_before();
-    __syncwarp();
-    // each warp owns the 32 rows it accumulated: write them out row by row, lanes along the mel axis
-    for (int rr = 0; rr < 32; ++rr) {
-      const int r = q * 32 + rr;
-      const int gr = m0 + r;
-      if (gr >= rows) break;
-      const bool live = rows_fn.live(gr);
-      float mx = -INFINITY;
-      for (int m = lane; m < NMEL; m += 32) {
-        float val = melacc[r * MELLD + m];
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int gr = tile * BM + row;
+      const bool in_range = gr < rows;
+      const bool live = in_range && rows_fn.live(gr);
+      float* orow = out + (size_t)(in_range ? gr : 0) * NMEL;
+      float accA = 0.f, accB = 0.f, mx = -INFINITY;
+      int cur = 0;
+      auto retire = [&]() {
+        float val = accA;
         if (LOG == 1) val = logf(fmaxf(val, 1.1920928955078125e-07f));
         if (LOG == 2) { val = log10f(fmaxf(val, 1e-10f)); mx = fmaxf(mx, val); }
-        out[(size_t)gr * NMEL + m] = live ? val : 0.f;
-      }
-      if constexpr (LOG == 2) {
+        if (in_range) orow[cur] = live ? val : 0.f;
+        accA = accB; accB = 0.f; ++cur;
+      };
+      mbar_wait(accum, ti & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < NTOT / 16; ++c) {
+        float v[16];
+        {
+          uint32_t* rv = reinterpret_cast<uint32_t*>(v);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(rv[0]), "=r"(rv[1]), "=r"(rv[2]), "=r"(rv[3]), "=r"(rv[4]), "=r"(rv[5]), "=r"(rv[6]), "=r"(rv[7]), "=r"(rv[8]),
+                "=r"(rv[9]), "=r"(rv[10]), "=r"(rv[11]), "=r"(rv[12]), "=r"(rv[13]), "=r"(rv[14]), "=r"(rv[15])
+              : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16))
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        if (c == NTOT / 16 - 1) {            // the last columns are in registers: the next tile's MMAs may overwrite the accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(drained);
+        }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if (lane == 0) rows_fn.note_max(gr, mx);
+        for (int i = 0; i < 8; ++i) {
+          const float pw = fmaf(v[2 * i], v[2 * i], v[2 * i + 1] * v[2 * i + 1]);
+          const float4 tb = sbins[c * 8 + i];                      // warp-uniform: {wA, wB, retire count, -}
+          for (int n = __float_as_int(tb.z); n > 0; --n) retire();
+          accA = fmaf(tb.x, pw, accA);
+          accB = fmaf(tb.y, pw, accB);
+        }
+      }
+      while (cur < NMEL) retire();
+      if constexpr (LOG == 2) {
+        if (in_range) rows_fn.note_max(gr, mx);
       }
     }
   }
@@ -276,8 +305,10 @@ void launch(cbx_ctx* c, cudaStream_t st, const char* tag, const CUtensorMap& hi0
   if (rows <= 0) return;
   auto kern = dftmel_kernel<Rows, NB1, NMEL, LOG>;
   ensure_max_smem(kern, SMEM_BYTES);
+  const int ntiles = (rows + BM - 1) / BM;
+  const int grid = ntiles < sm_count() ? ntiles : sm_count();
   Scope sc(c->launches, st, tag, 2.0 * rows * (256 + NB1) * KTOT, 4.0 * rows * (160 + NMEL));   // ALGORITHMIC: one fp32 DFT per frame (the 3xTF32 split executes 3x this on the tensor pipe); one hop of PCM in, one feature row out
-  kern<<<(rows + BM - 1) / BM, 192, SMEM_BYTES, st>>>(hi0, lo0, hi1, lo1, pcm, rf, reinterpret_cast<const float4*>(bintab), out, rows);
+  kern<<<grid, THREADS, SMEM_BYTES, st>>>(hi0, lo0, hi1, lo1, pcm, rf, reinterpret_cast<const float4*>(bintab), out, rows, ntiles);
 }
 
 // second pass of the S3Tokenizer log-mel: floor at (clip max - 8), (x + 4) / 4, [T][128] -> [128][T] through a 32 x 32 tile

@@ -336,19 +336,38 @@ void split_dft(Packer& pk, const std::vector<double>& dd, int K, int first_bin, 
   pk.add(hi_slot, hi);
   pk.add(lo_slot, lo);
 }
-// Per DFT bin: the (at most two) mel filters it feeds, {w0, w1, bits(m0), bits(m1)} -- triangular banks are 2-sparse per bin.
+// Per DFT bin, for the epilogue's running mel accumulation: triangular banks are 2-sparse per bin and the two filters a bin
+// feeds are adjacent, so a thread keeps TWO accumulators in registers -- filter `cur` (A) and `cur + 1` (B) -- and walks the bins
+// in order.  Entry b = {wA, wB, bits(pre)}: first write out and retire `pre` finished filters (A -> out[cur], A = B, B = 0, ++cur),
+// then A += wA * power, B += wB * power.  Every filter receives its bins' contributions in ascending bin order starting from 0,
+// exactly like a per-filter sum.  (The previous table {w0, w1, m0, m1} drove read-modify-write accumulators in shared memory: a
+// dependent LDS -> FFMA -> STS chain per bin.)
 void bin_table(Packer& pk, const std::vector<float>& bank, int nmel, int nbank_bins, int first_bin, int nbins, const float** slot) {
   std::vector<float> t((size_t)4 * nbins, 0.f);
+  int cur = 0;
   for (int b = 0; b < nbins; ++b) {
     int m[2] = {0, 0}; float w[2] = {0.f, 0.f}; int cnt = 0;
     const int k = first_bin + b;
     if (b < nbins - 1 && k < nbank_bins)
       for (int mm = 0; mm < nmel; ++mm) {
         const float v = bank[(size_t)mm * nbank_bins + k];
-        if (v != 0.f && cnt < 2) { m[cnt] = mm; w[cnt] = v; ++cnt; }
+        if (v != 0.f) {
+          if (cnt < 2) { m[cnt] = mm; w[cnt] = v; }
+          ++cnt;
+        }
       }
-    t[4 * b] = w[0]; t[4 * b + 1] = w[1];
-    std::memcpy(&t[4 * b + 2], &m[0], 4); std::memcpy(&t[4 * b + 3], &m[1], 4);
+    int pre = 0;
+    float wA = 0.f, wB = 0.f;
+    bool ok = cnt <= 2 && (cnt < 2 || m[1] == m[0] + 1) && (cnt == 0 || m[0] >= cur);
+    if (ok && cnt > 0) {
+      if (cnt == 2 || m[0] > cur + 1) { pre = m[0] - cur; cur = m[0]; }      // a lone filter one ahead goes into B without retiring A
+      if (cnt == 2) { wA = w[0]; wB = w[1]; }
+      else if (m[0] == cur) wA = w[0];
+      else wB = w[0];
+    }
+    if (!ok) { fprintf(stderr, "libcbx: mel bank is not a chain of adjacent triangles at bin %d (cnt %d)\n", k, cnt); }
+    t[4 * b] = wA; t[4 * b + 1] = wB;
+    std::memcpy(&t[4 * b + 2], &pre, 4);
   }
   pk.add(slot, t);
 }
