@@ -282,6 +282,7 @@ int cbx_set_option(cbx_ctx* c, const char* key, int64_t v) {
   else if (k == "xw_bf16" && (v == 0 || v == 1)) c->xw_bf16 = v;
   else if (k == "fcm_fuse" && (v == 0 || v == 1)) c->fcm_fuse = v;
   else if (k == "transit_n256" && (v == 0 || v == 1)) c->transit_n256 = v;
+  else if (k == "dft_eo" && (v == 0 || v == 1)) c->dft_eo = v;
   else if (k == "lstm_gate_warps" && (v == 2 || v == 4)) c->lstm_gate_warps = v;
   else if (k == "overlap" && (v == 0 || v == 1)) c->overlap = v;
 #ifdef CBX_DEV_TOOLS   // timing experiments of tools/ (results are wrong while "probe" is set): not in the product library
@@ -307,6 +308,7 @@ int64_t cbx_get_option(const cbx_ctx* c, const char* key) {
   if (k == "xw_bf16") return c->xw_bf16;
   if (k == "fcm_fuse") return c->fcm_fuse;
   if (k == "transit_n256") return c->transit_n256;
+  if (k == "dft_eo") return c->dft_eo;
   if (k == "lstm_gate_warps") return c->lstm_gate_warps;
   if (k == "overlap") return c->overlap;
   if (k == "pdl") return c->pdl;

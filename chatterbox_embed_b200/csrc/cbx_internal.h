@@ -129,6 +129,10 @@ struct FrontendTables {
   const float *ve_bins, *k_bins;        // [200][4], [256][4]
   const float *s3_bins;                 // [200][4]
   CUtensorMap tm_ve_hi[2], tm_ve_lo[2], tm_k_hi, tm_k_lo;
+  // even/odd form of the VoiceEncoder / S3 DFT (frontend_tc.cu, dftmel_eo_kernel): rows [0, 208) = cos part of bins 1..199 against
+  // e[j] = s[j] + s[400-j], rows [208, 416) = -sin part against o[j] = s[j] - s[400-j], j = 1..200 in columns 0..199 of 224
+  const float *ve_eo_hi, *ve_eo_lo;     // [416][224]
+  CUtensorMap tm_ve_eo_hi, tm_ve_eo_lo;
 };
 // S3Gen prompt mel (promptmel_tc.cu), built on first use: Hann-folded 1920-point DFT rows of bins 1..639 split hi/lo, bin -> mel table
 struct PromptMelTables {
@@ -157,6 +161,7 @@ struct cbx_ctx {
   int64_t lstm_impl = 2;              // 1: DSMEM-push recurrence, 2: L2 multicast-TMA recurrence
   int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)
   int64_t lstm_gate_warps = 4;        // gate warps per TMEM lane quadrant of the recurrence kernel: 4 (16 gate warps) or 2 (8, round 1)
+  int64_t dft_eo = 1;                 // VoiceEncoder / S3 front-end DFT in its even / odd form (two K = 200 GEMMs); 0 = one K = 400 GEMM
   int64_t transit_n256 = 1;           // transit GEMMs with 128 x 256 output tiles
   int64_t fcm_fuse = 1;               // identity residual blocks of the FCM head as one fused kernel (fcm_block_tc.cu); 0 = two convolution kernels
   int64_t xw_bf16 = 0;                // 1 = the LSTM input projections are stored as bf16 (bf16 mode)

@@ -311,6 +311,225 @@ void launch(cbx_ctx* c, cudaStream_t st, const char* tag, const CUtensorMap& hi0
   kern<<<grid, THREADS, SMEM_BYTES, st>>>(hi0, lo0, hi1, lo1, pcm, rf, reinterpret_cast<const float4*>(bintab), out, rows, ntiles);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Even / odd form of the VoiceEncoder / S3Tokenizer DFT (tables: weights.cu, ve_eo_hi / ve_eo_lo).  The Hann window is
+// symmetric, so re X[k] needs only e[j] = s[j] + s[400-j] and im X[k] only o[j] = s[j] - s[400-j] (j = 1..200): two K = 200
+// GEMMs into two accumulator blocks (re: TMEM columns [0, 208), im: [208, 416)) instead of one K = 400 GEMM -- half the MMAs and
+// half the DFT-matrix bytes streamed from L2 per tile, which is what bounds the K loop.  Same persistent structure as
+// dftmel_kernel; the unit of the pipeline is a HALF block: hb = 2 kb + part, part 0 = (e, cos rows), part 1 = (o, sin rows).
+// Producer group 0 makes the e stages, group 1 the o stages (14 half blocks per tile: the stage of a half block is its part).
+namespace eo {
+constexpr int NHB = 14;                         // 7 K blocks of 32 columns (200 valid) x {re, im}
+constexpr int NROWS = 208;                      // 199 bins + padding to a legal UMMA N
+constexpr int SBE = 5;                          // B slots
+constexpr int BE_BYTES = 27 * 1024;             // 208 x 128 B, rounded up to the 1 KB swizzle atom
+constexpr int SMEM_BYTES = SA * 2 * A_BYTES + SBE * BE_BYTES + 1024 + 2 * 128 * 16 + MAX_BINS * 16 + 256;
+}  // namespace eo
+
+template <class Rows, int NMEL, int LOG>
+__global__ void __launch_bounds__(THREADS, 1)
+dftmel_eo_kernel(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo,
+                 const float* __restrict__ pcm, Rows rows_fn, const float4* __restrict__ bintab, float* __restrict__ out, int rows, int ntiles) {
+  using namespace eo;
+  constexpr int NBINS = 200;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                   // [2 parts][hi | lo][128 x 128 B]
+  uint8_t* sB = smem + SA * 2 * A_BYTES;                // [SBE][208 x 128 B]
+  RowDesc* rdesc = reinterpret_cast<RowDesc*>(sB + SBE * BE_BYTES);   // [2][128]
+  float4* sbins = reinterpret_cast<float4*>(rdesc + 2 * BM);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbins + MAX_BINS);
+  uint64_t* a_full = bars;                 // [2] 128 producer arrivals
+  uint64_t* a_empty = bars + SA;           // [2] MMA commit
+  uint64_t* b_full = bars + 2 * SA;        // [SBE] TMA bytes
+  uint64_t* b_empty = b_full + SBE;        // [SBE] MMA commit
+  uint64_t* accum = b_empty + SBE;
+  uint64_t* drained = accum + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(drained + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmHi); tma_prefetch_desc(&tmLo);
+    for (int s = 0; s < SA; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < SBE; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(accum, 1);
+    mbar_init(drained, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < NBINS; i += THREADS) sbins[i] = __ldg(bintab + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        for (int hb = 0; hb < NHB; ++hb)
+          for (int q = 0; q < 2; ++q, ++it) {
+            const int s = it % SBE, ph = (it / SBE) & 1;
+            mbar_wait(&b_empty[s], ph ^ 1);
+            mbar_expect_tx(&b_full[s], NROWS * BK * 4);
+            tma_load_2d(sB + s * BE_BYTES, q ? &tmLo : &tmHi, &b_full[s], (hb >> 1) * BK, (hb & 1) * NROWS);
+          }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_tf32(BM, NROWS);
+    int it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      mbar_wait(drained, (ti & 1) ^ 1);
+      tc_fence_after();
+      for (int hb = 0; hb < NHB; ++hb) {
+        const int sa = hb & 1, pa = (ti * (NHB / 2) + (hb >> 1)) & 1;      // stage = part; its use count = ti * 7 + kb
+        const int kb = hb >> 1;
+        mbar_wait(&a_full[sa], pa);
+        tc_fence_after();
+        const uint64_t ahi = make_desc_sw128(smem_u32(sA + sa * 2 * A_BYTES));
+        const uint64_t alo = make_desc_sw128(smem_u32(sA + sa * 2 * A_BYTES + A_BYTES));
+        const int ksteps = (kb == NHB / 2 - 1) ? (NBINS - (NHB / 2 - 1) * BK) / UMMA_K : BK / UMMA_K;     // 200 = 6 x 32 + 8
+        const uint32_t d = tmem_base + (uint32_t)(hb & 1) * NROWS;
+        for (int q = 0; q < 2; ++q, ++it) {
+          const int s = it % SBE, ph = (it / SBE) & 1;
+          mbar_wait(&b_full[s], ph);
+          tc_fence_after();
+          const uint64_t bd = make_desc_sw128(smem_u32(sB + s * BE_BYTES));
+          if (elect_one()) {
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ko = (uint64_t)(k * UMMA_K * 4 >> 4);
+              if (q == 0) {             // B_hi: A_hi.B_hi + A_lo.B_hi
+                umma_tf32(d, ahi + ko, bd + ko, idesc, (kb | k) != 0);
+                umma_tf32(d, alo + ko, bd + ko, idesc, 1);
+              } else {                  // B_lo: A_hi.B_lo
+                umma_tf32(d, ahi + ko, bd + ko, idesc, 1);
+              }
+            }
+            umma_commit(&b_empty[s]);
+            if (q == 1) {
+              umma_commit(&a_empty[sa]);
+              if (hb == NHB - 1) umma_commit(accum);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < 2 + 4 * PGRP) {
+    // ===== frame producers: group 0 -> e = s[j] + s[400 - j], group 1 -> o = s[j] - s[400 - j]; column c of a stage is j = 32 kb + c + 1
+    const int g = (warp - 2) >> 2, wq = (warp - 2) & 3;
+    const int r_own = (threadIdx.x - 64) & 127;
+    const float sgn = g == 0 ? 1.f : -1.f;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int m0 = tile * BM;
+      RowDesc* rd = rdesc + (ti & 1) * BM;
+      if (g == 0) rd[r_own] = (m0 + r_own < rows) ? rows_fn(m0 + r_own) : RowDesc{0, 0, 0};
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int kb = 0; kb < NHB / 2; ++kb) {
+        const int pa = (ti * (NHB / 2) + kb) & 1;
+        const int j = kb * BK + lane + 1;                 // 1 .. 224; valid up to 200
+        float v[32];
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          const RowDesc d = rd[wq * 32 + rr];
+          int i1 = d.start + j, i2 = d.start + KTOT - j;
+          if (i1 < 0) i1 = -i1; else if (i1 >= d.n) i1 = 2 * (d.n - 1) - i1;
+          if (i2 < 0) i2 = -i2; else if (i2 >= d.n) i2 = 2 * (d.n - 1) - i2;
+          const bool on = d.n > 0 && j <= KTOT / 2;
+          const float a = on ? __ldg(pcm + d.base + i1) : 0.f;
+          const float b = (on && j < KTOT / 2) ? __ldg(pcm + d.base + i2) : 0.f;      // j = 200: the centre sample stands alone
+          v[rr] = (g == 1 && j == KTOT / 2) ? 0.f : fmaf(sgn, b, a);
+        }
+        mbar_wait(&a_empty[g], pa ^ 1);
+        uint8_t* hi = sA + g * 2 * A_BYTES;
+        uint8_t* lo = hi + A_BYTES;
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          const int r = wq * 32 + rr;
+          const float vh = to_tf32(v[rr]);
+          const float vl = to_tf32(v[rr] - vh);
+          const uint32_t o = r * 128 + ((((uint32_t)lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4;
+          *reinterpret_cast<float*>(hi + o) = vh;
+          *reinterpret_cast<float*>(lo + o) = vl;
+        }
+        fence_proxy_async();
+        mbar_arrive(&a_full[g]);
+      }
+    }
+  } else {
+    // ===== epilogue: thread = frame row; re of bin b in column b, im in column 208 + b
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int gr = tile * BM + row;
+      const bool in_range = gr < rows;
+      const bool live = in_range && rows_fn.live(gr);
+      float* orow = out + (size_t)(in_range ? gr : 0) * NMEL;
+      float accA = 0.f, accB = 0.f, mx = -INFINITY;
+      int cur = 0;
+      auto retire = [&]() {
+        float val = accA;
+        if (LOG == 1) val = logf(fmaxf(val, 1.1920928955078125e-07f));
+        if (LOG == 2) { val = log10f(fmaxf(val, 1e-10f)); mx = fmaxf(mx, val); }
+        if (in_range) orow[cur] = live ? val : 0.f;
+        accA = accB; accB = 0.f; ++cur;
+      };
+      mbar_wait(accum, ti & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < NBINS / 8; ++c) {
+        float vr[8], vi[8];
+        {
+          uint32_t* a = reinterpret_cast<uint32_t*>(vr);
+          uint32_t* b = reinterpret_cast<uint32_t*>(vi);
+          const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 8);
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]) : "r"(t0) : "memory");
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                       : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]) : "r"(t0 + NROWS) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        if (c == NBINS / 8 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(drained);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float pw = fmaf(vr[i], vr[i], vi[i] * vi[i]);
+          const float4 tb = sbins[c * 8 + i];
+          for (int n = __float_as_int(tb.z); n > 0; --n) retire();
+          accA = fmaf(tb.x, pw, accA);
+          accB = fmaf(tb.y, pw, accB);
+        }
+      }
+      while (cur < NMEL) retire();
+      if constexpr (LOG == 2) {
+        if (in_range) rows_fn.note_max(gr, mx);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+template <class Rows, int NMEL, int LOG>
+void launch_eo(cbx_ctx* c, cudaStream_t st, const char* tag, const CUtensorMap& hi, const CUtensorMap& lo, const float* pcm, Rows rf,
+               const float* bintab, float* out, int rows) {
+  if (rows <= 0) return;
+  auto kern = dftmel_eo_kernel<Rows, NMEL, LOG>;
+  ensure_max_smem(kern, eo::SMEM_BYTES);
+  const int ntiles = (rows + BM - 1) / BM;
+  const int grid = ntiles < sm_count() ? ntiles : sm_count();
+  // ALGORITHMIC flops: the fp32 DFT of a real 400-sample frame as the reference computes it (2 x 400 x 400 per frame), so that the
+  // figure stays comparable across rounds; this kernel executes 3 x 2 x 2 x 200 x 208 per frame on the tensor pipe
+  Scope sc(c->launches, st, tag, 2.0 * rows * 400 * KTOT, 4.0 * rows * (160 + NMEL));
+  kern<<<grid, THREADS, eo::SMEM_BYTES, st>>>(hi, lo, pcm, rf, reinterpret_cast<const float4*>(bintab), out, rows, ntiles);
+}
+
 // second pass of the S3Tokenizer log-mel: floor at (clip max - 8), (x + 4) / 4, [T][128] -> [128][T] through a 32 x 32 tile
 __global__ void __launch_bounds__(256) s3_finish_kernel(const float* __restrict__ tmp, const S3Clip* __restrict__ clips, const float* __restrict__ cmax,
                                                         float* __restrict__ out) {
@@ -336,7 +555,11 @@ __global__ void __launch_bounds__(256) s3_finish_kernel(const float* __restrict_
 
 void run_ve_mel_tc(cbx_ctx* c, const float* pcm, const VeChunk& ch, cudaStream_t st) {
   const FrontendTables& F = c->ft;
-  fe::launch<fe::VeRows, 2 * kVeTcBins - 256, kVeMels, 0>(c, st, "ve_dftmel_tc_kernel", F.tm_ve_hi[0], F.tm_ve_lo[0], F.tm_ve_hi[1], F.tm_ve_lo[1],
+  if (c->dft_eo)
+    fe::launch_eo<fe::VeRows, kVeMels, 0>(c, st, "ve_dftmel_tc_kernel", F.tm_ve_eo_hi, F.tm_ve_eo_lo, pcm, fe::VeRows{ch.plan, ch.dyn, ch.mel_row_clip},
+                                          F.ve_bins, ch.mel, ch.mel_rows);
+  else
+    fe::launch<fe::VeRows, 2 * kVeTcBins - 256, kVeMels, 0>(c, st, "ve_dftmel_tc_kernel", F.tm_ve_hi[0], F.tm_ve_lo[0], F.tm_ve_hi[1], F.tm_ve_lo[1],
                                                             pcm, fe::VeRows{ch.plan, ch.dyn, ch.mel_row_clip}, F.ve_bins, ch.mel, ch.mel_rows);
 }
 
@@ -395,8 +618,12 @@ int cbx_s3_log_mel(cbx_ctx* c, const float* pcm_dev, const int64_t* offsets_host
   float* cmax = reinterpret_cast<float*>(dclips + n_clips);
   CBX_CUDA_OK(c, cudaMemcpyAsync(dclips, host.data(), table_bytes, cudaMemcpyHostToDevice, st));
   const FrontendTables& F = c->ft;
-  fe::launch<fe::S3Rows, 2 * kVeTcBins - 256, kS3Mels, 2>(c, st, "s3_dftmel_tc_kernel", F.tm_ve_hi[0], F.tm_ve_lo[0], F.tm_ve_hi[1], F.tm_ve_lo[1],
-                                                          pcm_dev, fe::S3Rows{dclips, n_clips, cmax}, F.s3_bins, c->s3_tmp, (int)rows);
+  if (c->dft_eo)
+    fe::launch_eo<fe::S3Rows, kS3Mels, 2>(c, st, "s3_dftmel_tc_kernel", F.tm_ve_eo_hi, F.tm_ve_eo_lo, pcm_dev, fe::S3Rows{dclips, n_clips, cmax}, F.s3_bins,
+                                          c->s3_tmp, (int)rows);
+  else
+    fe::launch<fe::S3Rows, 2 * kVeTcBins - 256, kS3Mels, 2>(c, st, "s3_dftmel_tc_kernel", F.tm_ve_hi[0], F.tm_ve_lo[0], F.tm_ve_hi[1], F.tm_ve_lo[1],
+                                                            pcm_dev, fe::S3Rows{dclips, n_clips, cmax}, F.s3_bins, c->s3_tmp, (int)rows);
   for (int z0 = 0; z0 < n_clips; z0 += 65535) {
     const int nz = std::min(65535, n_clips - z0);
     Scope sc(c->launches, st, "s3_finish_kernel", 0.0, 8.0 * rows * kS3Mels * nz / n_clips);

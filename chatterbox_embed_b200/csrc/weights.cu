@@ -391,6 +391,30 @@ int build_frontend_tables(cbx_ctx* c) {
     for (size_t i = 0; i < d.size(); ++i) d[i] = (float)dd[i];
     pk.add(&F.ve_dft, d);
     split_dft(pk, dd, kVeNfft, 1, kVeTcBins, &F.ve_dft_hi, &F.ve_dft_lo);
+    {
+      // Even / odd form.  The periodic Hann window is symmetric about j = 200 (w[j] = w[400 - j], w[0] = 0, w[200] = 1), so
+      //   re X[k] = sum_{j=1..199} w[j] cos(2 pi k j / 400) (s[j] + s[400-j])  +  (-1)^k s[200]
+      //   im X[k] = - sum_{j=1..199} w[j] sin(2 pi k j / 400) (s[j] - s[400-j])
+      // : two K = 200 products instead of one K = 400 product -- half the MMAs, half the DFT-matrix bytes per tile.
+      // Column c of the matrix is j = c + 1 (c = 0..199; c = 199 is j = 200: e[200] = s[200], o[200] = 0), padded to 224.
+      constexpr int EO_ROWS = 208, EO_K = 224;
+      std::vector<float> hi((size_t)2 * EO_ROWS * EO_K, 0.f), lo((size_t)2 * EO_ROWS * EO_K, 0.f);
+      for (int b = 0; b < kVeTcBins - 1; ++b) {
+        const int k = 1 + b;
+        for (int c = 0; c < 200; ++c) {
+          const int j = c + 1;
+          const double wj = 0.5 - 0.5 * std::cos(2.0 * PI * j / kVeNfft);
+          const double ang = 2.0 * PI * (double)((k * j) % kVeNfft) / kVeNfft;
+          const double vr = j < 200 ? wj * std::cos(ang) : ((k & 1) ? -1.0 : 1.0);
+          const double vi = j < 200 ? -wj * std::sin(ang) : 0.0;
+          const float hr = round_tf32((float)vr), hi_i = round_tf32((float)vi);
+          hi[(size_t)b * EO_K + c] = hr;                       lo[(size_t)b * EO_K + c] = round_tf32((float)(vr - (double)hr));
+          hi[(size_t)(EO_ROWS + b) * EO_K + c] = hi_i;          lo[(size_t)(EO_ROWS + b) * EO_K + c] = round_tf32((float)(vi - (double)hi_i));
+        }
+      }
+      pk.add(&F.ve_eo_hi, hi);
+      pk.add(&F.ve_eo_lo, lo);
+    }
     // librosa.filters.mel(sr=16000,n_fft=400,n_mels,fmin=0,fmax=8000): Slaney scale + area norm (melspec.py:11-16)
     auto slaney_bank = [](int nmels) {
       std::vector<double> edges(nmels + 2);
@@ -461,6 +485,8 @@ int build_frontend_tables(cbx_ctx* c) {
   F.tm_ve_lo[0] = tc::make_map_2d(F.ve_dft_lo, 2 * kVeTcBins, kVeNfft, kVeNfft, 256, false);
   F.tm_ve_hi[1] = tc::make_map_2d(F.ve_dft_hi, 2 * kVeTcBins, kVeNfft, kVeNfft, 2 * kVeTcBins - 256, false);
   F.tm_ve_lo[1] = tc::make_map_2d(F.ve_dft_lo, 2 * kVeTcBins, kVeNfft, kVeNfft, 2 * kVeTcBins - 256, false);
+  F.tm_ve_eo_hi = tc::make_map_2d(F.ve_eo_hi, 416, 224, 224, 208, false);
+  F.tm_ve_eo_lo = tc::make_map_2d(F.ve_eo_lo, 416, 224, 224, 208, false);
   F.tm_k_hi = tc::make_map_2d(F.k_dft_hi, 2 * kKTcBins, kKWin, kKWin, 256, false);
   F.tm_k_lo = tc::make_map_2d(F.k_dft_lo, 2 * kKTcBins, kKWin, kKWin, 256, false);
   return CBX_OK;
