@@ -226,6 +226,7 @@ int cbx_create(int device, cbx_ctx** out) {
   cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&c->ev_dtdnn, cudaEventDisableTiming);
   cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking);
   for (auto& s : c->slot) {
@@ -262,6 +263,7 @@ void cbx_destroy(cbx_ctx* c) {
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->ev_order) cudaEventDestroy(c->ev_order);
+  if (c->ev_dtdnn) cudaEventDestroy(c->ev_dtdnn);
   if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
   if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
   delete c;
@@ -283,6 +285,7 @@ int cbx_set_option(cbx_ctx* c, const char* key, int64_t v) {
   else if (k == "fcm_fuse" && (v == 0 || v == 1)) c->fcm_fuse = v;
   else if (k == "transit_n256" && (v == 0 || v == 1)) c->transit_n256 = v;
   else if (k == "dft_eo" && (v == 0 || v == 1)) c->dft_eo = v;
+  else if (k == "lstm_late" && (v == 0 || v == 1)) c->lstm_late = v;
   else if (k == "lstm_gate_warps" && (v == 2 || v == 4)) c->lstm_gate_warps = v;
   else if (k == "overlap" && (v == 0 || v == 1)) c->overlap = v;
 #ifdef CBX_DEV_TOOLS   // timing experiments of tools/ (results are wrong while "probe" is set): not in the product library
@@ -309,6 +312,7 @@ int64_t cbx_get_option(const cbx_ctx* c, const char* key) {
   if (k == "fcm_fuse") return c->fcm_fuse;
   if (k == "transit_n256") return c->transit_n256;
   if (k == "dft_eo") return c->dft_eo;
+  if (k == "lstm_late") return c->lstm_late;
   if (k == "lstm_gate_warps") return c->lstm_gate_warps;
   if (k == "overlap") return c->overlap;
   if (k == "pdl") return c->pdl;
@@ -371,32 +375,48 @@ static int embed_core(cbx_ctx* c, const float* pcm, const float* feats, const in
     CBX_CUDA_OK(c, cudaStreamWaitEvent(sx, c->ev_fork, 0));
   }
   const bool no_trim = (flags & CBX_NO_TRIM) != 0 || !(trim_top_db > 0.f);
+  // Where the recurrence runs.  The LSTM kernel occupies 112 SMs with one 226 KB CTA each; whatever shares the GPU with it only gets
+  // the other 36.  The FCM head / front-end kernels of the CAMPPlus chain are persistent one-CTA-per-SM kernels: launched beside the
+  // recurrence, 112 of their 148 CTAs cannot start until it ends.  The D-TDNN GEMMs are ~1000 small CTAs and fill any free SM.  So with
+  // one chunk per encoder the CAMPPlus chain is enqueued first, records an event when it enters the D-TDNN phase, and the VoiceEncoder
+  // stream waits for that event between its input-projection GEMM and the first recurrence launch (scheduling only: same results).
+  const bool late = sx != st && c->lstm_late && c->mode == 1 && cs.ve.size() == 1 && cs.xv.size() == 1;
+  c->xv_mark_dtdnn = late; c->ve_wait_dtdnn = late;
+  auto run_ve = [&]() -> int {
   for (auto& r : cs.ve) {
-    VeLayout L = plan_ve(b, r.first, r.second);
-    Carver cv(ws, ve_region);
-    VeChunk ch = carve_ve(cv, L, c);
-    CBX_CUDA_OK(c, cudaMemcpyAsync(ch.plan, L.plan.data(), sizeof(ClipPlan) * L.plan.size(), cudaMemcpyHostToDevice, st));
-    run_ve_chunk(c, pcm, ch, trim_top_db, no_trim, step, min_cov, ve_out, status, st);
-    for (size_t i = 0; i < L.plan.size(); ++i) {
-      ClipPlan& lp = c->last_plan[r.first + i];
-      lp.mel_row = L.plan[i].mel_row; lp.mel_rows = L.plan[i].mel_rows; lp.slot0 = L.plan[i].slot0; lp.slots = L.plan[i].slots;
+      VeLayout L = plan_ve(b, r.first, r.second);
+      Carver cv(ws, ve_region);
+      VeChunk ch = carve_ve(cv, L, c);
+      CBX_CUDA_OK(c, cudaMemcpyAsync(ch.plan, L.plan.data(), sizeof(ClipPlan) * L.plan.size(), cudaMemcpyHostToDevice, st));
+      run_ve_chunk(c, pcm, ch, trim_top_db, no_trim, step, min_cov, ve_out, status, st);
+      for (size_t i = 0; i < L.plan.size(); ++i) {
+        ClipPlan& lp = c->last_plan[r.first + i];
+        lp.mel_row = L.plan[i].mel_row; lp.mel_rows = L.plan[i].mel_rows; lp.slot0 = L.plan[i].slot0; lp.slots = L.plan[i].slots;
+      }
+      // the host plan vector dies at the end of this iteration; the async copy above reads pageable memory, which the
+      // runtime stages before returning, so this is safe
     }
-    // the host plan vector dies at the end of this iteration; the async copy above reads pageable memory, which the
-    // runtime stages before returning, so this is safe
-  }
+    return CBX_OK;
+  };
+  auto run_xv = [&]() -> int {
   for (auto& r : cs.xv) {
-    XvLayout L = plan_xv(b, r.first, r.second, c->fcm_chunk_rows);
-    // taps are byte offsets from the start of the caller's workspace
-    Carver cv_abs(ws, ws_bytes); cv_abs.off = ve_region;
-    XvChunk ch = carve_xv(cv_abs, L, c, c->cat_bf16 != 0);
-    ch.hplan = L.plan.data();
-    CBX_CUDA_OK(c, cudaMemcpyAsync(ch.plan, L.plan.data(), sizeof(ClipPlan) * L.plan.size(), cudaMemcpyHostToDevice, sx));
-    run_xv_chunk(c, pcm, ch, xv_out, status, sx, feats, feat_off);
-    for (size_t i = 0; i < L.plan.size(); ++i) {
-      ClipPlan& lp = c->last_plan[r.first + i];
-      lp.fb_row = L.plan[i].fb_row; lp.td_row = L.plan[i].td_row; lp.xv_frames = L.plan[i].xv_frames; lp.xv_tdnn = L.plan[i].xv_tdnn;
+      XvLayout L = plan_xv(b, r.first, r.second, c->fcm_chunk_rows);
+      // taps are byte offsets from the start of the caller's workspace
+      Carver cv_abs(ws, ws_bytes); cv_abs.off = ve_region;
+      XvChunk ch = carve_xv(cv_abs, L, c, c->cat_bf16 != 0);
+      ch.hplan = L.plan.data();
+      CBX_CUDA_OK(c, cudaMemcpyAsync(ch.plan, L.plan.data(), sizeof(ClipPlan) * L.plan.size(), cudaMemcpyHostToDevice, sx));
+      run_xv_chunk(c, pcm, ch, xv_out, status, sx, feats, feat_off);
+      for (size_t i = 0; i < L.plan.size(); ++i) {
+        ClipPlan& lp = c->last_plan[r.first + i];
+        lp.fb_row = L.plan[i].fb_row; lp.td_row = L.plan[i].td_row; lp.xv_frames = L.plan[i].xv_frames; lp.xv_tdnn = L.plan[i].xv_tdnn;
+      }
     }
-  }
+    return CBX_OK;
+  };
+  if (late) { if ((rc = run_xv())) return rc; if ((rc = run_ve())) return rc; }
+  else { if ((rc = run_ve())) return rc; if ((rc = run_xv())) return rc; }
+  c->xv_mark_dtdnn = false; c->ve_wait_dtdnn = false;
   if (sx != st) {     // join: everything after this call on the caller's stream also follows the CAMPPlus work
     CBX_CUDA_OK(c, cudaEventRecord(c->ev_join, sx));
     CBX_CUDA_OK(c, cudaStreamWaitEvent(st, c->ev_join, 0));

@@ -161,6 +161,7 @@ struct cbx_ctx {
   int64_t lstm_impl = 2;              // 1: DSMEM-push recurrence, 2: L2 multicast-TMA recurrence
   int64_t lstm_dbg = 0;               // timing experiments (lstm_tc.cu)
   int64_t lstm_gate_warps = 4;        // gate warps per TMEM lane quadrant of the recurrence kernel: 4 (16 gate warps) or 2 (8, round 1)
+  int64_t lstm_late = 1;              // with both encoders on two streams: start the recurrence when CAMPPlus enters its D-TDNN phase
   int64_t dft_eo = 1;                 // VoiceEncoder / S3 front-end DFT in its even / odd form (two K = 200 GEMMs); 0 = one K = 400 GEMM
   int64_t transit_n256 = 1;           // transit GEMMs with 128 x 256 output tiles
   int64_t fcm_fuse = 1;               // identity residual blocks of the FCM head as one fused kernel (fcm_block_tc.cu); 0 = two convolution kernels
@@ -197,6 +198,9 @@ struct cbx_ctx {
   // single buffers.  Every stream-ordered entry point calls cbx::enter_stream(): when the caller's stream differs from the
   // one the previous call used, the new stream first waits for everything the previous stream had been given, so two calls on
   // different streams can never overlap on those buffers (they serialise instead of corrupting each other).
+  // recurrence placement (api.cu, embed_core): event recorded by the CAMPPlus chain when it enters the D-TDNN phase; the two flags are
+  // set for the duration of one call
+  cudaEvent_t ev_dtdnn = nullptr; bool xv_mark_dtdnn = false, ve_wait_dtdnn = false;
   cudaStream_t last_stream = nullptr; bool last_stream_valid = false;
   cudaEvent_t ev_order = nullptr;
   // last-run bookkeeping for the stage taps

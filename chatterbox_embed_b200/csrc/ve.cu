@@ -290,6 +290,8 @@ void run_ve_lstm(cbx_ctx* c, const VeChunk& ch, cudaStream_t st) {
       // L2-exchange recurrence: hseq / xw of layers 1, 2 in the tiled time-major row order over whole 224-partial tiles
       const int prow = lstm_padded_slots(ch.slots) * kVePartial;
       const size_t hl = (size_t)ch.slots * kVeHidden;
+      // two-stream overlap: hold the recurrence back until the CAMPPlus chain is in its D-TDNN phase (see cbx_embed)
+      if (c->ve_wait_dtdnn) cudaStreamWaitEvent(st, c->ev_dtdnn, 0);
       run_lstm_rec_tc2(c, ch.xw0, x16, ch.slot_row, W.whh_p[0], ch.hseq, ch.hlast, ch.slots, st);
       for (int l = 1; l < 3; ++l) {
         CUtensorMap tmH = tc::make_map_2d(ch.hseq, prow, kVeHidden, kVeHidden, tc::BM, true);

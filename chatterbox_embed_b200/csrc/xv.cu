@@ -521,6 +521,9 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     sgemm(L, st, "tdnn_gemm", M, kTdnnC, W.tdnn.K, TdnnA{ch.fcm_out, ch.fb_rows}, W.tdnn.w, W.tdnn.K, BiasReluMaskEpi{ch.cat1, 512, W.tdnn.bias, ch.td_row_clip});
   }
 
+  // the D-TDNN phase starts here: its GEMMs are many small CTAs (two per SM, 75 KB of shared memory each) that fill whatever SMs are
+  // free -- this is the phase the VoiceEncoder's recurrence (112 SMs, one 226 KB CTA each) should share the GPU with (api.cu)
+  if (c->xv_mark_dtdnn) cudaEventRecord(c->ev_dtdnn, st);
   if (tcm && ch.segs > 0) cudaMemsetAsync(ch.seg_sum, 0, sizeof(unsigned long long) * (size_t)ch.segs * kBnC, st);
   static const int kLayers[3] = {12, 24, 16};
   static const int kDil[3] = {1, 2, 2};

@@ -35,7 +35,7 @@ def run(flags):
 
 
 BOTH, VE, XV = _lib.DO_VE | _lib.DO_XV, _lib.DO_VE, _lib.DO_XV
-DEFAULTS = {"overlap": 1, "pdl": 1, "probe": 0, "lstm_gate_warps": 4, "fcm_fuse": 1, "mode": 1, "transit_n256": 1}
+DEFAULTS = {"overlap": 1, "pdl": 1, "probe": 0, "lstm_gate_warps": 4, "fcm_fuse": 1, "mode": 1, "transit_n256": 1, "lstm_late": 1, "dft_eo": 1}
 rows = []
 for name, flags, opts in (("both encoders (the bench step)", BOTH, {}), ("VoiceEncoder alone", VE, {}), ("CAMPPlus alone", XV, {}),
                           ("both, one stream (overlap 0)", BOTH, {"overlap": 0}), ("CAMPPlus alone, no dependent launch (pdl 0)", XV, {"pdl": 0}),
@@ -45,6 +45,9 @@ for name, flags, opts in (("both encoders (the bench step)", BOTH, {}), ("VoiceE
                           ("CAMPPlus alone, fcm_fuse 0", XV, {"fcm_fuse": 0}),
                           ("CAMPPlus alone, transit GEMMs with 128-wide tiles (transit_n256 0)", XV, {"transit_n256": 0}),
                           ("CAMPPlus alone again", XV, {}),
+                          ("both, recurrence beside the FCM phase (lstm_late 0)", BOTH, {"lstm_late": 0}),
+                          ("both encoders (lstm_late 1 again)", BOTH, {}),
+                          ("both, lstm_late 0 again", BOTH, {"lstm_late": 0}),
                           ("both, bf16 mode (mode 2)", BOTH, {"mode": 2}),
                           ("both encoders again (drift check)", BOTH, {}),
                           ("CAMPPlus alone, CAM gate kernel removed (probe 1; dev build only)", XV, {"probe": 1})):
