@@ -32,6 +32,7 @@ for f in $FAMS; do
     fcm_conv)   run fcm_conv fcm_conv_kernel 85 2 ;;
     fcm_block)  run fcm_block fcm_block_kernel 24 2 ;;
     dftmel)     run dftmel dftmel 6 2 ;;
+    cmn)        run cmn cmn_mean_kernel 3 1 ;;
     pgemm)      run pgemm pgemm_kernel 10 2 ;;
     tdnn)       run tdnn ^tgemm_kernel 3 1 ;;
     stats_pool) run stats_pool stats_pool_kernel 3 1 ;;
