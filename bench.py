@@ -384,6 +384,7 @@ def main():
     ap.add_argument("--ragged", action="store_true", help="--config 4: 3-30 s clips instead of 10 s")
     ap.add_argument("--opt", action="append", default=[], help="libcbx option key=value (cbx_set_option)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sustain", type=float, default=3.0, help="seconds of back-to-back steps for the `sustained` object of the line (0 = skip)")
     ap.add_argument("--no-job", action="store_true", help="N > 1: skip the 1e5-clip voice-bank job that is attached to the line")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -548,6 +549,21 @@ def main():
         if k in EXEC_FACTOR and tfl:
             kernels[k]["exec_tflops"] = tfl * EXEC_FACTOR[k]
 
+    # ---- the same step repeated for >= --sustain seconds (AFTER every other measurement, so that it does not pre-heat them): the
+    # figure a long job sees once the clocks have settled under the power cap
+    sustained = None
+    if args.sustain > 0 and args.config == 2:
+        clk2 = ClockSampler(local).start()
+        k_s = max(K, int(args.sustain * 1e3 / (ms / K)) + 1)
+        for _ in range(2):
+            step_device()
+        ts0 = time.time()
+        ms_s, _ = timed(step_device, k_s)
+        ts1 = time.time()
+        sustained = {"value": world * n_clips * k_s / (ms_s / 1e3), "unit": "clips/s", "steps": k_s, "seconds": ms_s / 1e3,
+                     "ms_per_step": ms_s / k_s, "clocks": clk2.summary(ts0, ts1)}
+        clk2.stop()
+
     # ---- N > 1: BASELINE configs[3] as well -- the 1e5-clip voice-bank job (strong scaling) on the same ranks ------------------
     job = None
     if world > 1 and args.config == 2 and not args.no_job:
@@ -588,7 +604,7 @@ def main():
                     "api": "SpeakerEmbedder.embed_stream (cbx_embed_host_submit/_wait, two batches in flight)"
                            + ("; one all_gather_into_tensor of the embeddings per step inside the timed region" if world > 1 else ""),
                     "single_call_value": e2e_sync_value, "single_call_api": "cbx_embed_host (copy, compute, copy back, sync)"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity, "job": job,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": parity, "job": job, "sustained": sustained,
             "tf32_peak_tflops": tf32, "timed_region_s": ms / 1e3,
             "algorithmic_tflops": (value * FLOPS_PER_CLIP / 1e12) if args.config == 2 else None, "kernels": kernels,
         }

@@ -5,11 +5,11 @@
 TAG=${1:-r02}; shift
 FAMS=${@:-"bottleneck transit lstm_rec fcm_conv fcm_block dftmel pgemm tdnn stats_pool trim local_conv cam_gate conv1"}
 OUT=gpurun_out/$TAG; mkdir -p $OUT
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --sustain 0"
 # 1. sustained line (>= 300 steps, ~6 s timed) with an nvidia-smi trace beside it
 nvidia-smi --query-gpu=timestamp,clocks.sm,clocks.mem,power.draw,temperature.gpu,clocks_event_reasons.sw_power_cap,clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_thermal_slowdown --format=csv -lms 100 > $OUT/clock_trace.csv &
 SMI=$!
-python bench.py --steps 300 --warmup 5 --no-cpu-baseline > $OUT/bench_sustained.json 2> $OUT/bench_sustained.err; echo "sustained rc=$?"
+python bench.py --steps 300 --warmup 5 --no-cpu-baseline --sustain 0 > $OUT/bench_sustained.json 2> $OUT/bench_sustained.err; echo "sustained rc=$?"
 kill $SMI
 python bench.py --steps 10 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
 $CMD > $OUT/plain.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/plain.log; exit 1; }
