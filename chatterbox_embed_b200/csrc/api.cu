@@ -91,7 +91,7 @@ XvLayout plan_xv(const Batch& b, int c0, int c1, int64_t fcm_chunk_rows) {
   return L;
 }
 
-XvChunk carve_xv(Carver& cv, const XvLayout& L, cbx_ctx* c, bool cat_bf16) {
+XvChunk carve_xv(Carver& cv, const XvLayout& L, cbx_ctx* c, bool cat_bf16, bool u_bf16) {
   XvChunk ch{};
   ch.n_clips = (int)L.plan.size(); ch.fb_rows = L.fb_rows; ch.td_rows = L.td_rows; ch.segs = L.segs; ch.fcm_rows = L.fcm_rows;
   ch.plan = cv.take<ClipPlan>(ch.n_clips);
@@ -118,6 +118,7 @@ XvChunk carve_xv(Carver& cv, const XvLayout& L, cbx_ctx* c, bool cat_bf16) {
   ch.cat2h = cat_bf16 ? cv.take<uint16_t>((int64_t)L.td_rows * 1024) : nullptr;
   ch.cat3h = cat_bf16 ? cv.take<uint16_t>((int64_t)L.td_rows * 1024) : nullptr;
   ch.u = cv.take<float>((int64_t)L.td_rows * kBnC);
+  ch.u16 = u_bf16 ? cv.take<uint16_t>((int64_t)L.td_rows * kBnC) : nullptr;
   ch.tr3 = cv.take<float>((int64_t)L.td_rows * kStatsC);
   ch.seg_sum = cv.take<float>((int64_t)std::max(L.segs, 1) * kBnC * 2);      // fp32 in the strict mode, 64-bit fixed point in the tensor-core mode
   ch.gate = cv.take<float>((int64_t)std::max(L.segs, 1) * kGrowth);
@@ -187,7 +188,7 @@ int64_t workspace_bytes_for(cbx_ctx* c, const Batch& b, int flags) {
   ChunkSets s = make_chunks(c, b, flags);
   int64_t ve_max = 0, xv_max = 0;
   for (auto& r : s.ve) { Carver cv(nullptr, 0); carve_ve(cv, plan_ve(b, r.first, r.second), nullptr); ve_max = std::max(ve_max, cv.off); }
-  for (auto& r : s.xv) { Carver cv(nullptr, 0); carve_xv(cv, plan_xv(b, r.first, r.second, c->fcm_chunk_rows), nullptr, c->cat_bf16 != 0); xv_max = std::max(xv_max, cv.off); }
+  for (auto& r : s.xv) { Carver cv(nullptr, 0); carve_xv(cv, plan_xv(b, r.first, r.second, c->fcm_chunk_rows), nullptr, c->cat_bf16 != 0, c->u_bf16 != 0 && c->mode == 1 && !c->batch_invariant); xv_max = std::max(xv_max, cv.off); }
   return ((ve_max + 255) & ~int64_t(255)) + ((xv_max + 255) & ~int64_t(255)) + 1024;
 }
 
@@ -278,9 +279,11 @@ int cbx_set_option(cbx_ctx* c, const char* key, int64_t v) {
   else if (k == "fcm_chunk_rows" && v >= 64) c->fcm_chunk_rows = v;
   else if (k == "lstm_chunk_partials" && v >= 1) c->lstm_chunk_slots = v;
   // mode 0: strict fp32 SIMT; 1: tcgen05 TF32 (the parity mode, default); 2: the bf16 mode (BASELINE config 5) = mode 1 with the
-  // D-TDNN bottleneck / transit GEMMs on bf16 operands (cat_bf16 = 2) and the LSTM input projections stored as bf16 (xw_bf16 = 1):
-  // its own, looser tolerance (tests test_mode2_*); setting mode 0 / 1 switches both off again
-  else if (k == "mode" && v >= 0 && v <= 2) { c->mode = v == 0 ? 0 : 1; c->cat_bf16 = v == 2 ? 2 : 0; c->xw_bf16 = v == 2 ? 1 : 0; }
+  // D-TDNN bottleneck / transit GEMMs on bf16 operands (cat_bf16 = 2), the bottleneck output u stored as bf16 with the local
+  // convolution on bf16 operands (u_bf16 = 1) and the LSTM input projections stored as bf16 (xw_bf16 = 1): its own, looser tolerance
+  // (tests test_mode2_*); setting mode 0 / 1 switches all of it off again
+  else if (k == "mode" && v >= 0 && v <= 2) { c->mode = v == 0 ? 0 : 1; c->cat_bf16 = v == 2 ? 2 : 0; c->xw_bf16 = v == 2 ? 1 : 0; c->u_bf16 = v == 2 ? 1 : 0; }
+  else if (k == "u_bf16" && (v == 0 || v == 1)) c->u_bf16 = v;
   else if (k == "xw_bf16" && (v == 0 || v == 1)) c->xw_bf16 = v;
   else if (k == "fcm_fuse" && (v == 0 || v == 1)) c->fcm_fuse = v;
   else if (k == "transit_n256" && (v == 0 || v == 1)) c->transit_n256 = v;
@@ -307,7 +310,8 @@ int64_t cbx_get_option(const cbx_ctx* c, const char* key) {
   if (k == "xv_chunk_rows") return c->xv_chunk_rows;
   if (k == "fcm_chunk_rows") return c->fcm_chunk_rows;
   if (k == "lstm_chunk_partials") return c->lstm_chunk_slots;
-  if (k == "mode") return (c->mode == 1 && c->cat_bf16 == 2 && c->xw_bf16 == 1) ? 2 : c->mode;
+  if (k == "mode") return (c->mode == 1 && c->cat_bf16 == 2 && c->xw_bf16 == 1 && c->u_bf16 == 1) ? 2 : c->mode;
+  if (k == "u_bf16") return c->u_bf16;
   if (k == "xw_bf16") return c->xw_bf16;
   if (k == "fcm_fuse") return c->fcm_fuse;
   if (k == "transit_n256") return c->transit_n256;
@@ -403,7 +407,7 @@ static int embed_core(cbx_ctx* c, const float* pcm, const float* feats, const in
       XvLayout L = plan_xv(b, r.first, r.second, c->fcm_chunk_rows);
       // taps are byte offsets from the start of the caller's workspace
       Carver cv_abs(ws, ws_bytes); cv_abs.off = ve_region;
-      XvChunk ch = carve_xv(cv_abs, L, c, c->cat_bf16 != 0);
+      XvChunk ch = carve_xv(cv_abs, L, c, c->cat_bf16 != 0, c->u_bf16 != 0 && c->mode == 1 && !c->batch_invariant);
       ch.hplan = L.plan.data();
       CBX_CUDA_OK(c, cudaMemcpyAsync(ch.plan, L.plan.data(), sizeof(ClipPlan) * L.plan.size(), cudaMemcpyHostToDevice, sx));
       run_xv_chunk(c, pcm, ch, xv_out, status, sx, feats, feat_off);

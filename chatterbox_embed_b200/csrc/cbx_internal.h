@@ -86,6 +86,7 @@ struct DenseLayerW {
   const float *w1, *t2;      // [128][cin] with BN2 scale folded, BN2 shift
   const float *w1h;          // the same as bf16 [128][cin] (option cat_bf16 = 2)
   const float *wl;           // [32][3*128] local conv, k = tap*128 + c
+  const float *wlh;          // the same as bf16 (bf16 mode)
   const float *wc1, *bc1;    // [64][128], [64]
   const float *wc2, *bc2;    // [32][64], [32]
   const float *wc1T, *wc2T;  // [128][64], [64][32] transposed copies
@@ -114,6 +115,7 @@ struct XvWeights {
   const float *fin_w, *fin_b;                     // [192][1024] (BN folded), [192]
   CUtensorMap tm_tdnn, tm_w1[52], tm_wl[52], tm_tr[3], tm_tr256[3];   // TMA maps of the GEMM B operands (tm_tr256: 256-row boxes for the N = 256 transit tiles)
   CUtensorMap tm_w1h[52], tm_trh[3];                     // bf16 copies: box {64 channels, 128 rows}
+  CUtensorMap tm_wlh[52];                                // bf16 local-conv weights: box {64 channels, 32 rows}
   CUtensorMap tm_res[2][2][2], tm_head2;
 };
 struct FrontendTables {
@@ -165,6 +167,7 @@ struct cbx_ctx {
   int64_t dft_eo = 1;                 // VoiceEncoder / S3 front-end DFT in its even / odd form (two K = 200 GEMMs); 0 = one K = 400 GEMM
   int64_t transit_n256 = 1;           // transit GEMMs with 128 x 256 output tiles
   int64_t fcm_fuse = 1;               // identity residual blocks of the FCM head as one fused kernel (fcm_block_tc.cu); 0 = two convolution kernels
+  int64_t u_bf16 = 0;                 // 1 = the bottleneck output u is stored as bf16 and the local convolution runs on bf16 operands (bf16 mode)
   int64_t xw_bf16 = 0;                // 1 = the LSTM input projections are stored as bf16 (bf16 mode)
   int64_t cat_bf16 = 0;               // 1 = the D-TDNN GEMMs read a bf16 copy of the concatenation buffers, 2 = and run on bf16 operands (kind::f16)
   int64_t probe = 0;                  // timing experiments, results are WRONG while set: bit 0 = no CAM gate kernel (tools/probe_bounds.py)
@@ -291,6 +294,7 @@ struct XvChunk {
   float *cat1, *cat2, *cat3;   // [td_rows][512|1024|1024]
   uint16_t *cat1h, *cat2h, *cat3h;   // bf16 copies of the same (option cat_bf16; null otherwise)
   float* u;                 // [td_rows][128]
+  uint16_t* u16;            // the same as bf16 (bf16 mode: the bottleneck GEMM writes it INSTEAD of u, the local convolution reads it)
   float* tr3;               // [td_rows][512]
   float* seg_sum;           // [segs][128] fp32 (strict mode) or 64-bit fixed point (tensor-core mode: 2 floats per entry)
   float* gate;              // [segs][32]
@@ -306,7 +310,7 @@ void run_ve_forward_partials(cbx_ctx* c, const float* mels, int n, float* out, v
 void run_ve_mel_tc(cbx_ctx* c, const float* pcm, const VeChunk& ch, cudaStream_t st);
 void run_kaldi_fbank_tc(cbx_ctx* c, const float* pcm, const XvChunk& ch, cudaStream_t st);
 void run_local_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmU, const CUtensorMap& tmW, const CUtensorMap& tmOut, int M, int dil,
-                       int col0, const float* gate, const int32_t* row_seg, bool pdl = false, uint16_t* shadow = nullptr, int ldh = 0);   // local_tc.cu
+                       int col0, const float* gate, const int32_t* row_seg, bool pdl = false, uint16_t* shadow = nullptr, int ldh = 0, bool u16 = false);   // local_tc.cu
 int lstm_padded_slots(int n_slots);     // slots rounded up to whole 224-partial cluster tiles (lstm_tc.cu)
 void run_lstm_rec_tc2(cbx_ctx* c, const void* xw, bool xw_bf16, const int32_t* slot_row, const float* whh_perm, float* hseq, float* hlast,
                       int n_slots, cudaStream_t st);

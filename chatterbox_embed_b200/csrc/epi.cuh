@@ -70,6 +70,8 @@ constexpr float kSegFix = 16777216.f;                 // 2^24
 template <bool kExact>
 struct EpiBiasReluMaskSegsumT {
   float* out; int ld; const float* bias; const int32_t* row_seg; unsigned long long* seg_sum; int M;     // out == nullptr: the kernel stores (TMA)
+  uint16_t* u16 = nullptr; int ldu = 0;        // bf16 mode: u goes out as bf16 from here and the kernel's fp32 TMA store is skipped
+  __device__ bool skip_c() const { return u16 != nullptr; }
   __device__ void operator()(int m, int n0, float* v) const {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -86,6 +88,7 @@ struct EpiBiasReluMaskSegsumT {
       v[4 * j + 3] = seg >= 0 ? fmaxf(v[4 * j + 3] + bb.w, 0.f) : 0.f;
     }
     if (out && m < M) store32(out + (size_t)m * ld + n0, v);
+    if (u16 && m < M) store32_bf16(u16 + (size_t)m * ldu + n0, v);
     unsigned rem = __ballot_sync(full, seg >= 0);
     while (rem) {
       const int s = __shfl_sync(full, seg, __ffs(rem) - 1);

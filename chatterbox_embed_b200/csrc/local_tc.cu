@@ -29,6 +29,9 @@ struct Params {
   uint16_t* shadow; int ldh;            // bf16 copy of the concatenation buffer (option cat_bf16), or null
 };
 
+// U16 (bf16 mode): u and the weights are bf16 -- a 128-byte row holds 64 channels, so the halo block is two planes instead of four and
+// a tap is 8 tcgen05.mma kind::f16 (K = 16) instead of 16 kind::tf32 (K = 8): half the MMAs and half the A-operand bytes per tile.
+template <bool U16>
 __global__ void __launch_bounds__(320, 1)
 local_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
                   const Params p) {
@@ -62,20 +65,23 @@ local_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(wfull, W_BYTES);
-      for (int kb = 0; kb < 12; ++kb) tma_load_2d(sW + kb * 4096, &tmW, wfull, kb * 32, 0);
+      constexpr int NPL = U16 ? 2 : 4;          // planes (K blocks of one 128-byte row) per halo block
+      constexpr int KCOLS = U16 ? 64 : 32;      // channels per plane
+      mbar_expect_tx(wfull, 3 * NPL * 4096);
+      for (int kb = 0; kb < 3 * NPL; ++kb) tma_load_2d(sW + kb * 4096, &tmW, wfull, kb * KCOLS, 0);
       pdl_wait();                   // u comes from the bottleneck GEMM, two kernels back (the weights above do not)
       int it = 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], 4 * plane_tx);
-        for (int kb = 0; kb < 4; ++kb)
-          tma_load_2d(sIn + s * STAGE_BYTES + kb * PLANE_BYTES, &tmU, &full[s], kb * 32, tile * 128 - p.dil);
+        mbar_expect_tx(&full[s], NPL * plane_tx);
+        for (int kb = 0; kb < NPL; ++kb)
+          tma_load_2d(sIn + s * STAGE_BYTES + kb * PLANE_BYTES, &tmU, &full[s], kb * KCOLS, tile * 128 - p.dil);
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc_tf32(128, 32);
+    constexpr uint32_t idesc = U16 ? make_idesc_bf16(128, 32) : make_idesc_tf32(128, 32);
+    constexpr int NPL = U16 ? 2 : 4;
     const uint64_t dhi = make_desc_sw128(0);
     const uint32_t w16 = smem_u32(sW) >> 4;
     const uint32_t tap16 = (uint32_t)p.dil * 8u;             // one tap = dil rows of 128 B, in 16-byte units
@@ -93,11 +99,14 @@ local_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
 #pragma unroll
         for (int tap = 0; tap < 3; ++tap)
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb) {
+          for (int kb = 0; kb < NPL; ++kb) {
             const uint64_t ad = dhi | (uint64_t)((in16 + kb * (PLANE_BYTES >> 4) + tap * tap16) & 0x3FFFu);
-            const uint64_t bd = dhi | (uint64_t)((w16 + (tap * 4 + kb) * 256) & 0x3FFFu);
+            const uint64_t bd = dhi | (uint64_t)((w16 + (tap * NPL + kb) * 256) & 0x3FFFu);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_tf32(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (tap | kb | k) != 0);
+            for (int k = 0; k < 4; ++k) {          // four instructions of 32 K bytes per 128-byte row either way
+              if constexpr (U16) umma_bf16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (tap | kb | k) != 0);
+              else umma_tf32(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (tap | kb | k) != 0);
+            }
           }
         umma_commit(&empty[s]);
         umma_commit(&tfull[a]);
@@ -158,14 +167,16 @@ local_conv_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant
 // u [M][128] -> cat[:, col0 : col0 + 32] = conv_k3_dil(u) * gate[segment]; tmU: {128 cols, M rows} box {32, 128 + 2 dil} (tf32),
 // tmOut: {ld cols, M rows} box {32, 128} (fp32) over the concat buffer
 void run_local_conv_tc(cbx_ctx* c, cudaStream_t st, const CUtensorMap& tmU, const CUtensorMap& tmW, const CUtensorMap& tmOut, int M, int dil,
-                       int col0, const float* gate, const int32_t* row_seg, bool pdl, uint16_t* shadow, int ldh) {
+                       int col0, const float* gate, const int32_t* row_seg, bool pdl, uint16_t* shadow, int ldh, bool u16) {
   using namespace lconv;
   if (M <= 0) return;
-  ensure_max_smem(local_conv_kernel, SMEM_BYTES);
+  ensure_max_smem(local_conv_kernel<false>, SMEM_BYTES);
+  ensure_max_smem(local_conv_kernel<true>, SMEM_BYTES);
   Params p{M, dil, col0, (M + 127) / 128, gate, row_seg, shadow, ldh};
   const int grid = p.ntiles < tc::sm_count() ? p.ntiles : tc::sm_count();
-  Scope sc(c->launches, st, "dense_local_gemm", 2.0 * M * kGrowth * 3 * kBnC, 4.0 * M * (kBnC + kGrowth));
-  tc::launch_pdl(local_conv_kernel, dim3(grid), dim3(320), SMEM_BYTES, st, pdl, tmU, tmW, tmOut, p);
+  Scope sc(c->launches, st, "dense_local_gemm", 2.0 * M * kGrowth * 3 * kBnC, (u16 ? 2.0 : 4.0) * M * kBnC + 4.0 * M * kGrowth);
+  if (u16) tc::launch_pdl(local_conv_kernel<true>, dim3(grid), dim3(320), SMEM_BYTES, st, pdl, tmU, tmW, tmOut, p);
+  else tc::launch_pdl(local_conv_kernel<false>, dim3(grid), dim3(320), SMEM_BYTES, st, pdl, tmU, tmW, tmOut, p);
 }
 
 }  // namespace cbx

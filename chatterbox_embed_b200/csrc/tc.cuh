@@ -350,6 +350,10 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 // XM = 2 (cat_bf16 = 2): bf16 OPERANDS as well -- a K block is 64 channels per 128-byte row, the stage holds bf16, W comes
 // from its bf16 copy (tmB: box {64, BN}), kind::f16 MMAs: half the stage stores and half the operand bytes per channel.
 // K need not be a multiple of 64: the tail block's missing channels are zeros on both sides (TMA fill / masked loads).
+// does the epilogue functor write the tile itself (then the kernel's staging + TMA store of C is skipped)?
+template <class E> __device__ __forceinline__ auto epi_skips_c(const E& e, int) -> decltype(e.skip_c()) { return e.skip_c(); }
+template <class E> __device__ __forceinline__ bool epi_skips_c(const E&, long) { return false; }
+
 template <int BN, int STAGES, class Epi, int XM>
 __global__ void __launch_bounds__(320, 2)
 tgemm_bnrelu_kernel(const void* __restrict__ Xv, int lda, int M, int K, const float* __restrict__ bn_a, const float* __restrict__ bn_b,
@@ -593,6 +597,7 @@ tgemm_bnrelu_kernel(const void* __restrict__ Xv, int lda, int M, int K, const fl
         if (tr && threadIdx.x == 64 && c < 128) tr[8 + (c >> 6) * 4] = gtime();
         epi(row, n0 + c, v);                               // transforms v in place (epi.out == nullptr: no store)
         if (tr && threadIdx.x == 64 && c < 128) tr[9 + (c >> 6) * 4] = gtime();
+        if (epi_skips_c(epi, 0)) continue;                 // the functor wrote the tile (bf16 u): no fp32 C store
         const int ci = c >> 5;
         uint8_t* stage = smem + (ci % NBUF) * (BM * 128);
         if (ci >= NBUF) {                                  // buffer reuse: the store that last used it must have read it

@@ -251,6 +251,7 @@ int load_xv(cbx_ctx* c, const TensorMap& t) {
         for (int cc = 0; cc < kBnC; ++cc)
           for (int tap = 0; tap < 3; ++tap) ol[(size_t)n * 384 + tap * kBnC + cc] = wl[((size_t)n * kBnC + cc) * 3 + tap];
       pk.add(&L.wl, ol);
+      pk.add(&L.wlh, to_bf16_words(ol.data(), ol.size()));      // bf16 copy (bf16 mode: local convolution on bf16 operands)
       pk.add(&L.wc1, std::vector<float>(wc1, wc1 + kCamHid * kBnC));
       {   // transposed copies: lanes along the output index read consecutive addresses in the gate kernel
         std::vector<float> t1((size_t)kBnC * kCamHid), t2((size_t)kCamHid * kGrowth);
@@ -296,6 +297,7 @@ int load_xv(cbx_ctx* c, const TensorMap& t) {
     W.tm_w1[i] = tc::make_map_2d(W.dense[i].w1, kBnC, W.dense[i].cin, W.dense[i].cin, 128, true);
     W.tm_w1h[i] = tc::make_map_2d_bf16(W.dense[i].w1h, kBnC, W.dense[i].cin, W.dense[i].cin, 128);
     W.tm_wl[i] = tc::make_map_2d(W.dense[i].wl, kGrowth, 3 * kBnC, 3 * kBnC, 32, true);
+    W.tm_wlh[i] = tc::make_map_2d_bf16(W.dense[i].wlh, kGrowth, 3 * kBnC, 3 * kBnC, 32);
   }
   for (int l = 0; l < 2; ++l)
     for (int b = 0; b < 2; ++b)

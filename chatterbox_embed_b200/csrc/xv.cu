@@ -542,7 +542,8 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
     CUtensorMap tm_cat, tm_u;
     tc::TapMap tap_local{};
     if (tcm) {
-      tm_u = tc::make_map_2d(ch.u, M, kBnC, kBnC, tc::BM + 2 * kDil[b], true);        // halo block: 128 + 2 d frames
+      // halo block: 128 + 2 d frames (bf16 mode: of the bf16 u the bottleneck GEMM wrote)
+      tm_u = ch.u16 ? tc::make_map_2d_bf16(ch.u16, M, kBnC, kBnC, tc::BM + 2 * kDil[b]) : tc::make_map_2d(ch.u, M, kBnC, kBnC, tc::BM + 2 * kDil[b], true);
       tm_cat = tc::make_map_2d(cat, M, ld, ld, tc::BM, false);                           // store target of the 32 new channels
       tap_local.cpb = kBnC / tc::BK;
       for (int t = 0; t < 3; ++t) tap_local.shift[t] = (t - 1) * kDil[b];
@@ -554,13 +555,13 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
                                  tc::EpiBiasReluMaskSegsumExact{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
       else if (bf && c->cat_bf16 == 2)
         tc::tgemm_bnrelu<128, 2, tc::EpiBiasReluMaskSegsum, 2>(L, st, "dense_bottleneck_gemm", cath[b], ld, D.a1, D.b1, W.tm_w1h[li], ch.u, kBnC, M, kBnC, D.cin,
-                                 tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
+                                 tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M, ch.u16, kBnC}, pdl);
       else if (bf)
         tc::tgemm_bnrelu<128, 2, tc::EpiBiasReluMaskSegsum, 1>(L, st, "dense_bottleneck_gemm", cath[b], ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
-                                 tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
+                                 tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M, ch.u16, kBnC}, pdl);
       else if (tcm)
         tc::tgemm_bnrelu<128, 2>(L, st, "dense_bottleneck_gemm", cat, ld, D.a1, D.b1, W.tm_w1[li], ch.u, kBnC, M, kBnC, D.cin,
-                                 tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M}, pdl);
+                                 tc::EpiBiasReluMaskSegsum{nullptr, kBnC, D.t2, ch.td_row_seg, reinterpret_cast<unsigned long long*>(ch.seg_sum), M, ch.u16, kBnC}, pdl);
       else
         sgemm(L, st, "dense_bottleneck_gemm", M, kBnC, D.cin, BnReluA{cat, ld, D.a1, D.b1}, D.w1, D.cin, BiasReluMaskEpi{ch.u, kBnC, D.t2, ch.td_row_clip});
 #ifdef CBX_DEV_TOOLS
@@ -578,7 +579,7 @@ void run_xv_chunk(cbx_ctx* c, const float* pcm, const XvChunk& ch, float* xv_out
         { Scope sc(L, st, "cam_gate_kernel"); cam_gate_kernel<<<ch.segs, 128, 0, st>>>(ch.seg_sum, ch.plan, ch.seg_clip, D, ch.gate); }
       }
       if (tcm)
-        run_local_conv_tc(c, st, tm_u, W.tm_wl[li], tm_cat, M, kDil[b], D.cin, ch.gate, ch.td_row_seg, pdl, bf ? cath[b] : nullptr, ld);
+        run_local_conv_tc(c, st, tm_u, ch.u16 ? W.tm_wlh[li] : W.tm_wl[li], tm_cat, M, kDil[b], D.cin, ch.gate, ch.td_row_seg, pdl, bf ? cath[b] : nullptr, ld, ch.u16 != nullptr);
       else
         sgemm(L, st, "dense_local_gemm", M, kGrowth, 3 * kBnC, LocalConvA{ch.u, kDil[b], M}, D.wl, 3 * kBnC, GateEpi{cat, ld, D.cin, ch.gate, ch.td_row_seg});
     }

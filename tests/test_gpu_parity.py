@@ -476,8 +476,9 @@ def test_cat_bf16_option(models, mode1, setting, kind, tol, min_cos):
 
 # ---- the bf16 mode (mode 2, BASELINE config 5): its own tolerance, stated separately from the fp32 / TF32 gate --------------------
 # mode 2 = mode 1 with (a) the D-TDNN bottleneck / transit GEMMs on bf16 operands (bf16 copy of the concatenation buffers, bf16
-# weight copies, tcgen05 kind::f16, fp32 accumulation) and (b) the LSTM input projections xw stored as bf16 (the projection GEMM
-# is bound by its C writes).  Everything else (front-ends, FCM head, local convolutions, recurrent product, all state) as in mode 1.
+# weight copies, tcgen05 kind::f16, fp32 accumulation), (b) the bottleneck output u stored as bf16 and the CAM local convolution on
+# bf16 operands, and (c) the LSTM input projections xw stored as bf16 (the projection GEMM is bound by its C writes).  Everything
+# else (front-ends, FCM head, TDNN, recurrent product, all state) as in mode 1.
 # Tolerance table against the fp32 oracle, per weight set: the CPU emulation of exactly these roundings (tests/tools/bf16_study.py)
 # predicts VE 1.1e-4 (W0) .. 7.6e-4 (W2) and x-vector 1.4e-4 (W0) / 2.9e-3 (W1) / 1.4e-1 at |x| <= 9.8, cos 0.9996 (W2).
 MODE2_TOL = {          # kind: (VE max-abs, x-vector max-abs / max(1, max|x|), x-vector min cos)
@@ -497,7 +498,7 @@ def mode2(models):
 
 @pytest.mark.parametrize("kind", ["W0", "W1", "W2"])
 def test_mode2_tolerances(models, mode2, kind):
-    assert mode2.get_option("mode") == 2 and mode2.get_option("cat_bf16") == 2 and mode2.get_option("xw_bf16") == 1
+    assert mode2.get_option("mode") == 2 and mode2.get_option("cat_bf16") == 2 and mode2.get_option("xw_bf16") == 1 and mode2.get_option("u_bf16") == 1
     sdv, sdc, emb = _emb(models, kind)
     lens = [int(x) for x in synth.ragged_lengths(6)] + EDGE[:4]
     wavs = [synth.mixed(i, n) for i, n in enumerate(lens)]
