@@ -92,22 +92,29 @@ void cbx_destroy(cbx_ctx* ctx);
 const char* cbx_last_error(const cbx_ctx* ctx);   /* ctx may be NULL: last error of cbx_create */
 const char* cbx_version(void);
 
-/* Tuning: key in {"xv_chunk_rows","fcm_chunk_rows","lstm_chunk_partials","mode","overlap","pdl","batch_invariant","cat_bf16"}.  mode: 1 (default) =
- * tensor-core (tcgen05, TF32 / 3xTF32) kernels, 0 = strict fp32 SIMT kernels everywhere (the on-device fp32 yardstick).
- * overlap: 1 (default) = with both encoders requested, CAMPPlus runs on an internal second stream beside the
- * VoiceEncoder chain (forked from / joined into the caller's stream).  pdl: 1 (default) = the CAMPPlus convolution and
- * dense-layer chains use programmatic dependent launch (a kernel sets up while its predecessor drains).  overlap and pdl
- * are scheduling only: results are bit-identical with either off.  batch_invariant: 1 = the x-vector of a clip is
- * bit-identical whatever else is in the batch and however the call is chunked (exact warp-level segment sums, ~3 %
- * slower); 0 (default) = reproducible from run to run, position dependent within ~1e-4 (the VoiceEncoder embedding is
- * batch invariant either way).  cat_bf16 (first pieces of a bf16 mode; looser tolerances): 1 = the D-TDNN
- * bottleneck / transit GEMMs read a bf16 copy of the concatenation buffers that the producing epilogues write beside the
- * fp32 one (activations rounded once to bf16; weights and MMAs stay TF32): 3 % faster, x-vector error 1.1-1.4x the TF32
- * mode's; 2 = those GEMMs also run on bf16 operands (kind::f16 MMAs, bf16 weight copies, fp32 accumulation): 10 % faster,
- * error 2-6x the TF32 mode's (still inside cos >= 0.9999 / 1e-3 with default-init weights); 0 (default) = fp32 storage.
- * ("lstm_impl", "lstm_dbg", "lstm_trace" select / probe
- * the recurrence kernel and are for the tools under tools/; "probe" != 0 removes kernels from the chain to time what is left
- * -- results are WRONG while it is set -- bit 0: the CAM gate kernel, tools/probe_bounds.py.) */
+/* Tuning.  key / values:
+ * "mode": 1 (default) = tensor-core kernels (tcgen05, TF32 / 3xTF32; the fp32 / TF32 parity mode); 0 = strict fp32 SIMT kernels
+ *   everywhere (the on-device fp32 yardstick); 2 = the bf16 mode (BASELINE config 5): mode 1 with cat_bf16 = 2, u_bf16 = 1 and
+ *   xw_bf16 = 1 -- its own, looser tolerance (tests/test_gpu_parity.py MODE2_TOL).  Setting 0 / 1 switches the
+ *   three bf16 options off again; cbx_get_option("mode") returns 2 only while all three are on.
+ * "cat_bf16" (0 | 1 | 2): 1 = the D-TDNN bottleneck / transit GEMMs read a bf16 copy of the concatenation buffers that the
+ *   producing epilogues write beside the fp32 one (activations rounded once to bf16; weights and MMAs stay TF32); 2 = those GEMMs
+ *   also run on bf16 operands (kind::f16 MMAs, bf16 weight copies, fp32 accumulation).
+ * "u_bf16" (0 | 1): the bottleneck output u is stored as bf16 only and the CAM local convolution runs on bf16 operands.
+ * "xw_bf16" (0 | 1): the LSTM input projections are stored as bf16 (the recurrence reads them as such).
+ * "batch_invariant": 1 = the x-vector of a clip is bit-identical whatever else is in the batch and however the call is chunked
+ *   (exact warp-level segment sums, ~3 % slower; u_bf16 is ignored while it is set); 0 (default) = reproducible from run to run,
+ *   position dependent within ~1e-4 (the VoiceEncoder embedding is batch invariant either way).
+ * Scheduling / layout switches -- results are bit-identical with either value (tested), defaults are the fast setting:
+ *   "overlap" (1): with both encoders requested, CAMPPlus runs on an internal second stream beside the VoiceEncoder chain (forked
+ *   from / joined into the caller's stream); "lstm_late" (1): on that path the recurrence starts when the CAMPPlus chain enters its
+ *   D-TDNN phase; "pdl" (1): the CAMPPlus convolution and dense-layer chains use programmatic dependent launch; "transit_n256" (1):
+ *   transit GEMMs on 128 x 256 output tiles; "lstm_gate_warps" (4 | 2): gate warps per TMEM lane quadrant of the recurrence kernel.
+ * Same arithmetic up to rounding order (tested against each other and the oracle): "fcm_fuse" (1): the identity residual blocks of the
+ *   FCM head as one fused kernel; "dft_eo" (1): the VoiceEncoder / S3 front-end DFT in its even / odd form.
+ * Chunking (results invariant): "xv_chunk_rows", "fcm_chunk_rows", "lstm_chunk_partials".
+ * ("lstm_trace" takes a device pointer for the recurrence kernel's clock trace; "lstm_impl", "lstm_dbg" and "probe" exist only in the
+ * CBX_DEV_TOOLS build of the library -- "probe" removes kernels from the chain to time what is left, results are WRONG while set.) */
 int cbx_set_option(cbx_ctx* ctx, const char* key, int64_t value);
 int64_t cbx_get_option(const cbx_ctx* ctx, const char* key);
 
