@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the speaker-embedding hot path (BASELINE.json metric: speaker embeddings/s on 10 s clips).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode 0|1] [--config 2|3|4] [--job-clips N] [--ragged]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode 0|1] [--config 2|3|4|5] [--job-clips N] [--ragged]
 
 --config 2 (default; BASELINE.json configs[1]): a "step" is one pass of VoiceEncoder + CAMPPlus over one batch of 256
 synthetic ten-second 16 kHz clips per GPU.  --config 3 (configs[2]): one ragged batch of 1024 clips, 3-30 s each, per GPU.
@@ -36,6 +36,7 @@ CLIP_SAMPLES = 160000
 WORKLOADS = {
     2: "256 x 10 s 16 kHz clips per GPU, VoiceEncoder(256-d)+CAMPPlus(192-d), random-init weights (BASELINE configs[1])",
     3: "ragged batch of 1024 clips, 3-30 s each (17 093 s of audio) per GPU, VoiceEncoder(256-d)+CAMPPlus(192-d), random-init weights (BASELINE configs[2])",
+    5: "prepare_conditionals over 256 x 10 s 24 kHz prompts on one GPU: resample to 16 kHz, 24 kHz prompt mel, S3 tokenizer log-mel front end, VoiceEncoder + CAMPPlus, generator-side projections (BASELINE configs[4])",
     4: "voice-bank job: {n} clips ({kind}) sharded over the GPUs by cbx_partition, 256-clip batches streamed from pinned host memory, one NCCL all-gather (BASELINE configs[3])",
 }
 WORKLOAD = WORKLOADS[2]
@@ -180,6 +181,69 @@ def tf32_peak(dev, seconds: float = 2.0):
                 "how": f"torch.matmul fp32 with allow_tf32, 8192^3, best of 10 / {reps} back to back"}
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def kernel_profile(ctx, step_fn, prof_steps, dev, rank, world, sync_all):
+    """Per-kernel device times of `prof_steps` separate profiled steps -> (roofline of the top kernel family, per-kernel table,
+    the TF32 dense peak measured in this run)."""
+    import torch
+    # ---- per-kernel device times (CUDA events on the launching stream), separate profiled steps ------------------
+    # (the two encoder chains are serialised for this pass so that a kernel's events time that kernel alone)
+    ctx.set_option("overlap", 0)
+    ctx.profile_enable(True)
+    for _ in range(prof_steps):
+        step_fn()
+    torch.cuda.synchronize()
+    prof = ctx.profile_report()
+    ctx.profile_enable(False)
+    ctx.set_option("overlap", 1)
+    # kernel families: the per-conv tags of the FCM head ("fcm_conv_gemm:l1b0c1" ...) are one kernel
+    fam = {}
+    for k, v in prof.items():
+        f = fam.setdefault(k.split(":")[0], dict(ms=0.0, launches=0, flops=0.0, bytes=0.0, exec_flops=0.0))
+        for key in ("ms", "launches", "flops", "bytes"):
+            f[key] += v[key]
+    tot_ms = sum(v["ms"] for v in fam.values()) or 1.0
+    tname, t = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    pk = peaks()
+    tf32 = tf32_peak(dev) if rank == 0 else None
+    if world > 1:
+        sync_all()
+    # TF32 dense peak: measured on this box in this run (cuBLAS 8192^3); a kernel timed inside the step is held against the
+    # sustained figure.  (Round 1 assumed half the measured bf16 rate.)
+    tensor_peak = tf32["sustained"] if tf32 else pk["bf16_sus"] / 2.0
+    tensor_src = "TF32 dense peak measured in this run (torch.matmul allow_tf32 8192^3, sustained)" if tf32 else "bf16 sustained / 2"
+    ridge = tensor_peak * 1e12 / (pk["hbm"] * 1e9)          # FLOP per byte above which a kernel is tensor bound
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram__bytes_read+write per launch from ncu --set full captures
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(tname, {}).get("dram_bytes_per_launch")
+    secs = t["ms"] / 1e3
+    common = {"kernel": tname, "share_of_step": t["ms"] / tot_ms, "avg_launch_ms": t["ms"] / t["launches"],
+              "launches_per_step": t["launches"] / prof_steps, "traffic": traffic,
+              "arithmetic_intensity_flop_per_byte": (t["flops"] / t["bytes"]) if t["bytes"] else None}
+    if t["bytes"] > 0 and (t["flops"] == 0 or t["flops"] / t["bytes"] < ridge):
+        achieved = t["bytes"] / secs / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
+                "peak_source": f"{pk['src']} HBM copy bandwidth", "tflops": t["flops"] / secs / 1e12, **common}
+    elif t["flops"] > 0:
+        achieved = t["flops"] / secs / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                "peak_source": tensor_src, **common}
+    else:
+        roof = {"bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None, **common}
+    # per kernel: ALGORITHMIC flops / bytes per second (what the reference op needs, SURVEY.md 8d); the 3xTF32 front-ends
+    # execute three MMAs per algorithmic one -- `exec_tflops` says what the tensor pipe actually ran
+    EXEC_FACTOR = {"kaldi_dftmel_tc_kernel": 3.0, "ve_dftmel_tc_kernel": 3.0}
+    kernels = {}
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        tfl = (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["flops"] > 0 and v["ms"] > 0 else None
+        gbs = (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["bytes"] > 0 and v["ms"] > 0 else None
+        kernels[k] = {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] / prof_steps, "tflops": tfl, "gbs": gbs,
+                      "frac_hbm": gbs / pk["hbm"] if gbs else None, "frac_tf32": tfl / tensor_peak if tfl else None}
+        if k in EXEC_FACTOR and tfl:
+            kernels[k]["exec_tflops"] = tfl * EXEC_FACTOR[k]
+    return roof, kernels, tf32
 
 
 def run_reference(args):
@@ -372,14 +436,182 @@ def run_job(args):
         dist.destroy_process_group()
 
 
+def run_conditionals(args):
+    """--config 5 (BASELINE configs[4]): the whole `prepare_conditionals` speaker-conditioning path over a batch of 24 kHz prompt
+    clips, bf16 mode by default -- what tts.py:329-387 / s3gen.py:150-207 do one clip at a time: resample 24 -> 16 kHz, the 24 kHz
+    prompt mel (`prompt_feat`), the S3 tokenizer's 128-bin log-mel front end on the 16 kHz audio (the tokenizer network itself is a
+    third-party model outside this path), VoiceEncoder + CAMPPlus embeddings, and the first projection each generator applies to
+    them (T3CondEnc.spkr_enc, flow.spk_embed_affine_layer).  One GPU; `value` with the 24 kHz PCM resident in HBM, `e2e` from
+    pinned host PCM with everything a voice profile stores copied back to the host inside the timed region."""
+    import torch
+    from chatterbox_embed_b200 import SpeakerProjections, _lib, synth
+    from chatterbox_embed_b200.mel import NUM_MELS
+    from chatterbox_embed_b200.s3tokenizer import N_MELS as S3_MELS
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"config": 5, "unavailable": "--config 5 is a one-GPU line (clips are independent: the N-GPU figure is the weak-scaling line of --config 2)"}))
+        return
+    world, rank, local, dev, emb, ctx, sdv, sdc = setup(args)
+    torch.manual_seed(1)
+    proj = SpeakerProjections().to(dev).eval()
+    W, K = max(args.warmup, 3), args.steps
+    clk = ClockSampler(local).start()
+    SR24, SR16 = 24000, 16000
+    n, L24 = CLIPS, 10 * SR24                                  # DEC_COND_LEN = 10 s of 24 kHz audio (tts.py:119)
+    wavs24 = [synth.mixed(i, L24) for i in range(n)]
+    host = torch.empty(n * L24, dtype=torch.float32).pin_memory()
+    for i, w in enumerate(wavs24):
+        host[i * L24:(i + 1) * L24] = torch.from_numpy(w)
+    L16 = _lib.resample_out_len(SR24, SR16, L24)
+    T24, T16 = _lib.prompt_mel_frames(L24), _lib.s3_log_mel_frames(L16)
+    off24 = np.arange(n + 1, dtype=np.int64) * L24
+    off16 = np.arange(n + 1, dtype=np.int64) * L16
+    pcm24 = host.to(dev)
+    def buffers():
+        return dict(w16=torch.empty(n * L16, dtype=torch.float32, device=dev), pmel=torch.empty((n * T24, NUM_MELS), dtype=torch.float32, device=dev),
+                    s3mel=torch.empty(n * S3_MELS * T16, dtype=torch.float32, device=dev))
+    B0 = buffers()
+    w16, pmel, s3mel = B0["w16"], B0["pmel"], B0["s3mel"]
+    res = {}
+
+    def step_device(src=None, B=None, out=None):
+        st = torch.cuda.current_stream(dev).cuda_stream
+        x = pcm24 if src is None else src
+        B = B0 if B is None else B
+        out = res if out is None else out
+        ctx.resample(x.data_ptr(), off24, SR24, SR16, B["w16"].data_ptr(), off16, st)
+        ctx.prompt_mel(x.data_ptr(), off24, B["pmel"].data_ptr(), st)
+        ctx.s3_log_mel(B["w16"].data_ptr(), off16, B["s3mel"].data_ptr(), st)
+        ve_o, xv_o, status = emb.embed_device(B["w16"], off16)
+        out.update(ve=ve_o, xv=xv_o, status=status, t3=proj.t3_speaker_cond(ve_o), flow=proj.flow_speaker_cond(xv_o))
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), time.perf_counter() - t0
+
+    for _ in range(W):
+        step_device()
+    torch.cuda.synchronize()
+    l0 = ctx.launch_count()
+    tw0 = time.time()
+    ms, _ = timed(step_device, K)
+    tw1 = time.time()
+    launches = ctx.launch_count() - l0
+    clocks = clk.summary(tw0, tw1)
+    clk.stop()
+    value = n * K / (ms / 1e3)
+    got = {k: v.detach().cpu().numpy() for k, v in res.items()}
+    got["prompt_feat"] = pmel.view(n, T24, NUM_MELS).cpu().numpy()
+    got["s3_mel"] = s3mel.view(n, S3_MELS, T16).cpu().numpy()
+
+    # ---- end to end: pinned host PCM in, everything a voice profile stores back on the host ----------------------------------
+    # two steps in flight on two streams, each with its own device and pinned buffers: the copies of one step overlap the kernels of
+    # the other (libcbx orders its own work across streams; the shared workspace is never used by two steps at once)
+    slots = []
+    for _ in range(2):
+        slots.append(dict(stream=torch.cuda.Stream(dev), dst24=torch.empty_like(pcm24), B=buffers(), out={},
+                          small=torch.empty((n, 256 + 192 + 1024 + 80), dtype=torch.float32).pin_memory(),
+                          mel=torch.empty((n * T24, NUM_MELS), dtype=torch.float32).pin_memory(),
+                          status=torch.empty(n, dtype=torch.int32).pin_memory(), busy=False))
+
+    def submit(sl):
+        with torch.cuda.stream(sl["stream"]):
+            sl["dst24"].copy_(host, non_blocking=True)
+            step_device(sl["dst24"], sl["B"], sl["out"])
+            o, hs = sl["out"], sl["small"]
+            hs[:, :256].copy_(o["ve"], non_blocking=True); hs[:, 256:448].copy_(o["xv"], non_blocking=True)
+            hs[:, 448:1472].copy_(o["t3"].view(n, 1024), non_blocking=True); hs[:, 1472:].copy_(o["flow"], non_blocking=True)
+            sl["mel"].copy_(sl["B"]["pmel"], non_blocking=True); sl["status"].copy_(o["status"], non_blocking=True)
+        sl["busy"] = True
+
+    def steps_host(k):
+        for i in range(k):
+            sl = slots[i & 1]
+            if sl["busy"]:
+                sl["stream"].synchronize()                     # the caller reads this slot's profile tensors before reusing it
+            submit(sl)
+        for sl in slots:
+            sl["stream"].synchronize(); sl["busy"] = False
+    steps_host(2)
+    _, wall = timed(lambda: steps_host(K), 1)
+    e2e_value = n * K / wall
+    h_small, h_mel, h_status = slots[(K - 1) & 1]["small"], slots[(K - 1) & 1]["mel"], slots[(K - 1) & 1]["status"]
+    e2e_same = float(max(np.abs(h_small[:, :256].numpy() - got["ve"]).max(), np.abs(h_small[:, 256:448].numpy() - got["xv"]).max(),
+                         np.abs(h_mel.numpy().reshape(got["prompt_feat"].shape) - got["prompt_feat"]).max()))
+
+    roof, kernels, tf32 = kernel_profile(ctx, step_device, min(K, 2), dev, 0, 1, torch.cuda.synchronize)
+
+    # ---- parity of the timed batch against the CPU oracle, and the CPU port timed on the host cores -----------------------------
+    from oracle import frontend, nets
+    lin = lambda x, l: torch.nn.functional.linear(torch.from_numpy(x), l.weight.detach().cpu(), l.bias.detach().cpu()).numpy()
+
+    def oracle_clip(w24):
+        w16o = frontend.resample_torchaudio(w24, SR24, SR16)
+        ve_o = nets.ve_embed_wavs(sdv, [w16o])[0]
+        xv_o = nets.campplus_embed_wavs(sdc, [w16o])[0]
+        return dict(w16=w16o, prompt_feat=frontend.prompt_mel_torch(w24), s3_mel=frontend.s3_log_mel_torch(w16o), ve=ve_o, xv=xv_o,
+                    t3=lin(ve_o[None], proj.spkr_enc)[0],
+                    flow=lin((xv_o / max(np.linalg.norm(xv_o), 1e-12))[None], proj.spk_embed_affine_layer)[0])
+    pick = [0, 1, n // 2, n - 1]
+    cosf = lambda a, b: float(np.dot(a.astype(np.float64).ravel(), b.astype(np.float64).ravel()) / (np.linalg.norm(a.astype(np.float64)) * np.linalg.norm(b.astype(np.float64))))
+    par = {"clips_checked": pick, "max_abs": {}, "min_cos": {}}
+    w16_np = w16.view(n, L16).cpu().numpy()
+    for i in pick:
+        o = oracle_clip(wavs24[i])
+        o_pm = np.asarray(o["prompt_feat"]).reshape(T24, NUM_MELS)
+        pairs = {"resampled_16k": (w16_np[i], np.asarray(o["w16"]).reshape(-1)), "prompt_feat": (got["prompt_feat"][i], o_pm),
+                 "s3_log_mel": (got["s3_mel"][i], np.asarray(o["s3_mel"]).reshape(S3_MELS, -1)), "ve": (got["ve"][i], o["ve"]), "xv": (got["xv"][i], o["xv"]),
+                 "t3_spkr_enc": (got["t3"][i].reshape(-1), o["t3"]), "flow_affine": (got["flow"][i], o["flow"])}
+        for kname, (a, b) in pairs.items():
+            par["max_abs"][kname] = max(par["max_abs"].get(kname, 0.0), float(np.abs(a - b).max()))
+            par["min_cos"][kname] = min(par["min_cos"].get(kname, 1.0), cosf(a, b))
+    par["all_finite"] = bool(all(np.isfinite(v).all() for v in got.values()))
+    par["status_nonzero"] = int((got["status"] != 0).sum())
+    par["e2e_equals_device_max_abs"] = e2e_same
+    par["oracle"] = "oracle/frontend.py + oracle/nets.py (CPU fp32 restatement pinned to the verbatim reference modules / torchaudio)"
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        n_s = 64
+        oracle_clip(wavs24[0])
+        t0 = time.perf_counter()
+        for i in range(n_s):
+            oracle_clip(wavs24[i])
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_s / dt, "unit": "clips/s", "cores": threads, "kind": "port",
+               "sample": f"{n_s} of the {n} ten-second 24 kHz prompts, B=1 loop, {dt:.1f} s of CPU work (oracle port: torchaudio-style resampler, prompt mel, S3 log-mel, both encoders, projections)"}
+    dtype, note = precision_fields(args, ctx)
+    line = {"metric": "prepare_conditionals speaker conditionings/sec (10 s 24 kHz prompts)", "value": value, "unit": "clips/s",
+            "audio_s_per_s": value * 10.0, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic", "precision_note": note,
+            "config": {"workload": WORKLOADS[5], "mode": {0: "strict-fp32 SIMT", 1: "tcgen05 TF32", 2: "bf16 mode (tcgen05 TF32 + bf16 D-TDNN GEMM operands + bf16 LSTM input projections)"}[args.mode],
+                       "l2": f"inputs ({n * L24 * 4 / 1e6:.0f} MB of 24 kHz PCM per step) and activations exceed the 126 MB L2; no flush needed",
+                       "parallelism": "dp1", "clips_per_gpu": n, "audio_seconds_per_gpu": n * 10.0},
+            "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": n * L24 * 4,
+                    "d2h_bytes_per_step": int(h_small.numel() * 4 + h_mel.numel() * 4 + h_status.numel() * 4),
+                    "api": "cbx_resample + cbx_prompt_mel + cbx_s3_log_mel + cbx_embed + cbx_project on torch's stream; pinned host PCM in, "
+                           "embeddings, projections and prompt_feat back to pinned host memory; two steps in flight on two streams"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "parity": par,
+            "tf32_peak_tflops": tf32, "timed_region_s": ms / 1e3, "kernels": kernels}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--mode", type=int, default=int(os.environ.get("CBX_MODE", "1")))
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4], help="BASELINE.json configs, 1-based: 2 = 256 x 10 s (default), 3 = ragged 1024, 4 = voice-bank job")
+    ap.add_argument("--mode", type=int, default=None, help="0 strict fp32, 1 tcgen05 TF32 (default), 2 bf16 mode (default of --config 5)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configs, 1-based: 2 = 256 x 10 s (default), 3 = ragged 1024, 4 = voice-bank job, 5 = prepare_conditionals (bf16 mode unless --mode is given)")
     ap.add_argument("--job-clips", type=int, default=100000)
     ap.add_argument("--ragged", action="store_true", help="--config 4: 3-30 s clips instead of 10 s")
     ap.add_argument("--opt", action="append", default=[], help="libcbx option key=value (cbx_set_option)")
@@ -387,10 +619,14 @@ def main():
     ap.add_argument("--sustain", type=float, default=3.0, help="seconds of back-to-back steps for the `sustained` object of the line (0 = skip)")
     ap.add_argument("--no-job", action="store_true", help="N > 1: skip the 1e5-clip voice-bank job that is attached to the line")
     args = ap.parse_args()
+    if args.mode is None:
+        args.mode = int(os.environ.get("CBX_MODE", "2" if args.config == 5 else "1"))
     if args.impl == "reference":
         return run_reference(args)
     if args.config == 4:
         return run_job(args)
+    if args.config == 5:
+        return run_conditionals(args)
 
     import torch
     import torch.distributed as dist
@@ -491,63 +727,7 @@ def main():
     e2e_value = world * n_clips * K / wall
     e2e_sync_value = world * n_clips * K / wall_sync
 
-    # ---- per-kernel device times (CUDA events on the launching stream), separate profiled steps ------------------
-    # (the two encoder chains are serialised for this pass so that a kernel's events time that kernel alone)
-    ctx.set_option("overlap", 0)
-    ctx.profile_enable(True)
-    prof_steps = min(K, 2)
-    for _ in range(prof_steps):
-        step_device()
-    torch.cuda.synchronize()
-    prof = ctx.profile_report()
-    ctx.profile_enable(False)
-    ctx.set_option("overlap", 1)
-    # kernel families: the per-conv tags of the FCM head ("fcm_conv_gemm:l1b0c1" ...) are one kernel
-    fam = {}
-    for k, v in prof.items():
-        f = fam.setdefault(k.split(":")[0], dict(ms=0.0, launches=0, flops=0.0, bytes=0.0, exec_flops=0.0))
-        for key in ("ms", "launches", "flops", "bytes"):
-            f[key] += v[key]
-    tot_ms = sum(v["ms"] for v in fam.values()) or 1.0
-    tname, t = max(fam.items(), key=lambda kv: kv[1]["ms"])
-    pk = peaks()
-    tf32 = tf32_peak(dev) if rank == 0 else None
-    if world > 1:
-        sync_all()
-    # TF32 dense peak: measured on this box in this run (cuBLAS 8192^3); a kernel timed inside the step is held against the
-    # sustained figure.  (Round 1 assumed half the measured bf16 rate.)
-    tensor_peak = tf32["sustained"] if tf32 else pk["bf16_sus"] / 2.0
-    tensor_src = "TF32 dense peak measured in this run (torch.matmul allow_tf32 8192^3, sustained)" if tf32 else "bf16 sustained / 2"
-    ridge = tensor_peak * 1e12 / (pk["hbm"] * 1e9)          # FLOP per byte above which a kernel is tensor bound
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram__bytes_read+write per launch from ncu --set full captures
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(tname, {}).get("dram_bytes_per_launch")
-    secs = t["ms"] / 1e3
-    common = {"kernel": tname, "share_of_step": t["ms"] / tot_ms, "avg_launch_ms": t["ms"] / t["launches"],
-              "launches_per_step": t["launches"] / prof_steps, "traffic": traffic,
-              "arithmetic_intensity_flop_per_byte": (t["flops"] / t["bytes"]) if t["bytes"] else None}
-    if t["bytes"] > 0 and (t["flops"] == 0 or t["flops"] / t["bytes"] < ridge):
-        achieved = t["bytes"] / secs / 1e9
-        roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
-                "peak_source": f"{pk['src']} HBM copy bandwidth", "tflops": t["flops"] / secs / 1e12, **common}
-    elif t["flops"] > 0:
-        achieved = t["flops"] / secs / 1e12
-        roof = {"bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-                "peak_source": tensor_src, **common}
-    else:
-        roof = {"bound": "hbm", "achieved": None, "peak": pk["hbm"], "unit": "GB/s", "frac": None, **common}
-    # per kernel: ALGORITHMIC flops / bytes per second (what the reference op needs); the 3xTF32 front-ends
-    # execute three MMAs per algorithmic one -- `exec_tflops` says what the tensor pipe actually ran
-    EXEC_FACTOR = {"kaldi_dftmel_tc_kernel": 3.0, "ve_dftmel_tc_kernel": 3.0}
-    kernels = {}
-    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
-        tfl = (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["flops"] > 0 and v["ms"] > 0 else None
-        gbs = (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["bytes"] > 0 and v["ms"] > 0 else None
-        kernels[k] = {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] / prof_steps, "tflops": tfl, "gbs": gbs,
-                      "frac_hbm": gbs / pk["hbm"] if gbs else None, "frac_tf32": tfl / tensor_peak if tfl else None}
-        if k in EXEC_FACTOR and tfl:
-            kernels[k]["exec_tflops"] = tfl * EXEC_FACTOR[k]
+    roof, kernels, tf32 = kernel_profile(ctx, step_device, min(K, 2), dev, rank, world, sync_all)
 
     # ---- the same step repeated for >= --sustain seconds (AFTER every other measurement, so that it does not pre-heat them): the
     # figure a long job sees once the clocks have settled under the power cap

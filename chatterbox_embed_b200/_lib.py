@@ -72,8 +72,8 @@ def lib() -> C.CDLL:
     """Load (building first if stale/missing) libcbx.so.  Raises if it cannot be had."""
     global _lib
     if _lib is None:
-        path = _build.LIB
-        if os.environ.get("CBX_NO_BUILD") != "1":
+        path = os.environ.get("CBX_LIB") or _build.LIB            # CBX_LIB: A/B runs of two builds of the library (tools/ab_bench.sh)
+        if os.environ.get("CBX_NO_BUILD") != "1" and not os.environ.get("CBX_LIB"):
             path = _build.build()
         if not os.path.exists(path):
             raise CbxError(f"{path} is missing and could not be built; there is no CPU fallback")

@@ -127,6 +127,7 @@ int cbx_resample(cbx_ctx* c, const float* x_dev, const int64_t* in_offsets_host,
   }
   std::vector<ResampleClip> clips(n_clips);
   int max_out = 0;
+  double tot_in = 0.0, tot_out = 0.0;               // algorithmic work of the call: every sample read once, `taps` MACs per output
   for (int i = 0; i < n_clips; ++i) {
     const int64_t len = in_offsets_host[i + 1] - in_offsets_host[i];
     if (len < 0 || len > ((int64_t)1 << 30)) { c->err = "offsets must be non-decreasing"; return CBX_ERR_ARG; }
@@ -134,7 +135,9 @@ int cbx_resample(cbx_ctx* c, const float* x_dev, const int64_t* in_offsets_host,
     if (out_offsets_host[i + 1] - out_offsets_host[i] != out_len) { c->err = "out_offsets do not match cbx_resample_out_len"; return CBX_ERR_ARG; }
     clips[i] = ResampleClip{(long long)in_offsets_host[i], (long long)out_offsets_host[i], (int)len, (int)out_len};
     max_out = std::max<int>(max_out, (int)out_len);
+    tot_in += (double)len; tot_out += (double)out_len;
   }
+  const double share = n_clips > 65535 ? 65535.0 / n_clips : 1.0;      // per launch (grid.y limit below)
   if (max_out == 0) return CBX_OK;
   // clip table: grown on demand, owned by the context
   if (c->resample_clips_cap < n_clips) {
@@ -154,11 +157,11 @@ int cbx_resample(cbx_ctx* c, const float* x_dev, const int64_t* in_offsets_host,
     if (tiled) {
       const int frames = (max_out + nnew - 1) / nnew;
       dim3 grid((frames + kRsFrames - 1) / kRsFrames, nz);
-      Scope sc(c->launches, st, "resample_tiled_kernel");
+      Scope sc(c->launches, st, "resample_tiled_kernel", 2.0 * taps * tot_out * share, 4.0 * (tot_in + tot_out) * share);
       resample_tiled_kernel<<<grid, 256, tiled_smem, st>>>(x_dev, dc, it->second + (size_t)nnew * taps, orig, nnew, width, taps, y_dev);
     } else {
       dim3 grid(std::min((max_out + 255) / 256, 4096), nz);
-      Scope sc(c->launches, st, "resample_kernel");
+      Scope sc(c->launches, st, "resample_kernel", 2.0 * taps * tot_out * share, 4.0 * (tot_in + tot_out) * share);
       resample_kernel<<<grid, 256, 0, st>>>(x_dev, dc, it->second, orig, nnew, width, taps, y_dev);
     }
   }
