@@ -290,6 +290,7 @@ int cbx_set_option(cbx_ctx* c, const char* key, int64_t v) {
   else if (k == "dft_eo" && (v == 0 || v == 1)) c->dft_eo = v;
   else if (k == "lstm_late" && (v == 0 || v == 1)) c->lstm_late = v;
   else if (k == "lstm_gate_warps" && (v == 2 || v == 4)) c->lstm_gate_warps = v;
+  else if (k == "bn_prefetch" && (v == 0 || v == 1)) c->launches.bn_prefetch = (int)v;
   else if (k == "overlap" && (v == 0 || v == 1)) c->overlap = v;
 #ifdef CBX_DEV_TOOLS   // timing experiments of tools/ (results are wrong while "probe" is set): not in the product library
   else if (k == "lstm_dbg") c->lstm_dbg = v;
@@ -318,6 +319,7 @@ int64_t cbx_get_option(const cbx_ctx* c, const char* key) {
   if (k == "dft_eo") return c->dft_eo;
   if (k == "lstm_late") return c->lstm_late;
   if (k == "lstm_gate_warps") return c->lstm_gate_warps;
+  if (k == "bn_prefetch") return c->launches.bn_prefetch;
   if (k == "overlap") return c->overlap;
   if (k == "pdl") return c->pdl;
   if (k == "batch_invariant") return c->batch_invariant;

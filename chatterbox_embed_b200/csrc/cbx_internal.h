@@ -60,6 +60,7 @@ struct ProfRec { const char* tag; double flops; double bytes; cudaEvent_t e0, e1
 struct Launches {
   int64_t count = 0;
   bool prof = false;
+  int bn_prefetch = 1;          // option bn_prefetch: successor-tile L2 prefetch of the pre-activation GEMM (tc.cuh)
   std::vector<ProfRec> recs;
 };
 struct Scope {

@@ -60,6 +60,22 @@ CUtensorMap make_map_2d(const float* base, int64_t rows, int64_t cols, int64_t l
   return m;
 }
 
+CUtensorMap make_map_2d_plain(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  CUtensorMap m;
+  std::memset(&m, 0, sizeof m);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  EncodeTiledFn fn = encode_fn();
+  CUresult r = fn ? fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+                  : CUDA_ERROR_NOT_FOUND;
+  if (r != CUDA_SUCCESS) fprintf(stderr, "libcbx: cuTensorMapEncodeTiled (plain) failed (%d) rows=%lld cols=%lld ld=%lld\n", (int)r,
+                                 (long long)rows, (long long)cols, (long long)ld);
+  return m;
+}
+
 // bf16 [rows][cols] (leading dimension ld elements): box {64 columns = 128 bytes, box_rows}, 128-byte swizzle
 CUtensorMap make_map_2d_bf16(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   CUtensorMap m;

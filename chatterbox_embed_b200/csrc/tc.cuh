@@ -357,7 +357,8 @@ template <class E> __device__ __forceinline__ bool epi_skips_c(const E&, long) {
 template <int BN, int STAGES, class Epi, int XM>
 __global__ void __launch_bounds__(320, 2)
 tgemm_bnrelu_kernel(const void* __restrict__ Xv, int lda, int M, int K, const float* __restrict__ bn_a, const float* __restrict__ bn_b,
-                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, int nkb, Epi epi) {
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, int nkb, Epi epi,
+                    const __grid_constant__ CUtensorMap tmX, int pf_stride) {
   constexpr bool XH = XM == 1;
   constexpr int KB = XM == 2 ? 64 : BK;          // channels per K block
   extern __shared__ uint8_t smem_raw[];
@@ -424,6 +425,12 @@ tgemm_bnrelu_kernel(const void* __restrict__ Xv, int lda, int M, int K, const fl
         mbar_expect_tx(&bfull[s], B_BYTES);
         tma_load_2d(sB + s * B_BYTES, &tmB, &bfull[s], kb * KB, n0);
       }
+      // L2 prefetch for the CTA that will take over this slot: the first four K blocks of the row tile `pf_stride` (= CTA slots of the
+      // GPU) further on, issued when this CTA's K loop is nearly done -- the successor's first loads then hit L2 instead of waiting
+      // for DRAM behind everyone else's stream
+      if (pf_stride > 0 && (int)(blockIdx.y + pf_stride) * BM < M)
+        asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                     ::"l"(reinterpret_cast<uint64_t>(&tmX)), "r"(0), "r"((int)(blockIdx.y + pf_stride) * BM) : "memory");
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = XM == 2 ? make_idesc_bf16(BM, BN) : make_idesc_tf32(BM, BN);
@@ -822,6 +829,7 @@ EncodeTiledFn encode_fn();
 
 // 2-D fp32 row-major [rows][cols] with leading dimension ld (floats); box = 32 columns x box_rows rows, 128B swizzle
 CUtensorMap make_map_2d(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool round_tf32);
+CUtensorMap make_map_2d_plain(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows);   // no swizzle (L2 prefetch)
 CUtensorMap make_map_2d_bf16(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
 template <int BN, int STAGES, class Pro, class Epi>
@@ -864,7 +872,15 @@ inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const vo
   Scope sc(L, st, tag, 2.0 * M * N * K, (XM ? 2.0 : 4.0) * (double)M * K + 4.0 * (double)M * N);
   CUtensorMap tmC = make_map_2d(C, M, N, ldc, BM, false);
   constexpr int KB = XM == 2 ? 64 : BK;
-  launch_pdl(kern, grid, dim3(320), SMEM, st, pdl, X, lda, M, K, bn_a, bn_b, tmB, tmC, (K + KB - 1) / KB, epi);
+  // option bn_prefetch (TF32 path): a plain tensor map of X, box = 128 columns x 128 rows, for the successor-tile L2 prefetch; the
+  // successor of a CTA in its slot is the row tile (CTA slots of the GPU) / (column tiles) further on (2 CTAs per SM)
+  CUtensorMap tmX = tmC;
+  int pf_stride = 0;
+  if (XM == 0 && L.bn_prefetch > 0 && K >= 128) {
+    tmX = make_map_2d_plain(static_cast<const float*>(X), M, K, lda, 128, BM);
+    pf_stride = (2 * sm_count() + (int)grid.x - 1) / (int)grid.x;
+  }
+  launch_pdl(kern, grid, dim3(320), SMEM, st, pdl, X, lda, M, K, bn_a, bn_b, tmB, tmC, (K + KB - 1) / KB, epi, tmX, pf_stride);
 }
 
 }  // namespace tc

@@ -109,7 +109,9 @@ const char* cbx_version(void);
  *   "overlap" (1): with both encoders requested, CAMPPlus runs on an internal second stream beside the VoiceEncoder chain (forked
  *   from / joined into the caller's stream); "lstm_late" (1): on that path the recurrence starts when the CAMPPlus chain enters its
  *   D-TDNN phase; "pdl" (1): the CAMPPlus convolution and dense-layer chains use programmatic dependent launch; "transit_n256" (1):
- *   transit GEMMs on 128 x 256 output tiles; "lstm_gate_warps" (4 | 2): gate warps per TMEM lane quadrant of the recurrence kernel.
+ *   transit GEMMs on 128 x 256 output tiles; "lstm_gate_warps" (4 | 2): gate warps per TMEM lane quadrant of the recurrence kernel;
+ *   "bn_prefetch" (1): every CTA of the pre-activation GEMM ends its K loop with an L2 prefetch of the first K blocks of the row tile
+ *   that the next CTA in its slot will take (a hint: no data reaches the SM).
  * Same arithmetic up to rounding order (tested against each other and the oracle): "fcm_fuse" (1): the identity residual blocks of the
  *   FCM head as one fused kernel; "dft_eo" (1): the VoiceEncoder / S3 front-end DFT in its even / odd form.
  * Chunking (results invariant): "xv_chunk_rows", "fcm_chunk_rows", "lstm_chunk_partials".

@@ -577,13 +577,13 @@ def test_launch_options_do_not_change_results(models, mode1):
     ctx = _lib.context(0)
     ref = emb.embed_wavs(wavs)
     try:
-        for key in ("pdl", "overlap", "transit_n256", "lstm_late"):   # lstm_late: the recurrence waits for the D-TDNN phase of the other stream        # transit_n256: 128 x 256 instead of 128 x 128 output tiles, same arithmetic per element
+        for key in ("pdl", "overlap", "transit_n256", "lstm_late", "bn_prefetch"):   # bn_prefetch: L2 prefetch hint for the CTA that takes over the slot; lstm_late: the recurrence waits for the D-TDNN phase of the other stream        # transit_n256: 128 x 256 instead of 128 x 128 output tiles, same arithmetic per element
             ctx.set_option(key, 0)
             got = emb.embed_wavs(wavs)
             ctx.set_option(key, 1)
             assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), key
     finally:
-        ctx.set_option("pdl", 1); ctx.set_option("overlap", 1); ctx.set_option("transit_n256", 1); ctx.set_option("lstm_late", 1)
+        ctx.set_option("pdl", 1); ctx.set_option("overlap", 1); ctx.set_option("transit_n256", 1); ctx.set_option("lstm_late", 1); ctx.set_option("bn_prefetch", 1)
 
 
 def test_many_small_batches_match_serialised_launches(models, mode1):

@@ -3,6 +3,9 @@ ONE box compare two kernels).
 
     python tools/ab_bench.py ab/libcbx_base.so ab/libcbx_new.so [--rounds 3] [--steps 20] [--tags dense_bottleneck_gemm,...] [-- bench args]
 
+An arm may also be `lib@key=value,key=value` (library options passed as `--opt`), or just `@key=value` for the in-tree library:
+    python tools/ab_bench.py @bn_ctas=2 @bn_ctas=3
+
 Runs `bench.py --no-cpu-baseline --sustain 0` with CBX_LIB pointing at each library in turn, `rounds` times, and prints per run the
 step time, clips/s and the per-step time of the named kernel tags (the library's own CUDA-event profile)."""
 import json
@@ -29,12 +32,14 @@ def main():
         elif argv[i] == "--tags":
             tags = argv[i + 1].split(","); i += 2
         else:
-            libs.append(os.path.abspath(argv[i])); i += 1
+            libs.append(argv[i]); i += 1
     rows = {l: [] for l in libs}
     for r in range(rounds):
         for l in libs:
-            env = dict(os.environ, CBX_LIB=l)
-            out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu-baseline", "--sustain", "0", "--steps", str(steps), *extra],
+            path, _, opts = l.partition("@")
+            env = dict(os.environ, CBX_LIB=os.path.abspath(path)) if path else dict(os.environ)
+            optargs = [a for kv in opts.split(",") if kv for a in ("--opt", kv)]
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-cpu-baseline", "--sustain", "0", "--steps", str(steps), *optargs, *extra],
                                  env=env, capture_output=True, text=True)
             if out.returncode != 0:
                 print(f"{os.path.basename(l)} round {r}: FAILED\n{out.stderr[-2000:]}", flush=True)
