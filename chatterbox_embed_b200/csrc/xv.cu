@@ -75,7 +75,17 @@ __global__ void __launch_bounds__(kCmnStripes * kKMels) cmn_mean_kernel(const fl
   const ClipPlan cp = plan[blockIdx.x];
   const int col = threadIdx.x % kKMels, stripe = threadIdx.x / kKMels;
   float a = 0.f;
-  for (int t = stripe; t < cp.xv_frames; t += kCmnStripes) a += fbank[(size_t)(cp.fb_row + t) * kKMels + col];
+  const float* src = fbank + (size_t)cp.fb_row * kKMels + col;
+  int t = stripe;
+  // eight loads in flight per thread; the additions keep their order (same bits as the plain loop)
+  for (; t + 7 * kCmnStripes < cp.xv_frames; t += 8 * kCmnStripes) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = src[(size_t)(t + k * kCmnStripes) * kKMels];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += v[k];
+  }
+  for (; t < cp.xv_frames; t += kCmnStripes) a += src[(size_t)t * kKMels];
   part[stripe][col] = a;
   __syncthreads();
   if (stripe == 0) {
