@@ -1,7 +1,7 @@
 """Per-kernel SASS evidence of the Blackwell-native instructions in libcbx.so (runs anywhere cuobjdump is: no GPU needed).
     python tools/sass_summary.py [round tag]  ->  profiles/<tag>_sass_summary.md
 Counts, per kernel of the product library: UTC*MMA (tcgen05.mma), LDTM / STTM (tcgen05.ld / .st), UTMALDG / UTMASTG (TMA tensor
-load / store), UTMAPF / UBLKCP (bulk copies), SYNCS (mbarrier), HMMA / IMMA (legacy mma.sync: must be 0), plus registers."""
+load / store), UTMAPF (TMA L2 prefetch) / UBLKCP (bulk copies), SYNCS (mbarrier), HMMA / IMMA (legacy mma.sync: must be 0), plus registers."""
 import collections, os, re, subprocess, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
@@ -18,7 +18,7 @@ for ln in res.splitlines():
     if m and cur:
         regs[cur] = (int(m.group(1)), int(m.group(2)))
 pats = collections.OrderedDict([("UTC*MMA", r"\bUTC[A-Z]*MMA"), ("LDTM", r"\bLDTM"), ("STTM", r"\bSTTM"), ("UTMALDG", r"\bUTMALDG"),
-                                ("UTMASTG", r"\bUTMASTG"), ("UBLKCP", r"\bUBLKCP"), ("SYNCS", r"\bSYNCS"), ("HMMA/IMMA", r"\b[HI]MMA"),
+                                ("UTMASTG", r"\bUTMASTG"), ("UTMAPF", r"\bUTMAPF"), ("UBLKCP", r"\bUBLKCP"), ("SYNCS", r"\bSYNCS"), ("HMMA/IMMA", r"\b[HI]MMA"),
                                 ("MUFU", r"\bMUFU"), ("SHFL", r"\bSHFL"), ("REDUX", r"\bREDUX")])
 counts, order = {}, []
 cur = None
