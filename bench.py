@@ -214,13 +214,16 @@ def kernel_profile(ctx, step_fn, prof_steps, dev, rank, world, sync_all):
     tensor_peak = tf32["sustained"] if tf32 else pk["bf16_sus"] / 2.0
     tensor_src = "TF32 dense peak measured in this run (torch.matmul allow_tf32 8192^3, sustained)" if tf32 else "bf16 sustained / 2"
     ridge = tensor_peak * 1e12 / (pk["hbm"] * 1e9)          # FLOP per byte above which a kernel is tensor bound
-    traffic = None
+    traffic = traffic_launch = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram__bytes_read+write per launch from ncu --set full captures
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(tname, {}).get("dram_bytes_per_launch")
+        rec = json.load(open(tpath)).get(tname, {})
+        traffic, traffic_launch = rec.get("dram_bytes_per_launch"), rec.get("launch")
     secs = t["ms"] / 1e3
     common = {"kernel": tname, "share_of_step": t["ms"] / tot_ms, "avg_launch_ms": t["ms"] / t["launches"],
               "launches_per_step": t["launches"] / prof_steps, "traffic": traffic,
+              # which launch the ncu capture is (its own algorithmic bytes are in the note); `achieved` averages over all launches
+              "traffic_launch": traffic_launch, "algorithmic_bytes_per_launch_avg": (t["bytes"] / t["launches"]) if t["launches"] else None,
               "arithmetic_intensity_flop_per_byte": (t["flops"] / t["bytes"]) if t["bytes"] else None}
     if t["bytes"] > 0 and (t["flops"] == 0 or t["flops"] / t["bytes"] < ridge):
         achieved = t["bytes"] / secs / 1e9
