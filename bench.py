@@ -190,6 +190,8 @@ def kernel_profile(ctx, step_fn, prof_steps, dev, rank, world, sync_all):
     # ---- per-kernel device times (CUDA events on the launching stream), separate profiled steps ------------------
     # (the two encoder chains are serialised for this pass so that a kernel's events time that kernel alone)
     ctx.set_option("overlap", 0)
+    step_fn()                                  # one unrecorded step in the serialised configuration (warm-up of this launch order)
+    torch.cuda.synchronize()
     ctx.profile_enable(True)
     for _ in range(prof_steps):
         step_fn()
