@@ -60,15 +60,15 @@ CUtensorMap make_map_2d(const float* base, int64_t rows, int64_t cols, int64_t l
   return m;
 }
 
-CUtensorMap make_map_2d_plain(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+CUtensorMap make_map_2d_plain(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, bool bf16) {
   CUtensorMap m;
   std::memset(&m, 0, sizeof m);
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : sizeof(float))};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   EncodeTiledFn fn = encode_fn();
-  CUresult r = fn ? fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn ? fn(&m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
                   : CUDA_ERROR_NOT_FOUND;
   if (r != CUDA_SUCCESS) fprintf(stderr, "libcbx: cuTensorMapEncodeTiled (plain) failed (%d) rows=%lld cols=%lld ld=%lld\n", (int)r,

@@ -829,7 +829,7 @@ EncodeTiledFn encode_fn();
 
 // 2-D fp32 row-major [rows][cols] with leading dimension ld (floats); box = 32 columns x box_rows rows, 128B swizzle
 CUtensorMap make_map_2d(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool round_tf32);
-CUtensorMap make_map_2d_plain(const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows);   // no swizzle (L2 prefetch)
+CUtensorMap make_map_2d_plain(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows, bool bf16 = false);   // no swizzle (L2 prefetch)
 CUtensorMap make_map_2d_bf16(const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
 
 template <int BN, int STAGES, class Pro, class Epi>
@@ -872,12 +872,12 @@ inline void tgemm_bnrelu(Launches& L, cudaStream_t st, const char* tag, const vo
   Scope sc(L, st, tag, 2.0 * M * N * K, (XM ? 2.0 : 4.0) * (double)M * K + 4.0 * (double)M * N);
   CUtensorMap tmC = make_map_2d(C, M, N, ldc, BM, false);
   constexpr int KB = XM == 2 ? 64 : BK;
-  // option bn_prefetch (TF32 path): a plain tensor map of X, box = 128 columns x 128 rows, for the successor-tile L2 prefetch; the
+  // option bn_prefetch: a plain tensor map of X, box = 512 bytes of a row x 128 rows, for the successor-tile L2 prefetch; the
   // successor of a CTA in its slot is the row tile (CTA slots of the GPU) / (column tiles) further on (2 CTAs per SM)
   CUtensorMap tmX = tmC;
   int pf_stride = 0;
-  if (XM == 0 && L.bn_prefetch > 0 && K >= 128) {
-    tmX = make_map_2d_plain(static_cast<const float*>(X), M, K, lda, 128, BM);
+  if (L.bn_prefetch > 0 && K >= 128) {
+    tmX = make_map_2d_plain(X, M, K, lda, XM ? 256 : 128, BM, XM != 0);          // 512 bytes of every row either way: four (bf16 X: eight / four) K blocks
     pf_stride = (2 * sm_count() + (int)grid.x - 1) / (int)grid.x;
   }
   launch_pdl(kern, grid, dim3(320), SMEM, st, pdl, X, lda, M, K, bn_a, bn_b, tmB, tmC, (K + KB - 1) / KB, epi, tmX, pf_stride);
